@@ -1,0 +1,189 @@
+/*
+ * sightpy_b200.h — C ABI of the B200-native rendering backend for sightpy.
+ *
+ * The reference (lmondada/Python-Raytracer) has no FFI: its hot path is the Python call chain
+ *     Scene.render            sightpy/scene.py:71-140
+ *       -> Camera.get_ray     sightpy/camera.py:51-85
+ *       -> get_raycolor       sightpy/ray.py:122-148   (Collider.intersect, Material.get_color ...)
+ *       -> accumulate/tonemap sightpy/scene.py:100-140, sightpy/utils/colour_functions.py:4-18
+ * This header is the boundary a maintainer binds instead (ctypes stub in INTEGRATION.md): the
+ * scene is handed over once as plain-old-data records, then one blocking call renders a frame.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, non-zero on failure; sp_last_error() returns a
+ *     thread-local, NUL-terminated description of the last failure on the calling thread;
+ *   - the caller owns every host buffer it passes (C-contiguous); the library owns all device
+ *     memory and copies what it needs before returning;
+ *   - scene parameters are double precision (they are rounded to float32 on upload; hit points
+ *     that feed texel indexing are re-evaluated in double from these values);
+ *   - one sp_scene handle is bound to one CUDA device and must not be used from two threads
+ *     at once; there is NO CPU fallback: without a usable CUDA device sp_init fails.
+ */
+#ifndef SIGHTPY_B200_H
+#define SIGHTPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_ABI_VERSION 1
+
+/* ---- enums (mirrored in python-raytracer_b200/sightpy/flatten.py) ------------------------- */
+enum { SP_COLLIDER_SPHERE = 0, SP_COLLIDER_PLANE = 1, SP_COLLIDER_CUBOID = 2, SP_COLLIDER_TRIANGLE = 3 };
+enum { SP_MAT_GLOSSY = 0, SP_MAT_REFRACTIVE = 1, SP_MAT_THINFILM = 2, SP_MAT_DIFFUSE = 3,
+       SP_MAT_EMISSIVE = 4, SP_MAT_SKYBOX = 5 };
+enum { SP_LIGHT_DIRECTIONAL = 0, SP_LIGHT_POINT = 1 };
+enum { SP_DECODE_PLAIN = 0,   /* texel byte b -> b/256                    image_functions.py:7-9   */
+       SP_DECODE_LINEAR = 1 };/* texel byte b -> sRGB_to_linear(b/256)     image_functions.py:19-33 */
+
+#define SP_COLLIDER_PAYLOAD 40
+#define SP_MAX_DEPTH_LEVELS 64
+
+/* Camera basis as computed by Camera.__init__ (camera.py:8-49). */
+typedef struct sp_camera {
+    double look_from[3], right[3], up[3], fwd[3];
+    double cam_w, cam_h;            /* 2*tan(fov/2), cam_w/aspect                                */
+    double lens_radius, focal_distance;
+    int32_t width, height;          /* screen_width, screen_height                                */
+} sp_camera;
+
+/* One record per Material object (materials/*.py).  Texture ids index sp_scene_add_texture order;
+ * -1 = none / solid colour. */
+typedef struct sp_material {
+    int32_t kind;                   /* SP_MAT_*                                                   */
+    int32_t medium;                 /* Refractive: row of the media table; otherwise -1           */
+    int32_t normalmap_tex;          /* Material.normalmap (material.py:18-36)                     */
+    int32_t color_tex;              /* image texture of diff_color / color; SkyBox: environment   */
+    int32_t aux_tex0;               /* ThinFilm: reflectance LUT; SkyBox: lightmap                */
+    int32_t aux_tex1;               /* ThinFilm: thickness noise                                  */
+    int32_t diffuse_rays;           /* Diffuse (diffuse.py:13)                                    */
+    int32_t max_diffuse_reflections;
+    int32_t index_h, index_w;       /* SkyBox: shape used to index the lightmap (skybox.py:74-81) */
+    double normalmap_repeat, color_repeat;
+    double color[3];                /* solid colour                                               */
+    double n_re[3], n_im[3];        /* complex index of refraction (Glossy, Refractive)           */
+    double roughness, spec_coeff, diff_coeff;         /* Glossy                                   */
+    double thickness, noise_factor;                   /* ThinFilmInterference                     */
+    double ambient_weight;                            /* Diffuse: weight of the cosine pdf        */
+    double light_intensity;                           /* SkyBox                                   */
+} sp_material;
+
+/* One record per Primitive (geometry/primitive.py:6-14). */
+typedef struct sp_primitive {
+    int32_t material, max_ray_depth, shadow, mc;
+    int32_t uv_cross_layout;        /* Cuboid/SkyBox: uv = (u/4, v/3)  (cuboid.py:29-32)          */
+    int32_t _pad;
+    double center[3];
+    double bounded_sphere_radius;   /* used by spherical_caps_pdf (random.py:112-127)             */
+} sp_primitive;
+
+/* Tagged collider record; ORDER == scene.collider_list (the index is the "hit id").
+ * Payload slots p[]:
+ *   sphere   (sphere.py:21-24)    center 0-2, radius 3
+ *   plane    (plane.py:39-55)     center 0-2, u_axis 3-5, v_axis 6-8, normal 9-11, w 12, h 13,
+ *                                 uv_shift 14-15, inverse_basis_matrix 16-24 (row major)
+ *   cuboid   (cuboid.py:60-103)   center 0-2, ax_w 3-5, ax_h 6-8, ax_l 9-11, lb_local 12-14,
+ *                                 rt_local 15-17, (width,height,length) 18-20,
+ *                                 basis_matrix 21-29, inverse_basis_matrix 30-38 (row major)
+ *   triangle (triangle.py:20-35)  p1 0-2, p2 3-5, p3 6-8, normal 9-11, centroid 12-14,
+ *                                 n31 15-17, n12 18-20, n23 21-23
+ */
+typedef struct sp_collider {
+    int32_t type;                   /* SP_COLLIDER_*                                              */
+    int32_t primitive;
+    double p[SP_COLLIDER_PAYLOAD];
+} sp_collider;
+
+typedef struct sp_light {           /* lights.py:25-52 */
+    int32_t kind, _pad;
+    double vec[3];                  /* directional: unit vector towards the light; point: position */
+    double color[3];
+} sp_light;
+
+/* Counters of one sp_render / sp_trace call. "Rays" follows the reference's definition: one per
+ * element of every get_raycolor call (primary + secondary); shadow rays are counted apart. */
+typedef struct sp_stats {
+    uint64_t rays_total;
+    uint64_t shadow_rays;
+    uint64_t rays_per_depth[SP_MAX_DEPTH_LEVELS];
+    uint64_t kernel_launches;       /* launches of this library's own kernels                     */
+    uint64_t chunks;                /* wavefront chunks the frame was split into                  */
+    double   device_ms;             /* CUDA-event time of the device work                         */
+    double   level_kernel_ms;       /* of which: the fused trace+shade wavefront kernel           */
+    uint64_t level_kernel_launches;
+    uint64_t queue_bytes;           /* ray-record bytes written + read (algorithmic HBM traffic)  */
+} sp_stats;
+
+typedef struct sp_scene sp_scene;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int  sp_abi_version(void);
+/* sizeof() of the ABI structs, so that a binding can verify its own layout. */
+int  sp_abi_sizes(int32_t out[6]);  /* camera, material, primitive, collider, light, stats */
+int  sp_init(int device);           /* bind the calling process to a CUDA device (idempotent)     */
+int  sp_device_count(void);
+const char* sp_last_error(void);
+void sp_shutdown(void);
+
+int  sp_scene_create(sp_scene** out);
+void sp_scene_destroy(sp_scene*);
+
+/* ---- scene description (Scene.__init__/add/add_*Light/add_Background, scene.py:29-69) ---------- */
+int  sp_scene_set_globals(sp_scene*, const double ambient[3],
+                          const double* media_re, const double* media_im, int n_media);
+int  sp_scene_set_camera(sp_scene*, const sp_camera*);
+int  sp_scene_add_texture(sp_scene*, const uint8_t* rgb_hw3, int H, int W, int decode, int* tex_id);
+int  sp_scene_set_materials(sp_scene*, const sp_material*, int n);
+int  sp_scene_set_primitives(sp_scene*, const sp_primitive*, int n);
+int  sp_scene_set_colliders(sp_scene*, const sp_collider*, int n);
+int  sp_scene_set_lights(sp_scene*, const sp_light*, int n);
+int  sp_scene_set_importance(sp_scene*, const int32_t* primitive_ids, int n);
+int  sp_scene_set_shadow_colliders(sp_scene*, const int32_t* collider_ids, int n);
+int  sp_scene_commit(sp_scene*);    /* validate + upload; must precede any render call            */
+
+/* ---- rendering ----------------------------------------------------------------------------------
+ * sp_render == Scene.render (scene.py:71-140): spp jittered samples per pixel, average, sRGB
+ * tonemap, truncation to uint8.  out_linear_rgb (nullable) receives the averaged linear radiance
+ * as 3 planes of H*W floats (the layout of the reference's colour.to_array()); out_srgb8
+ * (nullable) receives H*W*3 interleaved bytes. */
+int  sp_render(sp_scene*, int spp, uint64_t seed, float* out_linear_rgb, uint8_t* out_srgb8,
+               sp_stats* stats);
+
+/* Sharded form used for multi-GPU rendering: accumulate samples [sample_begin, sample_end) of
+ * every pixel into the scene's device accumulation buffer (float4 per pixel, xyz = sum of
+ * radiance).  clear != 0 zeroes the buffer first.  The work is enqueued on the scene's stream and
+ * the call returns after it completed. */
+int  sp_render_samples(sp_scene*, int sample_begin, int sample_end, uint64_t seed, int clear,
+                       sp_stats* stats);
+void*    sp_accum_device_ptr(sp_scene*);      /* float4[H*W] on the scene's device                 */
+uint64_t sp_accum_bytes(sp_scene*);
+/* Resolve the accumulation buffer: divide by spp_total, tonemap, copy to the host buffers. */
+int  sp_resolve(sp_scene*, int spp_total, float* out_linear_rgb, uint8_t* out_srgb8);
+
+/* sp_trace == get_raycolor(Ray(o, d, depth 0, scene.n), scene) (ray.py:122-148) on caller rays:
+ * n rays, origins/directions as n x 3 interleaved floats.  Outputs (each nullable): linear
+ * radiance n x 3, index into collider_list of the nearest hit (-1 = none), hit distance. */
+int  sp_trace(sp_scene*, const float* origins, const float* dirs, int n, uint64_t seed,
+              float* out_rgb, int32_t* out_hit_id, float* out_t, sp_stats* stats);
+
+/* Primary rays of one sample as Camera.get_ray would build them (camera.py:51-85), n = W*H,
+ * row-major pixels, interleaved xyz. */
+int  sp_camera_rays(sp_scene*, int sample, uint64_t seed, float* out_origins, float* out_dirs);
+
+/* Nearest-hit distance of one jittered primary ray per pixel == ray.get_distances before its
+ * clip/normalise step (ray.py:151-163); misses are +inf. */
+int  sp_distances(sp_scene*, uint64_t seed, float* out_t);
+
+/* ---- tuning / measurement ---------------------------------------------------------------------- */
+/* options: "ray_queue_capacity", "fan_queue_capacity" (records), "chunk_primaries" (0 = auto) */
+int  sp_set_option(sp_scene*, const char* name, int64_t value);
+/* Roofline denominators measured on the bound device: dependent-free FFMA chains (TFLOP/s, 2 flop
+ * per FFMA) and a float4 copy (GB/s, read + write bytes). */
+int  sp_measure_peaks(double* fp32_tflops, double* copy_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGHTPY_B200_H */

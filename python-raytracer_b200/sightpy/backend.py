@@ -1,0 +1,235 @@
+"""ctypes binding of the C ABI declared in include/sightpy_b200.h.
+
+This is the *only* way the package renders: if ``libsightpy_b200.so`` is missing or no CUDA
+device can be bound, importing/using it raises — there is no CPU fallback.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+from .flatten import (CAMERA_DT, COLLIDER_DT, LIGHT_DT, MATERIAL_DT, PRIMITIVE_DT, FlatScene)
+
+__all__ = ["NativeScene", "load_library", "library_path", "Stats", "measure_peaks"]
+
+SP_MAX_DEPTH_LEVELS = 64
+_LIB = None
+_BOUND_DEVICE = None
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("rays_total", C.c_uint64), ("shadow_rays", C.c_uint64),
+        ("rays_per_depth", C.c_uint64 * SP_MAX_DEPTH_LEVELS),
+        ("kernel_launches", C.c_uint64), ("chunks", C.c_uint64),
+        ("device_ms", C.c_double), ("level_kernel_ms", C.c_double),
+        ("level_kernel_launches", C.c_uint64), ("queue_bytes", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        depth = [int(v) for v in self.rays_per_depth]
+        while depth and depth[-1] == 0:
+            depth.pop()
+        return dict(rays_total=int(self.rays_total), shadow_rays=int(self.shadow_rays),
+                    rays_per_depth=depth, kernel_launches=int(self.kernel_launches),
+                    chunks=int(self.chunks), device_ms=float(self.device_ms),
+                    level_kernel_ms=float(self.level_kernel_ms),
+                    level_kernel_launches=int(self.level_kernel_launches),
+                    queue_bytes=int(self.queue_bytes))
+
+
+def library_path():
+    override = os.environ.get("SIGHTPY_B200_LIB")
+    if override:
+        return Path(override)
+    return Path(__file__).resolve().parent.parent / "csrc" / "libsightpy_b200.so"
+
+
+def load_library():
+    """dlopen the CUDA library and declare its prototypes.  Raises if it was not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C python-raytracer_b200/csrc`). sightpy-b200 has no CPU fallback.")
+    lib = C.CDLL(str(path))
+    vp, i32, u64, f64p = C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_double)
+    proto = {
+        "sp_abi_version": (i32, []),
+        "sp_abi_sizes": (i32, [vp]),
+        "sp_init": (i32, [i32]),
+        "sp_device_count": (i32, []),
+        "sp_last_error": (C.c_char_p, []),
+        "sp_shutdown": (None, []),
+        "sp_scene_create": (i32, [C.POINTER(vp)]),
+        "sp_scene_destroy": (None, [vp]),
+        "sp_scene_set_globals": (i32, [vp, vp, vp, vp, i32]),
+        "sp_scene_set_camera": (i32, [vp, vp]),
+        "sp_scene_add_texture": (i32, [vp, vp, i32, i32, i32, C.POINTER(i32)]),
+        "sp_scene_set_materials": (i32, [vp, vp, i32]),
+        "sp_scene_set_primitives": (i32, [vp, vp, i32]),
+        "sp_scene_set_colliders": (i32, [vp, vp, i32]),
+        "sp_scene_set_lights": (i32, [vp, vp, i32]),
+        "sp_scene_set_importance": (i32, [vp, vp, i32]),
+        "sp_scene_set_shadow_colliders": (i32, [vp, vp, i32]),
+        "sp_scene_commit": (i32, [vp]),
+        "sp_render": (i32, [vp, i32, u64, vp, vp, C.POINTER(Stats)]),
+        "sp_render_samples": (i32, [vp, i32, i32, u64, i32, C.POINTER(Stats)]),
+        "sp_accum_device_ptr": (vp, [vp]),
+        "sp_accum_bytes": (u64, [vp]),
+        "sp_resolve": (i32, [vp, i32, vp, vp]),
+        "sp_trace": (i32, [vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(Stats)]),
+        "sp_camera_rays": (i32, [vp, i32, u64, vp, vp]),
+        "sp_distances": (i32, [vp, u64, vp]),
+        "sp_set_option": (i32, [vp, C.c_char_p, C.c_int64]),
+        "sp_measure_peaks": (i32, [f64p, f64p]),
+    }
+    for name, (res, args) in proto.items():
+        fn = getattr(lib, name)       # AttributeError here == header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    sizes = (C.c_int32 * 6)()
+    lib.sp_abi_sizes(sizes)
+    expect = [CAMERA_DT.itemsize, MATERIAL_DT.itemsize, PRIMITIVE_DT.itemsize,
+              COLLIDER_DT.itemsize, LIGHT_DT.itemsize, C.sizeof(Stats)]
+    if list(sizes) != expect:
+        raise RuntimeError(f"ABI struct size mismatch: library {list(sizes)} vs binding {expect}")
+    _LIB = lib
+    return lib
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        msg = lib.sp_last_error()
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else 'unknown error'}")
+
+
+def default_device():
+    for var in ("SIGHTPY_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(var, "") != "":
+            return int(os.environ[var])
+    return 0
+
+
+def bind_device(device=None):
+    global _BOUND_DEVICE
+    lib = load_library()
+    device = default_device() if device is None else int(device)
+    if _BOUND_DEVICE != device:
+        _check(lib, lib.sp_init(device), f"sp_init({device})")
+        _BOUND_DEVICE = device
+    return lib
+
+
+def measure_peaks(device=None):
+    lib = bind_device(device)
+    a, b = C.c_double(), C.c_double()
+    _check(lib, lib.sp_measure_peaks(C.byref(a), C.byref(b)), "sp_measure_peaks")
+    return dict(fp32_tflops=a.value, copy_gbs=b.value)
+
+
+def _ptr(arr):
+    return arr.ctypes.data_as(C.c_void_p) if arr is not None else None
+
+
+class NativeScene:
+    """A committed scene living on one GPU."""
+
+    def __init__(self, flat: FlatScene, device=None):
+        self.lib = bind_device(device)
+        self.flat = flat
+        self.width = int(flat.camera["width"])
+        self.height = int(flat.camera["height"])
+        self.handle = C.c_void_p()
+        _check(self.lib, self.lib.sp_scene_create(C.byref(self.handle)), "sp_scene_create")
+        try:
+            self._upload(flat)
+        except Exception:
+            self.close()
+            raise
+
+    def _upload(self, flat):
+        lib, h = self.lib, self.handle
+        amb = np.ascontiguousarray(flat.ambient, dtype=np.float64)
+        mre = np.ascontiguousarray(flat.media.real, dtype=np.float64)
+        mim = np.ascontiguousarray(flat.media.imag, dtype=np.float64)
+        _check(lib, lib.sp_scene_set_globals(h, _ptr(amb), _ptr(mre), _ptr(mim), len(flat.media)), "set_globals")
+        cam = np.ascontiguousarray(flat.camera.reshape(1))
+        _check(lib, lib.sp_scene_set_camera(h, _ptr(cam)), "set_camera")
+        for t in flat.textures:
+            tid = C.c_int(-1)
+            u8 = np.ascontiguousarray(t.u8)
+            _check(lib, lib.sp_scene_add_texture(h, _ptr(u8), u8.shape[0], u8.shape[1], t.decode, C.byref(tid)),
+                   "add_texture")
+        for name, fn in (("materials", lib.sp_scene_set_materials), ("primitives", lib.sp_scene_set_primitives),
+                         ("colliders", lib.sp_scene_set_colliders), ("lights", lib.sp_scene_set_lights),
+                         ("importance", lib.sp_scene_set_importance),
+                         ("shadow_colliders", lib.sp_scene_set_shadow_colliders)):
+            arr = np.ascontiguousarray(getattr(flat, name))
+            _check(lib, fn(h, _ptr(arr), len(arr)), "set_" + name)
+        _check(lib, lib.sp_scene_commit(h), "sp_scene_commit")
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.sp_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    __del__ = close
+
+    def set_option(self, name, value):
+        _check(self.lib, self.lib.sp_set_option(self.handle, name.encode(), int(value)), f"set_option({name})")
+
+    def render(self, spp, seed=0, want_linear=True):
+        """Full frame on this GPU -> (uint8 H x W x 3, float32 3 x H x W linear or None, stats)."""
+        srgb = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        lin = np.empty((3, self.height, self.width), dtype=np.float32) if want_linear else None
+        st = Stats()
+        _check(self.lib, self.lib.sp_render(self.handle, int(spp), int(seed), _ptr(lin), _ptr(srgb), C.byref(st)),
+               "sp_render")
+        return srgb, lin, st.as_dict()
+
+    def render_samples(self, sample_begin, sample_end, seed=0, clear=True):
+        st = Stats()
+        _check(self.lib, self.lib.sp_render_samples(self.handle, int(sample_begin), int(sample_end), int(seed),
+                                                    int(bool(clear)), C.byref(st)), "sp_render_samples")
+        return st.as_dict()
+
+    def accum_pointer(self):
+        return int(self.lib.sp_accum_device_ptr(self.handle)), int(self.lib.sp_accum_bytes(self.handle))
+
+    def resolve(self, spp_total, want_linear=True):
+        srgb = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        lin = np.empty((3, self.height, self.width), dtype=np.float32) if want_linear else None
+        _check(self.lib, self.lib.sp_resolve(self.handle, int(spp_total), _ptr(lin), _ptr(srgb)), "sp_resolve")
+        return srgb, lin
+
+    def trace(self, origins, dirs, seed=0, want_rgb=True):
+        o = np.ascontiguousarray(origins, dtype=np.float32)
+        d = np.ascontiguousarray(dirs, dtype=np.float32)
+        if o.shape != d.shape or o.ndim != 2 or o.shape[1] != 3:
+            raise ValueError("origins/dirs must both be (n, 3)")
+        n = o.shape[0]
+        rgb = np.empty((n, 3), dtype=np.float32) if want_rgb else None
+        hit = np.empty(n, dtype=np.int32)
+        t = np.empty(n, dtype=np.float32)
+        st = Stats()
+        _check(self.lib, self.lib.sp_trace(self.handle, _ptr(o), _ptr(d), n, int(seed), _ptr(rgb), _ptr(hit),
+                                           _ptr(t), C.byref(st)), "sp_trace")
+        return dict(rgb=rgb, hit_id=hit, t=t, stats=st.as_dict())
+
+    def camera_rays(self, sample=0, seed=0):
+        n = self.width * self.height
+        o = np.empty((n, 3), dtype=np.float32)
+        d = np.empty((n, 3), dtype=np.float32)
+        _check(self.lib, self.lib.sp_camera_rays(self.handle, int(sample), int(seed), _ptr(o), _ptr(d)),
+               "sp_camera_rays")
+        return o, d
+
+    def distances(self, seed=0):
+        t = np.empty(self.width * self.height, dtype=np.float32)
+        _check(self.lib, self.lib.sp_distances(self.handle, int(seed), _ptr(t)), "sp_distances")
+        return t

@@ -1,0 +1,64 @@
+"""Frame-level sharding across the GPUs of one node.
+
+Pixels and samples are independent, so the only exchange is the final image: rank r of R renders
+the contiguous sample range [r*spp/R, (r+1)*spp/R) of the whole frame into its own float4
+accumulation buffer; the buffers are summed onto rank 0 with one NCCL ``reduce`` over NVLink
+(33 MB at 1080p) and rank 0 tonemaps.  The counter-based RNG is keyed by the *global* sample
+index, so the union of the shards is the same set of light paths as a single-GPU render.
+Replaces the multiprocessing.Pool fan-out of the reference (sightpy/scene.py:78-116).
+"""
+import os
+
+import numpy as np
+
+__all__ = ["sample_range", "world", "render_frame", "accum_as_tensor"]
+
+
+def sample_range(spp, rank, world_size):
+    """Contiguous, balanced split of range(spp); ranks beyond spp get an empty range."""
+    base, extra = divmod(int(spp), int(world_size))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def world():
+    """(rank, world_size) of an initialised torch.distributed job, else (0, 1)."""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return 0, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+class _CudaBlob:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {
+            "shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": None}
+
+
+def accum_as_tensor(native):
+    """torch.float32 view (no copy) of the scene's device accumulation buffer."""
+    import torch
+    ptr, nbytes = native.accum_pointer()
+    return torch.as_tensor(_CudaBlob(ptr, nbytes // 4), device=torch.device("cuda", torch.cuda.current_device()))
+
+
+def render_frame(native, spp, seed=0, want_linear=False):
+    """Render one frame with every rank of the job.  Returns (uint8 H x W x 3, stats) — on ranks
+    other than 0 the image is the rank-local (unreduced) resolve and only rank 0's is the frame."""
+    rank, size = world()
+    if size == 1:
+        srgb, lin, stats = native.render(spp, seed, want_linear=want_linear)
+        return (srgb, stats) if not want_linear else (srgb, lin, stats)
+    import torch.distributed as dist
+    begin, end = sample_range(spp, rank, size)
+    stats = native.render_samples(begin, end, seed, clear=True)
+    acc = accum_as_tensor(native)
+    dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+    import torch
+    torch.cuda.synchronize()
+    srgb, lin = native.resolve(spp, want_linear=want_linear)
+    return (srgb, stats) if not want_linear else (srgb, lin, stats)
