@@ -49,7 +49,7 @@ typedef struct sp_camera {
     int32_t width, height;          /* screen_width, screen_height                                */
 } sp_camera;
 
-/* One record per Material object (materials/*.py).  Texture ids index sp_scene_add_texture order;
+/* One record per Material object (materials/ *.py).  Texture ids index sp_scene_add_texture order;
  * -1 = none / solid colour. */
 typedef struct sp_material {
     int32_t kind;                   /* SP_MAT_*                                                   */
@@ -114,6 +114,9 @@ typedef struct sp_stats {
     double   level_kernel_ms;       /* of which: the fused trace+shade wavefront kernel           */
     uint64_t level_kernel_launches;
     uint64_t queue_bytes;           /* ray-record bytes written + read (algorithmic HBM traffic)  */
+    double   level_ms[SP_MAX_DEPTH_LEVELS];   /* level kernel time per recursion depth            */
+    uint64_t peak_ray_records;      /* largest per-level queue occupancy seen (records)           */
+    uint64_t peak_fan_records;
 } sp_stats;
 
 typedef struct sp_scene sp_scene;
@@ -177,7 +180,8 @@ int  sp_camera_rays(sp_scene*, int sample, uint64_t seed, float* out_origins, fl
 int  sp_distances(sp_scene*, uint64_t seed, float* out_t);
 
 /* ---- tuning / measurement ---------------------------------------------------------------------- */
-/* options: "ray_queue_capacity", "fan_queue_capacity" (records), "chunk_primaries" (0 = auto) */
+/* options: "ray_queue_capacity", "fan_queue_capacity" (records), "chunk_primaries" (0 = auto),
+ * "max_levels" (debugging: trace only the first k recursion depths, 0 = all) */
 int  sp_set_option(sp_scene*, const char* name, int64_t value);
 /* Roofline denominators measured on the bound device: dependent-free FFMA chains (TFLOP/s, 2 flop
  * per FFMA) and a float4 copy (GB/s, read + write bytes). */

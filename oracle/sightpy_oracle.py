@@ -158,6 +158,7 @@ class Oracle:
         self._tex = {}
         self.rays_per_depth = {}
         self.shadow_rays = 0
+        self.max_levels = 0          # debugging aid: rays of depth >= max_levels return black (0 = off)
         C = flat.colliders
         self.ctype = [int(t) for t in C["type"]]
         self.cprim = [int(p) for p in C["primitive"]]
@@ -363,6 +364,8 @@ class Oracle:
     # =============================================================================================
     def radiance(self, b: Bundle, want_hits=False):
         n = len(b)
+        if self.max_levels and b.depth >= self.max_levels and not want_hits:
+            return np.zeros((3, n))
         self.rays_per_depth[b.depth] = self.rays_per_depth.get(b.depth, 0) + n
         inters = [self.intersect(ci, b.O, b.D) for ci in range(len(self.ctype))]
         nearest = inters[0][0]
@@ -631,10 +634,19 @@ class Oracle:
         color, hit, t = self.radiance(b, want_hits=True)
         return dict(rgb=color.T.copy(), hit_id=hit, t=t)
 
-    def trace(self, origins, dirs, pix=None, sample=0):
-        """Same with (N, 3) arrays (the sp_trace layout) -> dict(rgb (N,3), hit_id (N,), t (N,))."""
+    def trace(self, origins, dirs, pix=None, sample=0, renormalize=True):
+        """Same with (N, 3) arrays (the sp_trace layout) -> dict(rgb (N,3), hit_id (N,), t (N,)).
+
+        Directions are renormalised in float64 first.  The reference only ever traces exactly
+        normalised directions (camera.py:85) and its hit points are ``O + D * |D t|``
+        (plane.py:66-67), so a float32-rounded direction (|D| = 1 +- 3e-8) would move every hit
+        point by t * 3e-8 along the ray — more than the 1e-6 origin nudge of its secondary rays
+        once t > 30, which makes children start *behind* the surface they leave.  That is an
+        artefact of handing float32 test rays to float64 code, not reference behaviour."""
         O = np.ascontiguousarray(np.asarray(origins, dtype=np.float64).T)
         D = np.ascontiguousarray(np.asarray(dirs, dtype=np.float64).T)
+        if renormalize:
+            D = D / np.sqrt(dot(D, D))
         return self.trace_columns(O, D, pix, sample)
 
     def render_linear(self, spp, sample_begin=0):

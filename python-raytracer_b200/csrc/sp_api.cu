@@ -1,0 +1,853 @@
+// C ABI of the sightpy B200 backend (include/sightpy_b200.h): scene assembly, device residency,
+// the chunked wavefront driver and frame resolve.  Host-only code; the kernels live in
+// sp_kernels.cu.  Replaces the body of Scene.render (sightpy/scene.py:71-140) and the
+// multiprocessing fan-out underneath it.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sp_launch.h"
+
+// ---- error handling -------------------------------------------------------------------------------
+static thread_local std::string g_error;
+static int g_device = -1;
+
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return 1;
+}
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) return fail("%s: %s", #expr, cudaGetErrorString(e__));            \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& h) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct HostTexture { int H, W, decode; std::vector<uint32_t> texels; };
+
+struct QueueSet {
+    DevBuf<float4> q0, q1, q2;
+    RayQueue view(uint32_t cap) { RayQueue q; q.q0 = q0.p; q.q1 = q1.p; q.q2 = q2.p; q.capacity = cap; return q; }
+    cudaError_t alloc(size_t n) {
+        cudaError_t e;
+        if ((e = q0.alloc(n)) != cudaSuccess) return e;
+        if ((e = q1.alloc(n)) != cudaSuccess) return e;
+        return q2.alloc(n);
+    }
+    void release() { q0.release(); q1.release(); q2.release(); }
+};
+
+struct sp_scene {
+    // ---- host description ---------------------------------------------------------------------
+    double ambient[3] = {0, 0, 0};
+    std::vector<double> media_re, media_im;
+    sp_camera cam{};
+    bool has_camera = false, committed = false;
+    std::vector<HostTexture> textures;
+    std::vector<sp_material> mats;
+    std::vector<sp_primitive> prims;
+    std::vector<sp_collider> cols;
+    std::vector<sp_light> lights;
+    std::vector<int32_t> importance, shadow_ids;
+    // ---- options ------------------------------------------------------------------------------------
+    int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0;
+    // ---- device residency -----------------------------------------------------------------------------
+    DScene d{};
+    int n_levels = 1;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events;
+    DevBuf<float4> geom_all, geom_shadow, accum;
+    DevBuf<int> off_all, off_shadow;
+    DevBuf<int2> slot_all, slot_shadow;
+    DevBuf<DCollider> d_cols;
+    DevBuf<double> d_cols_d;
+    DevBuf<DPrimitive> d_prims;
+    DevBuf<DMaterial> d_mats;
+    DevBuf<DTexture> d_texdesc;
+    std::vector<DevBuf<uint32_t>> d_texels;
+    DevBuf<DMedium> d_media;
+    DevBuf<uint32_t> counts;
+    DevBuf<DeviceStats> d_stats;
+    QueueSet ray_q[2], fan_q[2];
+    uint32_t ray_cap = 0, fan_cap = 0;
+    uint32_t chunk_primaries = 0;
+    double use_ray = 0.0, use_fan = 0.0;         // peak records per primary seen so far
+    int grid = 0;
+
+    ~sp_scene() { release_device(); }
+    void release_device() {
+        for (auto& b : d_texels) b.release();
+        d_texels.clear();
+        geom_all.release(); geom_shadow.release(); accum.release(); off_all.release(); off_shadow.release();
+        slot_all.release(); slot_shadow.release(); d_cols.release(); d_cols_d.release(); d_prims.release();
+        d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
+        for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
+        for (auto e : events) cudaEventDestroy(e);
+        events.clear();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+        ray_cap = fan_cap = 0;
+    }
+};
+
+static float3 f3(const double* v) { return make_float3((float)v[0], (float)v[1], (float)v[2]); }
+
+// ---- geometry stream construction (layout documented in sp_types.cuh) ------------------------------
+static int type_vec4(int t) {
+    return t == SP_COLLIDER_SPHERE ? SP_V4_SPHERE : t == SP_COLLIDER_PLANE ? SP_V4_PLANE
+         : t == SP_COLLIDER_CUBOID ? SP_V4_CUBOID : SP_V4_TRIANGLE;
+}
+
+static void pack_collider(const sp_collider& c, float* out) {
+    const double* p = c.p;
+    auto put3 = [&](int at, double x, double y, double z) { out[at] = (float)x; out[at + 1] = (float)y; out[at + 2] = (float)z; };
+    switch (c.type) {
+    case SP_COLLIDER_SPHERE:
+        put3(0, p[0], p[1], p[2]); out[3] = (float)(p[3] * p[3]);
+        break;
+    case SP_COLLIDER_PLANE:
+        put3(0, p[9], p[10], p[11]);  out[3] = (float)p[12];        // N, w
+        put3(4, p[0], p[1], p[2]);    out[7] = (float)p[13];        // C, h
+        put3(8, p[3], p[4], p[5]);    out[11] = 0.f;                // U
+        put3(12, p[6], p[7], p[8]);   out[15] = 0.f;                // V
+        break;
+    case SP_COLLIDER_CUBOID: {
+        const double* B = p + 21;
+        double bc[3], lo[3], hi[3];
+        for (int r = 0; r < 3; ++r) {
+            bc[r] = B[3 * r] * p[0] + B[3 * r + 1] * p[1] + B[3 * r + 2] * p[2];
+            lo[r] = p[12 + r] - bc[r];
+            hi[r] = p[15 + r] - bc[r];
+        }
+        put3(0, B[0], B[1], B[2]);  out[3] = (float)lo[0];
+        put3(4, B[3], B[4], B[5]);  out[7] = (float)lo[1];
+        put3(8, B[6], B[7], B[8]);  out[11] = (float)lo[2];
+        put3(12, p[0], p[1], p[2]); out[15] = (float)hi[0];
+        out[16] = (float)hi[1]; out[17] = (float)hi[2]; out[18] = 0.f; out[19] = 0.f;
+        break;
+    }
+    default:   // triangle: N, centroid, n31, p1, n12, p2, n23, p3
+        put3(0, p[9], p[10], p[11]);  put3(3, p[12], p[13], p[14]);
+        put3(6, p[15], p[16], p[17]); put3(9, p[0], p[1], p[2]);
+        put3(12, p[18], p[19], p[20]); put3(15, p[3], p[4], p[5]);
+        put3(18, p[21], p[22], p[23]); put3(21, p[6], p[7], p[8]);
+        break;
+    }
+}
+
+struct BuiltStream {
+    std::vector<float4> data;
+    std::vector<int> chunk_off;
+    std::vector<int2> slot;          // per collider id of the scene
+    int n_items = 0;
+};
+
+static BuiltStream build_stream(const std::vector<sp_collider>& cols, std::vector<int32_t> ids) {
+    BuiltStream bs;
+    bs.slot.assign(cols.size(), make_int2(-1, -1));
+    bs.n_items = (int)ids.size();
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return cols[a].type < cols[b].type; });
+    bs.chunk_off.push_back(0);
+    size_t pos = 0;
+    while (pos < ids.size()) {
+        // greedy fill of one chunk
+        int cnt[4] = {0, 0, 0, 0}, vec4 = 4;
+        size_t end = pos;
+        while (end < ids.size()) {
+            const int t = cols[ids[end]].type;
+            const int items = (int)(end - pos) + 1;
+            const int need = vec4 + type_vec4(t) + (items + 3) / 4;
+            if (need > SP_CHUNK_VEC4) break;
+            vec4 += type_vec4(t);
+            cnt[t]++;
+            ++end;
+        }
+        const int items = (int)(end - pos);
+        GeomChunkHeader h{};
+        h.n_sphere = cnt[0]; h.n_plane = cnt[1]; h.n_cuboid = cnt[2]; h.n_tri = cnt[3];
+        h.off_sphere = 4;
+        h.off_plane = h.off_sphere + cnt[0] * SP_V4_SPHERE;
+        h.off_cuboid = h.off_plane + cnt[1] * SP_V4_PLANE;
+        h.off_tri = h.off_cuboid + cnt[2] * SP_V4_CUBOID;
+        h.off_ids = h.off_tri + cnt[3] * SP_V4_TRIANGLE;
+        h.n_vec4 = h.off_ids + (items + 3) / 4;
+        std::vector<float4> chunk((size_t)h.n_vec4, make_float4(0, 0, 0, 0));
+        memcpy(chunk.data(), &h, sizeof h);
+        float* fl = reinterpret_cast<float*>(chunk.data());
+        int* idp = reinterpret_cast<int*>(chunk.data() + h.off_ids);
+        int at = 4 * 4, local[4] = {0, 0, 0, 0};
+        const int chunk_index = (int)bs.chunk_off.size() - 1;
+        for (size_t k = pos; k < end; ++k) {
+            const sp_collider& c = cols[ids[k]];
+            pack_collider(c, fl + at);
+            at += 4 * type_vec4(c.type);
+            idp[k - pos] = ids[k];
+            bs.slot[ids[k]] = make_int2(chunk_index, (c.type << 28) | local[c.type]);
+            local[c.type]++;
+        }
+        bs.data.insert(bs.data.end(), chunk.begin(), chunk.end());
+        bs.chunk_off.push_back((int)bs.data.size());
+        pos = end;
+    }
+    if (ids.empty()) {                       // an empty stream still has one (empty) chunk
+        GeomChunkHeader h{};
+        h.off_sphere = h.off_plane = h.off_cuboid = h.off_tri = h.off_ids = h.n_vec4 = 4;
+        std::vector<float4> chunk(4, make_float4(0, 0, 0, 0));
+        memcpy(chunk.data(), &h, sizeof h);
+        bs.data = chunk;
+        bs.chunk_off.push_back(4);
+    }
+    return bs;
+}
+
+// =================================================================================================
+// lifetime
+// =================================================================================================
+extern "C" {
+
+int sp_abi_version(void) { return SP_ABI_VERSION; }
+
+int sp_abi_sizes(int32_t out[6]) {
+    out[0] = (int32_t)sizeof(sp_camera);   out[1] = (int32_t)sizeof(sp_material);
+    out[2] = (int32_t)sizeof(sp_primitive); out[3] = (int32_t)sizeof(sp_collider);
+    out[4] = (int32_t)sizeof(sp_light);    out[5] = (int32_t)sizeof(sp_stats);
+    return 0;
+}
+
+const char* sp_last_error(void) { return g_error.c_str(); }
+
+int sp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sp_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail("no CUDA device available (%s); sightpy-b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail("device %d out of range (0..%d)", device, n - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail("device %d is %s (sm_%d%d); this library is built for sm_100a (B200) only", device, prop.name,
+                    prop.major, prop.minor);
+    float plain[256], linear[256];
+    for (int b = 0; b < 256; ++b) {
+        const double x = b / 256.0;                                   // image_functions.py:7-9
+        plain[b] = (float)x;                                          // colour_functions.py:21-28
+        linear[b] = (float)(x <= 0.03928 ? x / 12.92 : std::pow((x + 0.055) / 1.055, 2.4));
+    }
+    CUDA_TRY(sp_upload_decode_tables(plain, linear));
+    g_device = device;
+    return 0;
+}
+
+void sp_shutdown(void) {
+    if (g_device >= 0) cudaDeviceSynchronize();
+    g_device = -1;
+}
+
+int sp_scene_create(sp_scene** out) {
+    if (!out) return fail("sp_scene_create: null output pointer");
+    if (g_device < 0) return fail("sp_scene_create: call sp_init first");
+    *out = new sp_scene();
+    return 0;
+}
+
+void sp_scene_destroy(sp_scene* s) { delete s; }
+
+// =================================================================================================
+// scene description
+// =================================================================================================
+#define NEED_SCENE(s) do { if (!(s)) return fail("%s: null scene", __func__); (s)->committed = false; } while (0)
+
+int sp_scene_set_globals(sp_scene* s, const double ambient[3], const double* media_re, const double* media_im,
+                         int n_media) {
+    NEED_SCENE(s);
+    if (n_media < 1 || n_media > 255) return fail("sp_scene_set_globals: need 1..255 media (row 0 = scene.n)");
+    memcpy(s->ambient, ambient, sizeof s->ambient);
+    s->media_re.assign(media_re, media_re + 3 * (size_t)n_media);
+    s->media_im.assign(media_im, media_im + 3 * (size_t)n_media);
+    return 0;
+}
+
+int sp_scene_set_camera(sp_scene* s, const sp_camera* cam) {
+    NEED_SCENE(s);
+    if (!cam || cam->width < 1 || cam->height < 1) return fail("sp_scene_set_camera: invalid camera");
+    if ((uint64_t)cam->width * (uint64_t)cam->height > 0x7FFFFFFFull) return fail("sp_scene_set_camera: frame too large");
+    s->cam = *cam;
+    s->has_camera = true;
+    return 0;
+}
+
+int sp_scene_add_texture(sp_scene* s, const uint8_t* rgb, int H, int W, int decode, int* tex_id) {
+    NEED_SCENE(s);
+    if (!rgb || H < 1 || W < 1) return fail("sp_scene_add_texture: invalid image");
+    if (decode != SP_DECODE_PLAIN && decode != SP_DECODE_LINEAR) return fail("sp_scene_add_texture: unknown decode %d", decode);
+    HostTexture t;
+    t.H = H; t.W = W; t.decode = decode;
+    t.texels.resize((size_t)H * W);
+    for (size_t i = 0; i < t.texels.size(); ++i)
+        t.texels[i] = (uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16);
+    s->textures.push_back(std::move(t));
+    if (tex_id) *tex_id = (int)s->textures.size() - 1;
+    return 0;
+}
+
+int sp_scene_set_materials(sp_scene* s, const sp_material* m, int n) {
+    NEED_SCENE(s);
+    if (n < 0 || (n > 0 && !m)) return fail("sp_scene_set_materials: invalid arguments");
+    s->mats.assign(m, m + n);
+    return 0;
+}
+
+int sp_scene_set_primitives(sp_scene* s, const sp_primitive* p, int n) {
+    NEED_SCENE(s);
+    if (n < 0 || (n > 0 && !p)) return fail("sp_scene_set_primitives: invalid arguments");
+    s->prims.assign(p, p + n);
+    return 0;
+}
+
+int sp_scene_set_colliders(sp_scene* s, const sp_collider* c, int n) {
+    NEED_SCENE(s);
+    if (n < 0 || (n > 0 && !c)) return fail("sp_scene_set_colliders: invalid arguments");
+    if (n > 16382) return fail("sp_scene_set_colliders: at most 16382 colliders (ray records carry a 14-bit source id)");
+    s->cols.assign(c, c + n);
+    return 0;
+}
+
+int sp_scene_set_lights(sp_scene* s, const sp_light* l, int n) {
+    NEED_SCENE(s);
+    if (n < 0 || (n > 0 && !l)) return fail("sp_scene_set_lights: invalid arguments");
+    if (n > SP_MAX_LIGHTS) return fail("sp_scene_set_lights: at most %d lights", SP_MAX_LIGHTS);
+    s->lights.assign(l, l + n);
+    return 0;
+}
+
+int sp_scene_set_importance(sp_scene* s, const int32_t* ids, int n) {
+    NEED_SCENE(s);
+    if (n < 0 || (n > 0 && !ids)) return fail("sp_scene_set_importance: invalid arguments");
+    if (n > SP_MAX_IMPORTANCE) return fail("sp_scene_set_importance: at most %d importance-sampled primitives", SP_MAX_IMPORTANCE);
+    s->importance.assign(ids, ids + n);
+    return 0;
+}
+
+int sp_scene_set_shadow_colliders(sp_scene* s, const int32_t* ids, int n) {
+    NEED_SCENE(s);
+    if (n < 0 || (n > 0 && !ids)) return fail("sp_scene_set_shadow_colliders: invalid arguments");
+    s->shadow_ids.assign(ids, ids + n);
+    return 0;
+}
+
+int sp_scene_commit(sp_scene* s) {
+    if (!s) return fail("sp_scene_commit: null scene");
+    if (g_device < 0) return fail("sp_scene_commit: call sp_init first");
+    if (s->media_re.empty()) return fail("sp_scene_commit: sp_scene_set_globals was not called");
+    const int n_tex = (int)s->textures.size(), n_mat = (int)s->mats.size(), n_prim = (int)s->prims.size();
+    const int n_col = (int)s->cols.size(), n_media = (int)s->media_re.size() / 3;
+
+    // ---- validation -----------------------------------------------------------------------------
+    auto tex_ok = [&](int id) { return id >= -1 && id < n_tex; };
+    for (int i = 0; i < n_mat; ++i) {
+        const sp_material& m = s->mats[i];
+        if (m.kind < SP_MAT_GLOSSY || m.kind > SP_MAT_SKYBOX) return fail("material %d: unknown kind %d", i, m.kind);
+        if (!tex_ok(m.normalmap_tex) || !tex_ok(m.color_tex) || !tex_ok(m.aux_tex0) || !tex_ok(m.aux_tex1))
+            return fail("material %d: texture id out of range", i);
+        if (m.kind == SP_MAT_REFRACTIVE && (m.medium < 0 || m.medium >= n_media)) return fail("material %d: medium out of range", i);
+        if (m.kind == SP_MAT_THINFILM && (m.aux_tex0 < 0 || (m.noise_factor != 0.0 && m.aux_tex1 < 0)))
+            return fail("material %d: thin film needs its reflectance LUT (and noise) texture", i);
+        if (m.kind == SP_MAT_SKYBOX && (m.color_tex < 0 || (m.light_intensity != 0.0 && m.aux_tex0 < 0)))
+            return fail("material %d: sky box needs its environment (and light map) texture", i);
+        if (m.kind == SP_MAT_DIFFUSE && (m.diffuse_rays < 1 || m.diffuse_rays > 4096 || m.max_diffuse_reflections < 0 ||
+                                         m.max_diffuse_reflections > 3))
+            return fail("material %d: diffuse_rays must be 1..4096 and max_diffuse_reflections 0..3", i);
+    }
+    for (int i = 0; i < n_prim; ++i) {
+        if (s->prims[i].material < 0 || s->prims[i].material >= n_mat) return fail("primitive %d: material out of range", i);
+        if (s->prims[i].max_ray_depth < 0 || s->prims[i].max_ray_depth > 40) return fail("primitive %d: max_ray_depth must be 0..40", i);
+    }
+    for (int i = 0; i < n_col; ++i) {
+        const sp_collider& c = s->cols[i];
+        if (c.type < SP_COLLIDER_SPHERE || c.type > SP_COLLIDER_TRIANGLE) return fail("collider %d: unknown type %d", i, c.type);
+        if (c.primitive < 0 || c.primitive >= n_prim) return fail("collider %d: primitive out of range", i);
+        const sp_material& m = s->mats[s->prims[c.primitive].material];
+        const bool uses_uv = (m.color_tex >= 0 && m.kind != SP_MAT_SKYBOX) || m.normalmap_tex >= 0 ||
+                             m.kind == SP_MAT_THINFILM || m.kind == SP_MAT_SKYBOX;
+        if (c.type == SP_COLLIDER_TRIANGLE && uses_uv) return fail("collider %d: triangles have no uv mapping (triangle.py:79-83)", i);
+        if (m.normalmap_tex >= 0 && c.type != SP_COLLIDER_PLANE && c.type != SP_COLLIDER_CUBOID)
+            return fail("collider %d: normal maps need a plane or cuboid tangent frame (material.py:32)", i);
+    }
+    for (int id : s->importance) if (id < 0 || id >= n_prim) return fail("importance list: primitive %d out of range", id);
+    for (int id : s->shadow_ids) if (id < 0 || id >= n_col) return fail("shadow list: collider %d out of range", id);
+
+    s->release_device();
+    CUDA_TRY(cudaSetDevice(g_device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    DScene& d = s->d;
+    memset(&d, 0, sizeof d);
+
+    // ---- materials, fan classes --------------------------------------------------------------------
+    d.n_fan_classes = 1;
+    d.fan_mult[0] = 1;
+    std::vector<DMaterial> dm((size_t)n_mat);
+    int max_dr = 0;
+    for (int i = 0; i < n_mat; ++i) {
+        const sp_material& m = s->mats[i];
+        DMaterial& o = dm[i];
+        memset(&o, 0, sizeof o);
+        o.kind = m.kind; o.medium = m.medium; o.normalmap_tex = m.normalmap_tex; o.color_tex = m.color_tex;
+        o.aux_tex0 = m.aux_tex0; o.aux_tex1 = m.aux_tex1; o.diffuse_rays = m.diffuse_rays;
+        o.max_dr = m.max_diffuse_reflections; o.index_h = m.index_h; o.index_w = m.index_w;
+        o.normalmap_repeat = (float)m.normalmap_repeat; o.color_repeat = (float)m.color_repeat;
+        o.color = f3(m.color); o.n_re = f3(m.n_re); o.n_im = f3(m.n_im);
+        o.roughness = (float)m.roughness; o.spec_coeff = (float)m.spec_coeff; o.diff_coeff = (float)m.diff_coeff;
+        o.thickness = (float)m.thickness; o.noise_factor = (float)m.noise_factor;
+        o.ambient_weight = (float)m.ambient_weight; o.light_intensity = (float)m.light_intensity;
+        // texel-addressed materials evaluate the hit in double (sp_surface.cuh)
+        o.precise = (m.color_tex >= 0 || m.normalmap_tex >= 0 || m.kind == SP_MAT_THINFILM || m.kind == SP_MAT_SKYBOX) ? 1 : 0;
+        o.fan_class = 0;
+        if (m.kind == SP_MAT_DIFFUSE) {
+            max_dr = std::max(max_dr, m.max_diffuse_reflections);
+            if (m.diffuse_rays > 1) {
+                int cls = -1;
+                for (int c = 1; c < d.n_fan_classes; ++c) if (d.fan_mult[c] == m.diffuse_rays) cls = c;
+                if (cls < 0) {
+                    if (d.n_fan_classes == SP_MAX_FAN_CLASSES)
+                        return fail("at most %d distinct diffuse_rays values (> 1) per scene", SP_MAX_FAN_CLASSES - 1);
+                    cls = d.n_fan_classes++;
+                    d.fan_mult[cls] = m.diffuse_rays;
+                }
+                o.fan_class = cls;
+            }
+        }
+    }
+    CUDA_TRY(s->d_mats.upload(dm));
+
+    std::vector<DPrimitive> dp((size_t)n_prim);
+    int max_depth = 0;
+    for (int i = 0; i < n_prim; ++i) {
+        dp[i].material = s->prims[i].material; dp[i].max_ray_depth = s->prims[i].max_ray_depth;
+        dp[i].mc = s->prims[i].mc; dp[i].uv_cross = s->prims[i].uv_cross_layout;
+        max_depth = std::max(max_depth, s->prims[i].max_ray_depth);
+    }
+    CUDA_TRY(s->d_prims.upload(dp));
+    // deepest ray.depth that can exist: specular children stop at max_ray_depth, every diffuse
+    // bounce adds one more level (diffuse.py tests diffuse_reflections, not depth)
+    s->n_levels = std::min(max_depth + max_dr + 1, SP_MAX_LEVELS - 1);
+
+    std::vector<DCollider> dc((size_t)n_col);
+    std::vector<double> dcd((size_t)n_col * 40);
+    for (int i = 0; i < n_col; ++i) {
+        dc[i].type = s->cols[i].type; dc[i].prim = s->cols[i].primitive;
+        for (int k = 0; k < 40; ++k) { dc[i].p[k] = (float)s->cols[i].p[k]; dcd[(size_t)i * 40 + k] = s->cols[i].p[k]; }
+    }
+    CUDA_TRY(s->d_cols.upload(dc));
+    CUDA_TRY(s->d_cols_d.upload(dcd));
+
+    // ---- textures ---------------------------------------------------------------------------------------
+    std::vector<DTexture> td((size_t)n_tex);
+    s->d_texels.resize((size_t)n_tex);
+    for (int i = 0; i < n_tex; ++i) {
+        CUDA_TRY(s->d_texels[i].upload(s->textures[i].texels));
+        td[i].texels = s->d_texels[i].p; td[i].H = s->textures[i].H; td[i].W = s->textures[i].W;
+        td[i].decode = s->textures[i].decode; td[i].pad = 0;
+    }
+    CUDA_TRY(s->d_texdesc.upload(td));
+
+    // ---- media (complex index + Beer-Lambert coefficient, refractive.py:113-121) -------------------------
+    std::vector<DMedium> med((size_t)n_media);
+    const double lambda[3] = {630.0, 550.0, 475.0};
+    for (int i = 0; i < n_media; ++i) {
+        med[i].re = f3(&s->media_re[3 * (size_t)i]);
+        med[i].im = f3(&s->media_im[3 * (size_t)i]);
+        double ab[3];
+        for (int c = 0; c < 3; ++c) ab[c] = 2.0 * s->media_im[3 * (size_t)i + c] * 2.0 * M_PI / lambda[c] * 1e9;
+        med[i].absorb = f3(ab);
+    }
+    CUDA_TRY(s->d_media.upload(med));
+
+    // ---- geometry streams -------------------------------------------------------------------------------
+    std::vector<int32_t> all_ids((size_t)n_col);
+    for (int i = 0; i < n_col; ++i) all_ids[i] = i;
+    BuiltStream all = build_stream(s->cols, all_ids), shadow = build_stream(s->cols, s->shadow_ids);
+    CUDA_TRY(s->geom_all.upload(all.data));
+    CUDA_TRY(s->off_all.upload(all.chunk_off));
+    CUDA_TRY(s->slot_all.upload(all.slot));
+    CUDA_TRY(s->geom_shadow.upload(shadow.data));
+    CUDA_TRY(s->off_shadow.upload(shadow.chunk_off));
+    CUDA_TRY(s->slot_shadow.upload(shadow.slot));
+    d.all.data = s->geom_all.p; d.all.chunk_off = s->off_all.p;
+    d.all.n_chunks = (int)all.chunk_off.size() - 1; d.all.n_items = all.n_items;
+    d.shadow.data = s->geom_shadow.p; d.shadow.chunk_off = s->off_shadow.p;
+    d.shadow.n_chunks = (int)shadow.chunk_off.size() - 1; d.shadow.n_items = shadow.n_items;
+
+    d.colliders = s->d_cols.p; d.colliders_d = s->d_cols_d.p; d.prims = s->d_prims.p; d.mats = s->d_mats.p;
+    d.textures = s->d_texdesc.p; d.media = s->d_media.p;
+    d.n_lights = (int)s->lights.size();
+    for (int i = 0; i < d.n_lights; ++i) {
+        d.lights[i].kind = s->lights[i].kind; d.lights[i].vec = f3(s->lights[i].vec); d.lights[i].color = f3(s->lights[i].color);
+    }
+    d.n_importance = (int)s->importance.size();
+    for (int i = 0; i < d.n_importance; ++i) {
+        const sp_primitive& p = s->prims[s->importance[i]];
+        d.importance[i].center = f3(p.center); d.importance[i].radius = (float)p.bounded_sphere_radius;
+    }
+    d.ambient = f3(s->ambient);
+    d.n_colliders = n_col;
+    if (s->has_camera) {
+        const sp_camera& c = s->cam;
+        d.cam.look_from = f3(c.look_from); d.cam.right = f3(c.right); d.cam.up = f3(c.up); d.cam.fwd = f3(c.fwd);
+        d.cam.cam_w = (float)c.cam_w; d.cam.cam_h = (float)c.cam_h; d.cam.lens_radius = (float)c.lens_radius;
+        d.cam.focal_distance = (float)c.focal_distance; d.cam.W = c.width; d.cam.H = c.height;
+        CUDA_TRY(s->accum.alloc((size_t)c.width * c.height));
+        CUDA_TRY(cudaMemset(s->accum.p, 0, s->accum.n * sizeof(float4)));
+    }
+    CUDA_TRY(s->counts.alloc((size_t)(SP_MAX_LEVELS + 1) * SP_COUNTS_PER_LEVEL));
+    CUDA_TRY(s->d_stats.alloc(1));
+    s->events.resize((size_t)s->n_levels + 1);
+    for (auto& e : s->events) CUDA_TRY(cudaEventCreate(&e));
+    s->grid = sp_level_grid(g_device);
+    s->use_ray = s->use_fan = 0.0;
+    s->committed = true;
+    return 0;
+}
+
+// =================================================================================================
+// wavefront driver
+// =================================================================================================
+static int ensure_queues(sp_scene* s) {
+    // Defaults: 1 Mi primaries per chunk; queues sized for 24 records per primary (a diffuse first
+    // bounce turns 1 primary into diffuse_rays secondary hits).  The driver below measures the
+    // real occupancy on a small first chunk and then sizes later chunks to fit.
+    const uint32_t want_ray = (uint32_t)std::min<int64_t>(s->opt_ray_cap > 0 ? s->opt_ray_cap : (int64_t)24 << 20, 0x7FFFFFF0ll);
+    const uint32_t want_fan = (uint32_t)std::min<int64_t>(s->opt_fan_cap > 0 ? s->opt_fan_cap : (int64_t)24 << 20, 0x7FFFFFF0ll);
+    if (want_ray != s->ray_cap) {
+        for (int i = 0; i < 2; ++i) CUDA_TRY(s->ray_q[i].alloc(want_ray));
+        s->ray_cap = want_ray;
+    }
+    if (want_fan != s->fan_cap || s->fan_q[0].q0.n != (size_t)want_fan * s->d.n_fan_classes) {
+        for (int i = 0; i < 2; ++i) CUDA_TRY(s->fan_q[i].alloc((size_t)want_fan * s->d.n_fan_classes));
+        s->fan_cap = want_fan;
+    }
+    for (int c = 0; c < s->d.n_fan_classes; ++c)
+        if ((uint64_t)s->fan_cap * (uint64_t)s->d.fan_mult[c] > 0x7FFFFFFFull)
+            return fail("fan_queue_capacity x diffuse_rays exceeds 2^31 work items; lower fan_queue_capacity");
+    return 0;
+}
+
+struct ChunkJob {
+    int source, run;
+    uint32_t pix_begin, n_pix, sample_begin, n_items, user_base;
+    const float* user_o; const float* user_d;
+    float4* accum; int32_t* out_hit; float* out_t; float* out_o; float* out_d;
+};
+
+// Enqueue all levels of one chunk, wait, fold its counters into `st`.
+static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
+    int n_levels = (job.run == SP_RUN_FULL) ? s->n_levels : 1;
+    if (s->opt_max_levels > 0) n_levels = std::min<int>(n_levels, (int)s->opt_max_levels);   // debugging aid
+    const int ncl = SP_COUNTS_PER_LEVEL;
+    CUDA_TRY(cudaMemsetAsync(s->counts.p, 0, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), s->stream));
+    for (int L = 0; L < n_levels; ++L) {
+        LevelArgs a;
+        memset(&a, 0, sizeof a);
+        a.level = L; a.run = job.run;
+        a.source = (L == 0) ? job.source : SP_SRC_QUEUES;
+        a.pix_begin = job.pix_begin; a.n_pix = job.n_pix; a.sample_begin = job.sample_begin;
+        a.n_items0 = job.n_items; a.user_base = job.user_base; a.user_o = job.user_o; a.user_d = job.user_d;
+        a.in_rays = s->ray_q[L & 1].view(s->ray_cap);
+        a.in_fans = s->fan_q[L & 1].view(s->fan_cap * s->d.n_fan_classes);
+        a.out.rays = s->ray_q[(L + 1) & 1].view(s->ray_cap);
+        a.out.fans = s->fan_q[(L + 1) & 1].view(s->fan_cap * s->d.n_fan_classes);
+        for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) {
+            a.in_fan_base[c] = a.out.fan_base[c] = (uint32_t)c * s->fan_cap;
+            a.in_fan_cap[c] = a.out.fan_cap[c] = (c < s->d.n_fan_classes) ? s->fan_cap : 0u;
+        }
+        a.in_counts = s->counts.p + (size_t)L * ncl;
+        a.out.counts = s->counts.p + (size_t)(L + 1) * ncl;
+        a.out.stats = s->d_stats.p;
+        a.accum = job.accum;
+        a.out_hit = job.out_hit; a.out_t = job.out_t; a.out_o = job.out_o; a.out_d = job.out_d;
+        a.all_slot = s->slot_all.p; a.shadow_slot = s->slot_shadow.p;
+        CUDA_TRY(cudaEventRecord(s->events[L], s->stream));
+        CUDA_TRY(sp_launch_level(s->d, a, s->grid, s->stream));
+    }
+    CUDA_TRY(cudaEventRecord(s->events[n_levels], s->stream));
+    std::vector<uint32_t> counts((size_t)(n_levels + 1) * ncl);
+    CUDA_TRY(cudaMemcpyAsync(counts.data(), s->counts.p, counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+
+    uint64_t peak_r = 0, peak_f = 0;
+    for (int L = 1; L <= n_levels; ++L) {
+        peak_r = std::max<uint64_t>(peak_r, counts[(size_t)L * ncl]);
+        for (int c = 0; c < s->d.n_fan_classes; ++c) peak_f = std::max<uint64_t>(peak_f, counts[(size_t)L * ncl + 1 + c]);
+    }
+    if (job.n_items > 0) {
+        s->use_ray = std::max(s->use_ray, (double)peak_r / job.n_items);
+        s->use_fan = std::max(s->use_fan, (double)peak_f / job.n_items);
+    }
+    if (peak_r > s->ray_cap || peak_f > s->fan_cap)
+        return fail("wavefront queue overflow (%llu ray / %llu fan records for %u primaries; capacities %u / %u): "
+                    "raise ray_queue_capacity / fan_queue_capacity or lower chunk_primaries",
+                    (unsigned long long)peak_r, (unsigned long long)peak_f, job.n_items, s->ray_cap, s->fan_cap);
+    if (st) {
+        st->chunks += 1;
+        st->kernel_launches += (uint64_t)n_levels;
+        st->level_kernel_launches += (uint64_t)n_levels;
+        st->peak_ray_records = std::max<uint64_t>(st->peak_ray_records, peak_r);
+        st->peak_fan_records = std::max<uint64_t>(st->peak_fan_records, peak_f);
+        for (int L = 0; L < n_levels; ++L) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s->events[L], s->events[L + 1]);
+            st->level_ms[L] += ms;
+            st->level_kernel_ms += ms;
+        }
+        // records written by level L-1 and read by level L: 48 B each way
+        for (int L = 1; L <= n_levels; ++L)
+            for (int k = 0; k < ncl; ++k) st->queue_bytes += 2ull * 48ull * counts[(size_t)L * ncl + k];
+    }
+    return 0;
+}
+
+static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what) {
+    if (!s) return fail("%s: null scene", what);
+    if (!s->committed) return fail("%s: scene not committed (sp_scene_commit)", what);
+    CUDA_TRY(cudaSetDevice(g_device));
+    s->d.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull);
+    s->d.seed_hi = (uint32_t)(seed >> 32);
+    if (st) memset(st, 0, sizeof *st);
+    CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
+    return ensure_queues(s);
+}
+
+static int end_call(sp_scene* s, sp_stats* st, cudaEvent_t t0, cudaEvent_t t1) {
+    DeviceStats ds;
+    CUDA_TRY(cudaMemcpyAsync(&ds, s->d_stats.p, sizeof ds, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaEventRecord(t1, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (st) {
+        for (int L = 0; L < SP_MAX_LEVELS && L < SP_MAX_DEPTH_LEVELS; ++L) {
+            st->rays_per_depth[L] = ds.rays[L];
+            st->rays_total += ds.rays[L];
+        }
+        st->shadow_rays = ds.shadow_rays;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        st->device_ms = ms;
+    }
+    if (ds.overflow) return fail("wavefront queue overflow: raise ray_queue_capacity / fan_queue_capacity or lower chunk_primaries");
+    return 0;
+}
+
+// primaries per chunk given the occupancy seen so far
+static uint32_t pick_chunk(sp_scene* s, bool first) {
+    int64_t p = s->opt_chunk > 0 ? s->opt_chunk : (int64_t)1 << 20;
+    if (first && s->use_ray == 0.0 && s->use_fan == 0.0) p = std::min<int64_t>(p, 1 << 16);   // probe
+    const double slack = 1.3;
+    if (s->use_ray > 0.0) p = std::min<int64_t>(p, (int64_t)(s->ray_cap / (s->use_ray * slack)));
+    if (s->use_fan > 0.0) p = std::min<int64_t>(p, (int64_t)(s->fan_cap / (s->use_fan * slack)));
+    return (uint32_t)std::max<int64_t>(p, 1024);
+}
+
+int sp_render_samples(sp_scene* s, int sample_begin, int sample_end, uint64_t seed, int clear, sp_stats* st) {
+    int rc = begin_call(s, seed, st, "sp_render_samples");
+    if (rc) return rc;
+    if (!s->has_camera) return fail("sp_render_samples: the scene has no camera");
+    if (sample_begin < 0 || sample_end < sample_begin) return fail("sp_render_samples: invalid sample range");
+    cudaEvent_t t0, t1;
+    CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+    CUDA_TRY(cudaEventRecord(t0, s->stream));
+    if (clear) CUDA_TRY(cudaMemsetAsync(s->accum.p, 0, s->accum.n * sizeof(float4), s->stream));
+    const uint32_t n_pix_total = (uint32_t)s->d.cam.W * (uint32_t)s->d.cam.H;
+    uint32_t sample = (uint32_t)sample_begin, pix = 0;
+    bool first = true;
+    while (sample < (uint32_t)sample_end && rc == 0) {
+        const uint32_t P = pick_chunk(s, first);
+        first = false;
+        ChunkJob job{};
+        job.source = SP_SRC_CAMERA; job.run = SP_RUN_FULL; job.accum = s->accum.p;
+        if (pix == 0 && P >= n_pix_total) {
+            const uint32_t ns = std::min<uint32_t>(P / n_pix_total, (uint32_t)sample_end - sample);
+            job.pix_begin = 0; job.n_pix = n_pix_total; job.sample_begin = sample; job.n_items = ns * n_pix_total;
+            sample += ns;
+        } else {
+            const uint32_t n = std::min<uint32_t>(P, n_pix_total - pix);
+            job.pix_begin = pix; job.n_pix = n; job.sample_begin = sample; job.n_items = n;
+            pix += n;
+            if (pix == n_pix_total) { pix = 0; ++sample; }
+        }
+        rc = run_chunk(s, job, st);
+    }
+    int rc2 = end_call(s, st, t0, t1);
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    return rc ? rc : rc2;
+}
+
+void* sp_accum_device_ptr(sp_scene* s) { return s ? (void*)s->accum.p : nullptr; }
+uint64_t sp_accum_bytes(sp_scene* s) { return s ? (uint64_t)(s->accum.n * sizeof(float4)) : 0; }
+
+int sp_resolve(sp_scene* s, int spp_total, float* out_linear, uint8_t* out_srgb8) {
+    if (!s || !s->committed || !s->has_camera) return fail("sp_resolve: scene not committed or has no camera");
+    if (spp_total < 1) return fail("sp_resolve: spp_total must be >= 1");
+    CUDA_TRY(cudaSetDevice(g_device));
+    const size_t n = s->accum.n;
+    DevBuf<float> d_lin;
+    DevBuf<uint8_t> d_u8;
+    if (out_linear) CUDA_TRY(d_lin.alloc(3 * n));
+    if (out_srgb8) CUDA_TRY(d_u8.alloc(3 * n));
+    ResolveArgs a;
+    a.accum = s->accum.p; a.n_pix = (uint32_t)n; a.spp = (double)spp_total; a.out_linear = d_lin.p; a.out_srgb8 = d_u8.p;
+    int rc = 0;
+    cudaError_t e = sp_launch_resolve(a, s->stream);
+    if (e == cudaSuccess && out_linear) e = cudaMemcpyAsync(out_linear, d_lin.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && out_srgb8) e = cudaMemcpyAsync(out_srgb8, d_u8.p, 3 * n, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) rc = fail("sp_resolve: %s", cudaGetErrorString(e));
+    d_lin.release(); d_u8.release();
+    return rc;
+}
+
+int sp_render(sp_scene* s, int spp, uint64_t seed, float* out_linear, uint8_t* out_srgb8, sp_stats* st) {
+    if (spp < 1) return fail("sp_render: samples_per_pixel must be >= 1");
+    int rc = sp_render_samples(s, 0, spp, seed, 1, st);
+    if (rc) return rc;
+    if (st) st->kernel_launches += 1;
+    return sp_resolve(s, spp, out_linear, out_srgb8);
+}
+
+int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64_t seed, float* out_rgb,
+             int32_t* out_hit_id, float* out_t, sp_stats* st) {
+    int rc = begin_call(s, seed, st, "sp_trace");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!origins || !dirs))) return fail("sp_trace: invalid arguments");
+    if (n == 0) return 0;
+    DevBuf<float> d_o, d_d, d_t;
+    DevBuf<float4> d_acc;
+    DevBuf<int32_t> d_hit;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    auto cleanup = [&]() {
+        d_o.release(); d_d.release(); d_t.release(); d_acc.release(); d_hit.release();
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
+    };
+#define TRY_OR_CLEAN(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail("%s: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+    TRY_OR_CLEAN(d_o.alloc(3 * (size_t)n)); TRY_OR_CLEAN(d_d.alloc(3 * (size_t)n));
+    TRY_OR_CLEAN(d_t.alloc((size_t)n)); TRY_OR_CLEAN(d_hit.alloc((size_t)n)); TRY_OR_CLEAN(d_acc.alloc((size_t)n));
+    TRY_OR_CLEAN(cudaMemcpyAsync(d_o.p, origins, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    TRY_OR_CLEAN(cudaMemcpyAsync(d_d.p, dirs, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    TRY_OR_CLEAN(cudaMemsetAsync(d_acc.p, 0, (size_t)n * sizeof(float4), s->stream));
+    TRY_OR_CLEAN(cudaEventCreate(&t0)); TRY_OR_CLEAN(cudaEventCreate(&t1));
+    TRY_OR_CLEAN(cudaEventRecord(t0, s->stream));
+    bool first = true;
+    for (uint32_t base = 0; base < (uint32_t)n && rc == 0;) {
+        const uint32_t P = std::min<uint32_t>(pick_chunk(s, first), (uint32_t)n - base);
+        first = false;
+        ChunkJob job{};
+        job.source = SP_SRC_USER; job.run = SP_RUN_FULL; job.accum = d_acc.p;
+        job.user_base = base; job.n_items = P; job.user_o = d_o.p; job.user_d = d_d.p;
+        job.out_hit = d_hit.p; job.out_t = d_t.p;
+        rc = run_chunk(s, job, st);
+        base += P;
+    }
+    int rc2 = end_call(s, st, t0, t1);
+    if (rc == 0) rc = rc2;
+    if (rc == 0) {
+        if (out_rgb) {
+            std::vector<float4> acc((size_t)n);
+            TRY_OR_CLEAN(cudaMemcpy(acc.data(), d_acc.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < n; ++i) { out_rgb[3 * (size_t)i] = acc[i].x; out_rgb[3 * (size_t)i + 1] = acc[i].y; out_rgb[3 * (size_t)i + 2] = acc[i].z; }
+        }
+        if (out_hit_id) TRY_OR_CLEAN(cudaMemcpy(out_hit_id, d_hit.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (out_t) TRY_OR_CLEAN(cudaMemcpy(out_t, d_t.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    cleanup();
+    return rc;
+}
+
+static int primary_pass(sp_scene* s, int run, int sample, uint64_t seed, float* out_o, float* out_d, float* out_t, const char* what) {
+    int rc = begin_call(s, seed, nullptr, what);
+    if (rc) return rc;
+    if (!s->has_camera) return fail("%s: the scene has no camera", what);
+    const size_t n = s->accum.n;
+    DevBuf<float> d_o, d_d, d_t;
+    auto cleanup = [&]() { d_o.release(); d_d.release(); d_t.release(); };
+    if (run == SP_RUN_DUMP_RAYS) { TRY_OR_CLEAN(d_o.alloc(3 * n)); TRY_OR_CLEAN(d_d.alloc(3 * n)); }
+    else TRY_OR_CLEAN(d_t.alloc(n));
+    ChunkJob job{};
+    job.source = SP_SRC_CAMERA; job.run = run; job.accum = s->accum.p;
+    job.pix_begin = 0; job.n_pix = (uint32_t)n; job.sample_begin = (uint32_t)sample; job.n_items = (uint32_t)n;
+    job.out_o = d_o.p; job.out_d = d_d.p; job.out_t = d_t.p;
+    rc = run_chunk(s, job, nullptr);
+    if (rc == 0 && run == SP_RUN_DUMP_RAYS) {
+        TRY_OR_CLEAN(cudaMemcpy(out_o, d_o.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+        TRY_OR_CLEAN(cudaMemcpy(out_d, d_d.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    } else if (rc == 0) {
+        TRY_OR_CLEAN(cudaMemcpy(out_t, d_t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    cleanup();
+    return rc;
+}
+
+int sp_camera_rays(sp_scene* s, int sample, uint64_t seed, float* out_origins, float* out_dirs) {
+    if (!out_origins || !out_dirs || sample < 0) return fail("sp_camera_rays: invalid arguments");
+    return primary_pass(s, SP_RUN_DUMP_RAYS, sample, seed, out_origins, out_dirs, nullptr, "sp_camera_rays");
+}
+
+int sp_distances(sp_scene* s, uint64_t seed, float* out_t) {
+    if (!out_t) return fail("sp_distances: invalid arguments");
+    return primary_pass(s, SP_RUN_DISTANCES, 0, seed, nullptr, nullptr, out_t, "sp_distances");
+}
+
+int sp_set_option(sp_scene* s, const char* name, int64_t value) {
+    if (!s || !name) return fail("sp_set_option: invalid arguments");
+    if (value < 0) return fail("sp_set_option: %s must be >= 0", name);
+    if (!strcmp(name, "ray_queue_capacity")) s->opt_ray_cap = value;
+    else if (!strcmp(name, "fan_queue_capacity")) s->opt_fan_cap = value;
+    else if (!strcmp(name, "chunk_primaries")) s->opt_chunk = value;
+    else if (!strcmp(name, "max_levels")) s->opt_max_levels = value;
+    else return fail("sp_set_option: unknown option '%s'", name);
+    s->use_ray = s->use_fan = 0.0;
+    return 0;
+}
+
+int sp_measure_peaks(double* fp32_tflops, double* copy_gbs) {
+    if (g_device < 0) return fail("sp_measure_peaks: call sp_init first");
+    CUDA_TRY(cudaSetDevice(g_device));
+    double a = 0.0, b = 0.0;
+    CUDA_TRY(sp_bench_ffma(&a, nullptr));
+    CUDA_TRY(sp_bench_copy(&b, nullptr));
+    if (fp32_tflops) *fp32_tflops = a;
+    if (copy_gbs) *copy_gbs = b;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Ray / collider intersection over one staged geometry chunk (FP32, brute force, nearest hit).
+//
+// Restates Sphere_Collider.intersect (sphere.py:26-52), Plane_Collider.intersect (plane.py:57-90),
+// Cuboid_Collider.intersect (cuboid.py:105-140) and Triangle_Collider.intersect (triangle.py:37-66)
+// in forms that are stable in float32:
+//   * sphere: discriminant from the perpendicular offset  r^2 - |oc - (D.oc) D|^2  instead of the
+//     expanded  |C|^2 + |O|^2 - 2 C.O - r^2  (which cancels catastrophically in float32);
+//   * plane / triangle: everything relative to O - C;  cuboid: slabs on B (O - C);
+//   * "FARAWAY" (1e39) does not exist in float32: a miss is t = +inf.
+// All lanes of a warp walk the same chunk in the same order, so every shared-memory read is a
+// broadcast (no bank conflicts) and there is no divergence in the loop structure.
+//
+// Self-intersection: the reference offsets secondary-ray origins by 1e-6 along the normal, which
+// is below float32 resolution at scene scale (ulp(555) = 6e-5).  Instead a ray record names the
+// collider it starts on and how it leaves it (SP_SELF_*, sp_types.cuh) and that one collider is
+// answered analytically — the eps -> 0 limit of what the reference computes in float64.
+#pragma once
+#include "sp_types.cuh"
+
+struct HitRec {
+    float t;        // parametric distance (directions are unit length), +inf = miss
+    int id;         // index into scene.collider_list, -1 = miss
+    int orient;     // +1 UPWARDS (outer face), -1 UPDOWN (inner face)
+};
+
+// where the ray's source collider sits inside the current chunk (-1 = not in this chunk)
+struct SelfSlot { int sphere, plane, cuboid, tri; uint32_t mode; };
+
+struct ChunkBest { float t; int idx; int orient; };   // idx = position in the chunk's id array
+
+SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D, SelfSlot self,
+                               ChunkBest& best) {
+    const GeomChunkHeader* h = reinterpret_cast<const GeomChunkHeader*>(ch);
+    const int n_sphere = h->n_sphere, n_plane = h->n_plane, n_cuboid = h->n_cuboid, n_tri = h->n_tri;
+
+    // ---- spheres ---------------------------------------------------------------------------
+    {
+        const float4* sp = ch + h->off_sphere;
+#pragma unroll 4
+        for (int i = 0; i < n_sphere; ++i) {
+            float4 s = sp[i];
+            float3 oc = O - xyz(s);
+            float b = dot(D, oc);
+            float3 q = fma3(D, -b, oc);
+            float disc = s.w - dot(q, q);
+            if (disc > 0.f) {
+                float sq = sqrtf(disc);
+                float h0 = -b - sq, h1 = -b + sq;
+                bool is_self = (i == self.sphere);
+                bool near_ok = (h0 > 0.f) && !is_self;             // SP_SELF_FAR: only the far root
+                float t = near_ok ? h0 : h1;
+                bool ok = (t > 0.f) && !(is_self && self.mode != SP_SELF_FAR);
+                if (ok && t < best.t) { best.t = t; best.idx = i; best.orient = near_ok ? 1 : -1; }
+            }
+        }
+    }
+    // ---- bounded planes ------------------------------------------------------------------------
+    {
+        const float4* pl = ch + h->off_plane;
+        for (int i = 0; i < n_plane; ++i) {
+            float4 a = pl[4 * i], c = pl[4 * i + 1], u4 = pl[4 * i + 2], v4 = pl[4 * i + 3];
+            float3 N = xyz(a), oc = O - xyz(c);
+            float nd = dot(N, D);
+            nd = (nd == 0.f) ? 1e-4f : nd;
+            float k = -dot(N, oc);
+            float t = k / nd;
+            float u = fmaf(t, dot(xyz(u4), D), dot(xyz(u4), oc));
+            float v = fmaf(t, dot(xyz(v4), D), dot(xyz(v4), oc));
+            bool ok = (fabsf(u) <= a.w) && (fabsf(v) <= c.w) && (k * nd > 0.f) && (i != self.plane);
+            if (ok && t < best.t) { best.t = t; best.idx = n_sphere + i; best.orient = nd < 0.f ? 1 : -1; }
+        }
+    }
+    // ---- oriented cuboids ------------------------------------------------------------------------
+    {
+        const float4* cb = ch + h->off_cuboid;
+        for (int i = 0; i < n_cuboid; ++i) {
+            float4 r0 = cb[5 * i], r1 = cb[5 * i + 1], r2 = cb[5 * i + 2], c = cb[5 * i + 3], e = cb[5 * i + 4];
+            float3 oc = O - xyz(c);
+            float3 Ol = v3(dot(xyz(r0), oc), dot(xyz(r1), oc), dot(xyz(r2), oc));
+            float3 Dl = v3(dot(xyz(r0), D), dot(xyz(r1), D), dot(xyz(r2), D));
+            float ix = 1.f / Dl.x, iy = 1.f / Dl.y, iz = 1.f / Dl.z;
+            float t1 = (r0.w - Ol.x) * ix, t2 = (c.w - Ol.x) * ix;
+            float t3 = (r1.w - Ol.y) * iy, t4 = (e.x - Ol.y) * iy;
+            float t5 = (r2.w - Ol.z) * iz, t6 = (e.y - Ol.z) * iz;
+            float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+            float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+            bool is_self = (i == self.cuboid);
+            bool miss = (tmax < 0.f) || (tmin > tmax);
+            bool inside = (tmin < 0.f) || is_self;                 // SP_SELF_FAR: exit point only
+            float t = inside ? tmax : tmin;
+            bool ok = !miss && !(is_self && self.mode != SP_SELF_FAR);
+            if (ok && t < best.t) { best.t = t; best.idx = n_sphere + n_plane + i; best.orient = inside ? -1 : 1; }
+        }
+    }
+    // ---- triangles -----------------------------------------------------------------------------
+    {
+        const float4* tr = ch + h->off_tri;
+        for (int i = 0; i < n_tri; ++i) {
+            float4 f0 = tr[6 * i], f1 = tr[6 * i + 1], f2 = tr[6 * i + 2];
+            float4 f3 = tr[6 * i + 3], f4 = tr[6 * i + 4], f5 = tr[6 * i + 5];
+            float3 N = v3(f0.x, f0.y, f0.z), cen = v3(f0.w, f1.x, f1.y);
+            float3 n31 = v3(f1.z, f1.w, f2.x), p1 = v3(f2.y, f2.z, f2.w);
+            float3 n12 = v3(f3.x, f3.y, f3.z), p2 = v3(f3.w, f4.x, f4.y);
+            float3 n23 = v3(f4.z, f4.w, f5.x), p3 = v3(f5.y, f5.z, f5.w);
+            float nd = dot(N, D);
+            nd = (nd == 0.f) ? 1e-4f : nd;
+            float k = -dot(N, O - cen);
+            float t = k / nd;
+            float e1 = fmaf(t, dot(n31, D), dot(n31, O - p1));
+            float e2 = fmaf(t, dot(n12, D), dot(n12, O - p2));
+            float e3 = fmaf(t, dot(n23, D), dot(n23, O - p3));
+            bool ok = (e1 >= 0.f) && (e2 >= 0.f) && (e3 >= 0.f) && (k * nd > 0.f) && (i != self.tri);
+            if (ok && t < best.t) {
+                best.t = t; best.idx = n_sphere + n_plane + n_cuboid + i; best.orient = nd < 0.f ? 1 : -1;
+            }
+        }
+    }
+}
+
+SP_DEV int sp_chunk_id(const float4* __restrict__ ch, int idx) {
+    const GeomChunkHeader* h = reinterpret_cast<const GeomChunkHeader*>(ch);
+    return reinterpret_cast<const int*>(ch + h->off_ids)[idx];
+}

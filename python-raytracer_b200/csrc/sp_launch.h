@@ -1,0 +1,45 @@
+// Host-callable launchers of the kernels in sp_kernels.cu (the runtime in sp_api.cpp is plain C++).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sp_types.cuh"
+
+// What a level launch reads its work items from.
+enum { SP_SRC_CAMERA = 0, SP_SRC_USER = 1, SP_SRC_QUEUES = 2 };
+// What a level-0 launch does with its rays.
+enum { SP_RUN_FULL = 0, SP_RUN_DISTANCES = 1, SP_RUN_DUMP_RAYS = 2 };
+
+
+struct LevelArgs {
+    int level, source, run;
+    // level 0, camera: item i -> pixel pix_begin + i % n_pix, sample sample_begin + i / n_pix
+    // level 0, user rays: item i -> ray user_base + i (interleaved xyz), pixel id = ray index
+    uint32_t pix_begin, n_pix, sample_begin, n_items0, user_base;
+    const float* user_o;
+    const float* user_d;
+    // level >= 1: records written by the previous level
+    RayQueue in_rays, in_fans;
+    uint32_t in_fan_base[SP_MAX_FAN_CLASSES], in_fan_cap[SP_MAX_FAN_CLASSES];
+    const uint32_t* in_counts;
+    LevelOut out;
+    float4* accum;                 // per pixel (or per user ray): xyz = sum of radiance
+    // optional per-item outputs of level 0
+    int32_t* out_hit; float* out_t; float* out_o; float* out_d;
+    const int2* all_slot;
+    const int2* shadow_slot;
+};
+
+struct ResolveArgs {
+    const float4* accum;
+    uint32_t n_pix;
+    double spp;                    // divide the sums by this (scene.py:119)
+    float* out_linear;             // 3 planes of n_pix floats (nullable)
+    uint8_t* out_srgb8;            // n_pix * 3 interleaved (nullable)
+};
+
+int sp_level_grid(int device);                       // CTAs of a persistent level launch
+cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, int grid, cudaStream_t st);
+cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
+cudaError_t sp_upload_decode_tables(const float* plain256, const float* linear256);
+cudaError_t sp_bench_ffma(double* tflops, cudaStream_t st);
+cudaError_t sp_bench_copy(double* gbs, cudaStream_t st);

@@ -1,0 +1,82 @@
+// Primary-ray generation and importance-sampled diffuse directions.
+//
+// Restates Camera.get_ray (camera.py:51-85), cosine_pdf / spherical_caps_pdf / mixed_pdf
+// (random.py:50-174).  The reference draws 2 + 3 uniforms per direction and evaluates both pdfs'
+// generators for every ray before selecting one; here one Philox block gives
+//   u0: mixture choice   u1: azimuth   u2: radial variate   u3: which cap
+// and only the selected generator runs (same distribution; oracle/ mirrors this mapping).
+#pragma once
+#include "sp_rng.cuh"
+#include "sp_types.cuh"
+
+// tangent frame of random.py:60-63: a = (0,1,0) if |w.x| > 0.9 else (1,0,0); v = norm(w x a); u = w x v
+SP_DEV void sp_onb(float3 w, float3& u, float3& v) {
+    float3 a = fabsf(w.x) > 0.9f ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
+    v = normalize0(cross(w, a));
+    u = cross(w, v);
+}
+
+SP_DEV void sp_camera_ray(const DCamera& cam, uint32_t pixel, uint32_t sample, uint32_t k0, uint32_t k1,
+                          float3& origin, float3& dir) {
+    float u[4];
+    sp_draw4(pixel, sp_root_path(sample), SP_BLOCK_DIRECTION, k0, k1, u);
+    int px = (int)(pixel % (uint32_t)cam.W), py = (int)(pixel / (uint32_t)cam.W);
+    // np.linspace(-w/2, w/2, W)[px] and np.linspace(h/2, -h/2, H)[py]
+    float gx = cam.W > 1 ? -0.5f * cam.cam_w + cam.cam_w * ((float)px / (float)(cam.W - 1)) : -0.5f * cam.cam_w;
+    float gy = cam.H > 1 ? 0.5f * cam.cam_h - cam.cam_h * ((float)py / (float)(cam.H - 1)) : 0.5f * cam.cam_h;
+    float x = gx + (u[0] - 0.5f) * cam.cam_w / (float)cam.W;
+    float y = gy + (u[1] - 0.5f) * cam.cam_h / (float)cam.H;
+    float rr = sqrtf(u[2]), sn, cs;
+    sincospif(2.f * u[3], &sn, &cs);
+    float rx = rr * cs * cam.lens_radius, ry = rr * sn * cam.lens_radius;
+    origin = cam.look_from + cam.right * rx + cam.up * ry;
+    float fd = cam.focal_distance;
+    float3 target = cam.look_from + cam.up * (y * fd) + cam.right * (x * fd) + cam.fwd * fd;
+    dir = normalize0(target - origin);
+}
+
+// Sample a direction for a diffuse bounce at `origin` with shading normal N; returns the estimator
+// weight  clip(N.d, 0, 1) / pdf(d) / pi  (diffuse.py:76-81), 0 if the sample carries nothing.
+SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float w_cos, uint32_t pix,
+                               uint32_t path, float3& dir) {
+    float u[4];
+    sp_draw4(pix, path, SP_BLOCK_DIRECTION, sc.seed_lo, sc.seed_hi, u);
+    float sn, cs;
+    sincospif(2.f * u[1], &sn, &cs);
+    const int l = sc.n_importance;
+    bool use_cos = (l == 0) || (u[0] < w_cos);
+    if (use_cos) {                                           // cosine_pdf.generate
+        float3 au, av;
+        sp_onb(N, au, av);
+        float s = sqrtf(u[2]);
+        dir = au * (cs * s) + av * (sn * s) + N * sqrtf(1.f - u[2]);
+    } else {                                                 // spherical_caps_pdf.generate
+        int pick = min((int)(u[3] * (float)l), l - 1);
+        float3 to_c = sc.importance[pick].center - origin;
+        float d2 = dot(to_c, to_c);
+        float3 w = to_c * rsqrtf(d2);
+        float ratio = clamp01(sc.importance[pick].radius * rsqrtf(d2));
+        float cmax = sqrtf(1.f - ratio * ratio);
+        float3 au, av;
+        sp_onb(w, au, av);
+        float z = 1.f + u[2] * (cmax - 1.f);
+        float s = sqrtf(fmaxf(1.f - z * z, 0.f));
+        dir = au * (cs * s) + av * (sn * s) + w * z;
+    }
+    float ndl = clamp01(dot(dir, N));
+    if (ndl <= 0.f) return 0.f;
+    float pdf = ndl * (1.f / SP_PI);
+    if (l > 0) {                                             // mixed_pdf.value
+        float caps = 0.f;
+        for (int i = 0; i < l; ++i) {
+            float3 to_c = sc.importance[i].center - origin;
+            float d2 = dot(to_c, to_c);
+            float inv = rsqrtf(d2);
+            float ratio = clamp01(sc.importance[i].radius * inv);
+            float cmax = sqrtf(1.f - ratio * ratio);
+            if (dot(dir, to_c) * inv > cmax) caps += 1.f / ((1.f - cmax) * 2.f * SP_PI);
+        }
+        pdf = pdf * w_cos + (caps / (float)l) * (1.f - w_cos);
+    }
+    return ndl / pdf * (1.f / SP_PI);
+}

@@ -1,0 +1,140 @@
+// Device-side scene description and wavefront queue layout.
+#pragma once
+#include "sp_math.cuh"
+#include "../../include/sightpy_b200.h"   // SP_COLLIDER_*, SP_MAT_*, SP_LIGHT_* enums
+
+// ---- geometry stream ----------------------------------------------------------------------------
+// The colliders a ray must be tested against are packed, type-sorted, into 16-byte vectors and cut
+// into chunks that fit the CTA's shared-memory staging buffer.  Every chunk is self-describing:
+//   [GeomChunkHeader (4 x float4)] [spheres 1 v4 each] [planes 4 v4] [cuboids 5 v4] [triangles 6 v4]
+//   [collider ids: int per item, same order]
+// sphere   : (cx, cy, cz, r^2)
+// plane    : (N.xyz, w) (C.xyz, h) (U.xyz, -) (V.xyz, -)
+// cuboid   : (B0.xyz, lo.x) (B1.xyz, lo.y) (B2.xyz, lo.z) (C.xyz, hi.x) (hi.y, hi.z, -, -)
+//            B = basis rows, lo/hi = box corners relative to B*C (so tests run on O - C)
+// triangle : 24 floats N, centroid, n31, p1, n12, p2, n23, p3
+#define SP_CHUNK_VEC4 2048            // 32 KB staging buffer
+#define SP_V4_SPHERE 1
+#define SP_V4_PLANE 4
+#define SP_V4_CUBOID 5
+#define SP_V4_TRIANGLE 6
+
+struct GeomChunkHeader {
+    int n_sphere, n_plane, n_cuboid, n_tri;
+    int off_sphere, off_plane, off_cuboid, off_tri;   // in float4 units from the chunk start
+    int off_ids, n_vec4, pad0, pad1;
+    int pad2, pad3, pad4, pad5;
+};
+static_assert(sizeof(GeomChunkHeader) == 64, "header is 4 float4");
+
+struct GeomStream {
+    const float4* data;        // all chunks back to back
+    const int* chunk_off;      // n_chunks + 1 offsets (float4 units)
+    int n_chunks;
+    int n_items;
+};
+
+// ---- full records used at shading time (one per collider / primitive / material) -------------
+struct DCollider {
+    int type, prim;
+    float p[40];               // same slots as sp_collider.p (include/sightpy_b200.h)
+};
+
+struct DPrimitive {
+    int material, max_ray_depth, mc, uv_cross;
+};
+
+struct DMaterial {
+    int kind, medium, normalmap_tex, color_tex;
+    int aux_tex0, aux_tex1, diffuse_rays, max_dr;
+    int index_h, index_w, fan_class, precise;
+    float normalmap_repeat, color_repeat;
+    float3 color;
+    float3 n_re, n_im;
+    float roughness, spec_coeff, diff_coeff;
+    float thickness, noise_factor, ambient_weight, light_intensity;
+};
+
+struct DTexture {
+    const uint32_t* texels;    // r | g << 8 | b << 16
+    int H, W, decode, pad;
+};
+
+struct DLight { int kind; float3 vec; float3 color; };
+struct DImportance { float3 center; float radius; };
+struct DMedium { float3 re, im, absorb; };   // absorb = 2*Im(n)*2*pi/lambda*1e9  (refractive.py:113-121)
+
+struct DCamera {
+    float3 look_from, right, up, fwd;
+    float cam_w, cam_h, lens_radius, focal_distance;
+    int W, H;
+};
+
+#define SP_MAX_FAN_CLASSES 4
+#define SP_MAX_IMPORTANCE 16
+#define SP_MAX_LIGHTS 8
+
+struct DScene {
+    GeomStream all, shadow;
+    const DCollider* colliders;
+    const double* colliders_d;     // [n][40] double payloads for the precise hit path
+    const DPrimitive* prims;
+    const DMaterial* mats;
+    const DTexture* textures;
+    const DMedium* media;
+    DLight lights[SP_MAX_LIGHTS];
+    DImportance importance[SP_MAX_IMPORTANCE];
+    DCamera cam;
+    float3 ambient;
+    int n_lights, n_importance, n_colliders, n_fan_classes;
+    int fan_mult[SP_MAX_FAN_CLASSES];     // rays per fan record of each class (class 0: 1)
+    uint32_t seed_lo, seed_hi;
+};
+
+// ---- wavefront records --------------------------------------------------------------------------
+// One record = three float4 in three SoA arrays (coalesced 16-byte accesses):
+//   q0 = (O.xyz, pixel)   q1 = (V.xyz, path)   q2 = (throughput.rgb, meta)
+// V is the ray direction in the ray queue, and the shading normal to sample around in the fan
+// queues (the consumer generates the direction: "generate + intersect" fused, so the 20 children
+// of a diffuse hit never exist in memory).
+// meta: depth[0:6) | diffuse_reflections[6:8) | medium[8:16) | source collider[16:30) | self mode[30:32)
+#define SP_SRC_NONE 0x3FFFu
+#define SP_SELF_SKIP 0u      // leaving the source surface: it cannot be hit again
+#define SP_SELF_ZERO 1u      // heading back into the source surface: immediate re-hit at t = 0
+#define SP_SELF_FAR  2u      // inside a convex source collider: take its far intersection
+
+SP_DEV uint32_t sp_pack_meta(uint32_t depth, uint32_t dr, uint32_t medium, uint32_t src, uint32_t mode) {
+    return (depth & 63u) | ((dr & 3u) << 6) | ((medium & 255u) << 8) | ((src & 0x3FFFu) << 16) | (mode << 30);
+}
+SP_DEV uint32_t meta_depth(uint32_t m) { return m & 63u; }
+SP_DEV uint32_t meta_dr(uint32_t m) { return (m >> 6) & 3u; }
+SP_DEV uint32_t meta_medium(uint32_t m) { return (m >> 8) & 255u; }
+SP_DEV uint32_t meta_src(uint32_t m) { return (m >> 16) & 0x3FFFu; }
+SP_DEV uint32_t meta_mode(uint32_t m) { return m >> 30; }
+
+struct RayQueue {
+    float4* q0; float4* q1; float4* q2;
+    uint32_t capacity;
+};
+
+#define SP_MAX_LEVELS 64
+// Per-level counters live in one device array so a whole chunk of levels needs a single memset:
+//   counts[level][0] = ray-queue records, counts[level][1 + c] = fan-queue records of class c
+#define SP_COUNTS_PER_LEVEL (1 + SP_MAX_FAN_CLASSES)
+
+struct DeviceStats;
+struct LevelOut {
+    RayQueue rays;                         // explicit-direction records for the next level
+    RayQueue fans;                         // fan records of all classes share one arena ...
+    uint32_t fan_base[SP_MAX_FAN_CLASSES]; // ... cut into per-class segments
+    uint32_t fan_cap[SP_MAX_FAN_CLASSES];
+    uint32_t* counts;                      // counts[0] rays, counts[1 + c] fan class c (next level)
+    DeviceStats* stats;
+};
+
+struct DeviceStats {
+    unsigned long long rays[SP_MAX_LEVELS];
+    unsigned long long shadow_rays;
+    unsigned int overflow;
+    unsigned int pad;
+};

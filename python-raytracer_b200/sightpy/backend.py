@@ -25,6 +25,8 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_uint64), ("chunks", C.c_uint64),
         ("device_ms", C.c_double), ("level_kernel_ms", C.c_double),
         ("level_kernel_launches", C.c_uint64), ("queue_bytes", C.c_uint64),
+        ("level_ms", C.c_double * SP_MAX_DEPTH_LEVELS),
+        ("peak_ray_records", C.c_uint64), ("peak_fan_records", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -36,7 +38,10 @@ class Stats(C.Structure):
                     chunks=int(self.chunks), device_ms=float(self.device_ms),
                     level_kernel_ms=float(self.level_kernel_ms),
                     level_kernel_launches=int(self.level_kernel_launches),
-                    queue_bytes=int(self.queue_bytes))
+                    queue_bytes=int(self.queue_bytes),
+                    level_ms=[float(v) for v in self.level_ms][:max(len(depth), 1)],
+                    peak_ray_records=int(self.peak_ray_records),
+                    peak_fan_records=int(self.peak_fan_records))
 
 
 def library_path():

@@ -8,7 +8,8 @@ For every scene in tests/scenes.py the script
   1. builds the scene twice from the same builder: with the reference's classes (imported under
      the alias ``refsightpy`` so it cannot be confused with this repo's ``sightpy``) and with ours;
   2. draws one set of jittered primary rays, rounds them to float32 (both renderers then see
-     bit-identical, float32-representable rays: SURVEY §7 "parity protocol");
+     bit-identical, float32-representable rays: SURVEY §7 "parity protocol"); the float64 side
+     renormalises the directions, as the reference's own camera rays are unit length to 1e-16;
   3. evaluates the reference's ``get_raycolor`` on them under ``np.random.seed(SEED)`` and records
      linear radiance, nearest collider index and hit distance per ray;
   4. evaluates the oracle (rng="legacy", same seed) on the flattening of BOTH scene objects and
@@ -82,7 +83,12 @@ def reference_trace(ref, scene, O32, D32):
     """get_raycolor + per-collider intersect of the reference on float32-representable rays."""
     v = ref.vec3
     O = v(*(O32[:, k].astype(np.float64) for k in range(3)))
-    D = v(*(D32[:, k].astype(np.float64) for k in range(3)))
+    # float32-representable directions, renormalised in float64: the reference's hit points are
+    # O + D*|D t|, so |D| must be 1 to rounding as it is for Camera.get_ray's own rays (see
+    # Oracle.trace, which applies the same renormalisation)
+    D64 = D32.astype(np.float64)
+    D64 = D64 / np.sqrt((D64 * D64).sum(axis=1, keepdims=True))
+    D = v(*(D64[:, k] for k in range(3)))
     ray = ref.Ray(O, D, 0, scene.n, 0, 0, 0)
     dists = [c.intersect(ray.origin, ray.dir)[0] for c in scene.collider_list]
     nearest = reduce(np.minimum, dists)
