@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Headline benchmark: Cornell box, 1920x1080, 256 samples per pixel (BASELINE.json configs[3]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # CPU arm (oracle port of the reference)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU
+
+One *step* renders the whole frame once (primary-ray generation, brute-force intersection, shading,
+importance-sampled bounces, accumulation, tonemap).  With N ranks the frame's samples are split into
+N contiguous ranges (sightpy/parallel.py), the float accumulation buffers are summed on rank 0 with
+one NCCL reduce and rank 0 tonemaps: total work is fixed, i.e. strong scaling.
+
+Metric: Mrays/s = rays traced against the collider list (primary + secondary, the reference's
+sum of len(ray) over get_raycolor calls; shadow rays not counted) / second.
+  value  scene already resident on the GPU, frame resolved on the device (no copy-out)
+  e2e    Scene.render() through the public API: scene flattened + uploaded from host memory and the
+         uint8 frame copied back to the host inside the timed region, every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+for p in (REPO, REPO / "python-raytracer_b200", REPO / "tests"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+WIDTH, HEIGHT, SPP = 1920, 1080, 256
+# algorithmic flops of one ray against the Cornell collider list
+# (6 bounded planes x 35 + 1 oriented cuboid x 55 + 1 sphere x 21); queue record = 48 B each way.
+FLOP_PER_RAY_CORNELL = 6 * 35 + 55 + 21
+METRIC = "Mrays/sec (primary+secondary), Cornell box 1920x1080 256spp"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--chunk", type=int, default=0, help="primaries per wavefront chunk (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---- clocks --------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md 'clocks line')."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU arm: the oracle port of the reference on the host cores ----------------------------------
+def _oracle_worker(job):
+    width, height, sample, seed = job
+    import scenes
+    import sightpy
+    from oracle.sightpy_oracle import Oracle
+    from sightpy.flatten import flatten_scene
+    flat = flatten_scene(scenes.cornell(sightpy, width=width, height=height))
+    orc = Oracle(flat, rng="philox", seed=seed)
+    t0 = time.perf_counter()
+    orc.render_linear(1, sample_begin=sample)
+    return orc.rays_total, time.perf_counter() - t0
+
+
+def cpu_sample(width, height, n_samples, processes):
+    """Cornell box at width x height, n_samples samples per pixel spread over `processes` workers.
+    Returns (rays, seconds)."""
+    jobs = [(width, height, s, 0) for s in range(n_samples)]
+    t0 = time.perf_counter()
+    if processes == 1:
+        res = [_oracle_worker(j) for j in jobs]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(processes) as pool:
+            pool.map(_oracle_worker, jobs[:processes])          # spin-up (imports) outside the timing
+            t0 = time.perf_counter()
+            res = pool.map(_oracle_worker, jobs)
+    return sum(r for r, _ in res), time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    w, h = 240, 135                       # 1/8-scale frame: ~1.9 M rays per sample (~5 s per core)
+    for _ in range(args.warmup):
+        cpu_sample(w // 4, h // 4, cores, cores)
+    rays = secs = 0.0
+    for _ in range(args.steps):
+        r, s = cpu_sample(w, h, cores, cores)
+        rays += r; secs += s
+    value = rays / secs / 1e6
+    sample = f"Cornell box {w}x{h}, {cores} spp per step (one sample per worker process), float64 numpy oracle"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "example_cornellbox.py scene, 1920x1080, 256 spp (timed on a bounded sample)",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---- native arm --------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["SIGHTPY_DEVICE"] = str(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import scenes
+    import sightpy
+    from sightpy import parallel
+    from sightpy.backend import NativeScene, measure_peaks
+    from sightpy.flatten import flatten_scene
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    scene = scenes.cornell(sightpy, width=args.width, height=args.height)
+    flat = flatten_scene(scene)
+    native = NativeScene(flat)
+    if args.chunk:
+        native.set_option("chunk_primaries", args.chunk)
+    stream = torch.cuda.current_stream()
+    native.set_stream(stream.cuda_stream)
+    begin, end = parallel.sample_range(args.spp, rank, world)
+    acc = parallel.accum_as_tensor(native) if world > 1 else None
+
+    def step():
+        """Device-resident frame: this rank's samples, reduce, resolve on the device."""
+        st = native.render_samples(begin, end, seed=0, clear=True)
+        if world > 1:
+            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            native.resolve_on_device(args.spp)
+        return st
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    totals = {"rays": 0, "launches": 0, "level_ms": 0.0, "level_launches": 0, "queue_bytes": 0, "shadow": 0}
+    per_depth = None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_wall = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            st = step()
+            totals["rays"] += st["rays_total"]; totals["launches"] += st["kernel_launches"] + (1 if rank == 0 else 0)
+            totals["level_ms"] += st["level_kernel_ms"]; totals["level_launches"] += st["level_kernel_launches"]
+            totals["queue_bytes"] += st["queue_bytes"]; totals["shadow"] += st["shadow_rays"]
+            per_depth = st["rays_per_depth"]
+        ev1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t_wall
+    dev_ms = ev0.elapsed_time(ev1)
+    clock_summary = clocks.summary()
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        return t.item()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    job_ms = allmax(dev_ms)
+    job_rays = allsum(totals["rays"])
+    job_launches = int(allsum(totals["launches"]))
+    value = job_rays / (job_ms * 1e-3) / 1e6
+
+    # ---- end to end through the public API ---------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        scene.seed = 0
+        e2e_rays = 0
+
+        def e2e_step():
+            scene.invalidate()                       # forget the device copy: flatten + upload again
+            img = scene.render(samples_per_pixel=args.spp)
+            return img, scene.last_stats["rays_total"]
+
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = max(1, min(args.steps, 2))
+            for _ in range(n_e2e):
+                img, r = e2e_step()
+                e2e_rays += r
+            barrier()
+            e2e_s = time.perf_counter() - t0
+        e2e_s = allmax(e2e_s)
+        h2d = sum(getattr(flat, k).nbytes for k in ("materials", "primitives", "colliders", "lights", "importance",
+                                                      "shadow_colliders", "media", "ambient")) + flat.camera.nbytes \
+            + sum(t.u8.nbytes for t in flat.textures)
+        e2e = {"value": allsum(e2e_rays) / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(args.width * args.height * 3), "steps": n_e2e,
+               "s_per_frame": e2e_s / n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the fused level kernel) -------------------------------------
+    peaks_file = REPO / "MEASURED_PEAKS.json"
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if peaks_file.exists():
+        hbm_peak, hbm_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    live = measure_peaks()
+    level_s = totals["level_ms"] * 1e-3
+    n_launch = max(totals["level_launches"], 1)
+    flops = FLOP_PER_RAY_CORNELL * totals["rays"]
+    roofline = {
+        "bound": "fp32", "kernel": "sp_level_kernel",
+        "achieved": flops / level_s / 1e12, "peak": live["fp32_tflops"], "unit": "TFLOP/s",
+        "frac": flops / level_s / 1e12 / live["fp32_tflops"],
+        "peak_source": "FFMA chain micro-benchmark run by this process (sp_measure_peaks); MEASURED_PEAKS.json has no FP32 entry",
+        "flop_per_ray": FLOP_PER_RAY_CORNELL, "rays_per_launch": totals["rays"] / n_launch,
+        "avg_launch_ms": totals["level_ms"] / n_launch, "traffic": None,
+    }
+    roofline_hbm = {
+        "bound": "hbm", "kernel": "sp_level_kernel (queue records only)",
+        "achieved": totals["queue_bytes"] / level_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": totals["queue_bytes"] / level_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+        "bytes_per_record": 96, "traffic": None,
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        w, h = 320, 180
+        r, s = cpu_sample(w, h, 2, 1)
+        cpu = {"value": r / s / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+               "sample": f"Cornell box {w}x{h}, 2 spp, float64 numpy oracle, single process"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": job_ms / args.steps, "s_per_frame": job_ms / args.steps / 1e3,
+        "wall_ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"example_cornellbox.py scene, {args.width}x{args.height}, {args.spp} spp "
+                               f"(BASELINE.json configs[3])",
+                   "sharding": f"{world} contiguous sample ranges, NCCL reduce of the float4 accumulation buffer",
+                   "rays_per_frame": job_rays / args.steps, "rays_per_depth_rank0": per_depth,
+                   "l2": "wavefront queues are several GB per chunk, far larger than the 126 MB L2"},
+        "e2e": e2e, "gpu_launches": job_launches, "clocks": clock_summary,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+        "shadow_rays": totals["shadow"],
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -162,8 +162,12 @@ int  sp_render_samples(sp_scene*, int sample_begin, int sample_end, uint64_t see
                        sp_stats* stats);
 void*    sp_accum_device_ptr(sp_scene*);      /* float4[H*W] on the scene's device                 */
 uint64_t sp_accum_bytes(sp_scene*);
-/* Resolve the accumulation buffer: divide by spp_total, tonemap, copy to the host buffers. */
+/* Resolve the accumulation buffer: divide by spp_total, tonemap (on the device), then copy to
+ * whichever host buffers are non-NULL. */
 int  sp_resolve(sp_scene*, int spp_total, float* out_linear_rgb, uint8_t* out_srgb8);
+/* Enqueue this scene's work on a caller-owned CUDA stream (a cudaStream_t, e.g. the stream an NCCL
+ * reduce of sp_accum_device_ptr is ordered on); use_it == 0 returns to the library's own stream. */
+int  sp_scene_set_stream(sp_scene*, void* cuda_stream, int use_it);
 
 /* sp_trace == get_raycolor(Ray(o, d, depth 0, scene.n), scene) (ray.py:122-148) on caller rays:
  * n rays, origins/directions as n x 3 interleaved floats.  Outputs (each nullable): linear

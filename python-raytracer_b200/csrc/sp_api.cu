@@ -68,6 +68,8 @@ struct sp_scene {
     std::vector<double> media_re, media_im;
     sp_camera cam{};
     bool has_camera = false, committed = false;
+    bool user_stream_set = false;
+    cudaStream_t user_stream = nullptr;
     std::vector<HostTexture> textures;
     std::vector<sp_material> mats;
     std::vector<sp_primitive> prims;
@@ -79,7 +81,10 @@ struct sp_scene {
     // ---- device residency -----------------------------------------------------------------------------
     DScene d{};
     int n_levels = 1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // where all work of this scene is enqueued
+    cudaStream_t own_stream = nullptr;  // the library's default stream for it
+    DevBuf<float> d_lin;                // resolve outputs (device copies, reused across frames)
+    DevBuf<uint8_t> d_u8;
     std::vector<cudaEvent_t> events;
     DevBuf<float4> geom_all, geom_shadow, accum;
     DevBuf<int> off_all, off_shadow;
@@ -109,8 +114,10 @@ struct sp_scene {
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
         for (auto e : events) cudaEventDestroy(e);
         events.clear();
-        if (stream) cudaStreamDestroy(stream);
+        if (own_stream) cudaStreamDestroy(own_stream);
+        own_stream = nullptr;
         stream = nullptr;
+        d_lin.release(); d_u8.release();
         ray_cap = fan_cap = 0;
     }
 };
@@ -411,7 +418,8 @@ int sp_scene_commit(sp_scene* s) {
 
     s->release_device();
     CUDA_TRY(cudaSetDevice(g_device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->user_stream_set ? s->user_stream : s->own_stream;
     DScene& d = s->d;
     memset(&d, 0, sizeof d);
 
@@ -720,20 +728,26 @@ int sp_resolve(sp_scene* s, int spp_total, float* out_linear, uint8_t* out_srgb8
     if (spp_total < 1) return fail("sp_resolve: spp_total must be >= 1");
     CUDA_TRY(cudaSetDevice(g_device));
     const size_t n = s->accum.n;
-    DevBuf<float> d_lin;
-    DevBuf<uint8_t> d_u8;
-    if (out_linear) CUDA_TRY(d_lin.alloc(3 * n));
-    if (out_srgb8) CUDA_TRY(d_u8.alloc(3 * n));
+    if (s->d_lin.n != 3 * n) CUDA_TRY(s->d_lin.alloc(3 * n));
+    if (s->d_u8.n != 3 * n) CUDA_TRY(s->d_u8.alloc(3 * n));
     ResolveArgs a;
-    a.accum = s->accum.p; a.n_pix = (uint32_t)n; a.spp = (double)spp_total; a.out_linear = d_lin.p; a.out_srgb8 = d_u8.p;
-    int rc = 0;
-    cudaError_t e = sp_launch_resolve(a, s->stream);
-    if (e == cudaSuccess && out_linear) e = cudaMemcpyAsync(out_linear, d_lin.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
-    if (e == cudaSuccess && out_srgb8) e = cudaMemcpyAsync(out_srgb8, d_u8.p, 3 * n, cudaMemcpyDeviceToHost, s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    if (e != cudaSuccess) rc = fail("sp_resolve: %s", cudaGetErrorString(e));
-    d_lin.release(); d_u8.release();
-    return rc;
+    a.accum = s->accum.p; a.n_pix = (uint32_t)n; a.spp = (double)spp_total; a.out_linear = s->d_lin.p; a.out_srgb8 = s->d_u8.p;
+    CUDA_TRY(sp_launch_resolve(a, s->stream));
+    if (out_linear) CUDA_TRY(cudaMemcpyAsync(out_linear, s->d_lin.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (out_srgb8) CUDA_TRY(cudaMemcpyAsync(out_srgb8, s->d_u8.p, 3 * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int sp_scene_set_stream(sp_scene* s, void* cuda_stream, int use_it) {
+    if (!s) return fail("sp_scene_set_stream: null scene");
+    s->user_stream_set = use_it != 0;
+    s->user_stream = (cudaStream_t)cuda_stream;
+    if (s->committed) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        s->stream = s->user_stream_set ? s->user_stream : s->own_stream;
+    }
+    return 0;
 }
 
 int sp_render(sp_scene* s, int spp, uint64_t seed, float* out_linear, uint8_t* out_srgb8, sp_stats* st) {

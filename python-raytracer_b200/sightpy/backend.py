@@ -87,6 +87,7 @@ def load_library():
         "sp_accum_device_ptr": (vp, [vp]),
         "sp_accum_bytes": (u64, [vp]),
         "sp_resolve": (i32, [vp, i32, vp, vp]),
+        "sp_scene_set_stream": (i32, [vp, vp, i32]),
         "sp_trace": (i32, [vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(Stats)]),
         "sp_camera_rays": (i32, [vp, i32, u64, vp, vp]),
         "sp_distances": (i32, [vp, u64, vp]),
@@ -205,6 +206,15 @@ class NativeScene:
 
     def accum_pointer(self):
         return int(self.lib.sp_accum_device_ptr(self.handle)), int(self.lib.sp_accum_bytes(self.handle))
+
+    def set_stream(self, cuda_stream):
+        """Run this scene's kernels on a caller-owned stream (int handle); None = library stream."""
+        _check(self.lib, self.lib.sp_scene_set_stream(self.handle, C.c_void_p(cuda_stream or 0),
+                                                      int(cuda_stream is not None)), "sp_scene_set_stream")
+
+    def resolve_on_device(self, spp_total):
+        """Average + tonemap into the library's device buffers without copying the frame out."""
+        _check(self.lib, self.lib.sp_resolve(self.handle, int(spp_total), None, None), "sp_resolve")
 
     def resolve(self, spp_total, want_linear=True):
         srgb = np.empty((self.height, self.width, 3), dtype=np.uint8)

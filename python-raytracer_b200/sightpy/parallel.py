@@ -53,12 +53,14 @@ def render_frame(native, spp, seed=0, want_linear=False):
     if size == 1:
         srgb, lin, stats = native.render(spp, seed, want_linear=want_linear)
         return (srgb, stats) if not want_linear else (srgb, lin, stats)
+    import torch
     import torch.distributed as dist
+    # same stream as the collective: the reduce is ordered after the last level kernel
+    native.set_stream(torch.cuda.current_stream().cuda_stream)
     begin, end = sample_range(spp, rank, size)
     stats = native.render_samples(begin, end, seed, clear=True)
     acc = accum_as_tensor(native)
     dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
-    import torch
-    torch.cuda.synchronize()
+    torch.cuda.current_stream().synchronize()
     srgb, lin = native.resolve(spp, want_linear=want_linear)
     return (srgb, stats) if not want_linear else (srgb, lin, stats)
