@@ -212,6 +212,16 @@ class NativeScene:
         _check(self.lib, self.lib.sp_scene_set_stream(self.handle, C.c_void_p(cuda_stream or 0),
                                                       int(cuda_stream is not None)), "sp_scene_set_stream")
 
+    def use_current_stream(self):
+        """Enqueue on torch's current CUDA stream (so that a following NCCL collective is ordered)."""
+        import torch
+        self.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def accum_tensor(self):
+        """torch.float32 view (no copy) of the device accumulation buffer (float4 per pixel)."""
+        from .parallel import accum_as_tensor
+        return accum_as_tensor(self)
+
     def resolve_on_device(self, spp_total):
         """Average + tonemap into the library's device buffers without copying the frame out."""
         _check(self.lib, self.lib.sp_resolve(self.handle, int(spp_total), None, None), "sp_resolve")

@@ -48,19 +48,20 @@ def accum_as_tensor(native):
 
 def render_frame(native, spp, seed=0, want_linear=False):
     """Render one frame with every rank of the job.  Returns (uint8 H x W x 3, stats) — on ranks
-    other than 0 the image is the rank-local (unreduced) resolve and only rank 0's is the frame."""
+    other than 0 the image is the rank-local (unreduced) resolve and only rank 0's is the frame.
+
+    ``native`` is a backend.NativeScene, or any object with the same ``render`` / ``render_samples`` /
+    ``accum_tensor`` / ``resolve`` / ``use_current_stream`` methods (the CPU tests drive this function
+    with a gloo group and a stand-in scene)."""
     rank, size = world()
     if size == 1:
         srgb, lin, stats = native.render(spp, seed, want_linear=want_linear)
         return (srgb, stats) if not want_linear else (srgb, lin, stats)
-    import torch
     import torch.distributed as dist
-    # same stream as the collective: the reduce is ordered after the last level kernel
-    native.set_stream(torch.cuda.current_stream().cuda_stream)
+    native.use_current_stream()      # same stream as the collective: the reduce is ordered after the last level kernel
     begin, end = sample_range(spp, rank, size)
     stats = native.render_samples(begin, end, seed, clear=True)
-    acc = accum_as_tensor(native)
+    acc = native.accum_tensor()
     dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
-    torch.cuda.current_stream().synchronize()
-    srgb, lin = native.resolve(spp, want_linear=want_linear)
+    srgb, lin = native.resolve(spp, want_linear=want_linear)     # synchronises the stream first
     return (srgb, stats) if not want_linear else (srgb, lin, stats)
