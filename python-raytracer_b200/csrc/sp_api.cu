@@ -90,6 +90,7 @@ struct sp_scene {
     DevBuf<int> off_all, off_shadow;
     DevBuf<int2> slot_all, slot_shadow;
     DevBuf<DCollider> d_cols;
+    DevBuf<DColInfo> d_colinfo;
     DevBuf<double> d_cols_d;
     DevBuf<DPrimitive> d_prims;
     DevBuf<DMaterial> d_mats;
@@ -109,7 +110,7 @@ struct sp_scene {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
         geom_all.release(); geom_shadow.release(); accum.release(); off_all.release(); off_shadow.release();
-        slot_all.release(); slot_shadow.release(); d_cols.release(); d_cols_d.release(); d_prims.release();
+        slot_all.release(); slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
         for (auto e : events) cudaEventDestroy(e);
@@ -479,6 +480,17 @@ int sp_scene_commit(sp_scene* s) {
         for (int k = 0; k < 40; ++k) { dc[i].p[k] = (float)s->cols[i].p[k]; dcd[(size_t)i * 40 + k] = s->cols[i].p[k]; }
     }
     CUDA_TRY(s->d_cols.upload(dc));
+    std::vector<DColInfo> dinfo((size_t)n_col);
+    for (int i = 0; i < n_col; ++i) {
+        const sp_primitive& pr = s->prims[s->cols[i].primitive];
+        const sp_material& m = s->mats[pr.material];
+        DColInfo& ci = dinfo[i];
+        ci.type = (uint8_t)s->cols[i].type; ci.kind = (uint8_t)m.kind; ci.mc = pr.mc ? 1 : 0;
+        ci.fan_class = (uint8_t)dm[pr.material].fan_class;
+        ci.max_ray_depth = (int16_t)pr.max_ray_depth; ci.max_dr = (int16_t)m.max_diffuse_reflections;
+        ci.mat = pr.material; ci.w_cos = (float)m.ambient_weight;
+    }
+    CUDA_TRY(s->d_colinfo.upload(dinfo));
     CUDA_TRY(s->d_cols_d.upload(dcd));
 
     // ---- textures ---------------------------------------------------------------------------------------
@@ -518,7 +530,7 @@ int sp_scene_commit(sp_scene* s) {
     d.shadow.data = s->geom_shadow.p; d.shadow.chunk_off = s->off_shadow.p;
     d.shadow.n_chunks = (int)shadow.chunk_off.size() - 1; d.shadow.n_items = shadow.n_items;
 
-    d.colliders = s->d_cols.p; d.colliders_d = s->d_cols_d.p; d.prims = s->d_prims.p; d.mats = s->d_mats.p;
+    d.colliders = s->d_cols.p; d.col_info = s->d_colinfo.p; d.colliders_d = s->d_cols_d.p; d.prims = s->d_prims.p; d.mats = s->d_mats.p;
     d.textures = s->d_texdesc.p; d.media = s->d_media.p;
     d.n_lights = (int)s->lights.size();
     for (int i = 0; i < d.n_lights; ++i) {

@@ -29,9 +29,26 @@ SP_DEV void sp_stage_chunk(float4* __restrict__ dst, const DScene& sc, const Geo
     for (int i = threadIdx.x; i < hi - lo; i += SP_BLOCK) dst[i] = __ldg(src + i);
 }
 
+// Per-CTA exchange area of one iteration (256 rays): the rays and their hits are parked here after
+// the intersection phase, regrouped by the material kind they hit, and picked up again by the
+// shading phase, so that the lanes of a warp shade the same material (the fused kernel would
+// otherwise run Diffuse / Refractive / Emissive code with a third of its lanes each).
+#define SP_STATE_WORDS 16
+#define SP_N_BINS 7              // the six material kinds + "nothing to shade"
+#define SP_N_QUEUES (1 + SP_MAX_FAN_CLASSES)
+#define SP_N_WARPS (SP_BLOCK / 32)
+struct IterShared {
+    uint32_t state[SP_STATE_WORDS][SP_BLOCK];      // SoA: o d thr pix path meta t (id|orient) ray_slot fan_slot
+    uint16_t perm[SP_BLOCK];                       // perm[j] = thread whose ray is shaded by thread j
+    uint32_t warp_cnt[SP_N_WARPS][16];             // per warp: [0..6] bins, [8..12] queue records
+    uint32_t queue_base[SP_N_QUEUES];              // CTA's reservation in each output queue
+    uint32_t n_shade;                              // rays with something to shade this iteration
+};
+
 __global__ void __launch_bounds__(SP_BLOCK, SP_CTAS_PER_SM)
 sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
     __shared__ float4 s_geom[SP_CHUNK_VEC4];
+    __shared__ IterShared sh;
 
     // ---- work items of this launch ---------------------------------------------------------
     uint32_t n_rays = 0, fan_n[SP_MAX_FAN_CLASSES];
@@ -59,14 +76,16 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         __syncthreads();
     }
 
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     ShadeCtx ctx;
-    ctx.sc = &sc; ctx.out = a.out; ctx.all_slot = a.all_slot; ctx.shadow_slot = a.shadow_slot;
+    ctx.sc = &sc; ctx.out = a.out; ctx.shadow_slot = a.shadow_slot;
     ctx.shadow_rays = 0;
     unsigned long long traced = 0;
 
     for (unsigned long long base = (unsigned long long)blockIdx.x * SP_BLOCK; base < total;
          base += (unsigned long long)gridDim.x * SP_BLOCK) {
-        const unsigned long long item = base + threadIdx.x;
+        const unsigned long long item = base + tid;
         bool active = item < total;
         Ray r;
         r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
@@ -91,9 +110,15 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
             } else if (item < n_rays) {
                 const uint32_t s = (uint32_t)item;
-                const float4 q0 = a.in_rays.q0[s], q1 = a.in_rays.q1[s], q2 = a.in_rays.q2[s];
-                r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
-                r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w); r.meta = __float_as_uint(q2.w);
+                const float4 q2 = a.in_rays.q2[s];
+                r.meta = __float_as_uint(q2.w);
+                if (r.meta == SP_META_DEAD) {
+                    active = false;
+                } else {
+                    const float4 q0 = a.in_rays.q0[s], q1 = a.in_rays.q1[s];
+                    r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
+                    r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
+                }
             } else {
                 unsigned long long local = item - n_rays;
                 int c = 0;
@@ -105,15 +130,20 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 const uint32_t m = (uint32_t)sc.fan_mult[c];
                 const uint32_t rec = (uint32_t)local / m, child = (uint32_t)local % m;
                 const uint32_t s = a.in_fan_base[c] + rec;
-                const float4 q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s], q2 = a.in_fans.q2[s];
-                r.o = xyz(q0); r.thr = xyz(q2);
-                r.pix = __float_as_uint(q0.w); r.meta = __float_as_uint(q2.w);
-                r.path = sp_child_path(__float_as_uint(q1.w), child);
-                const DCollider& sc_col = sc.colliders[meta_src(r.meta)];
-                const float w_cos = sc.mats[sc.prims[sc_col.prim].material].ambient_weight;
-                const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), w_cos, r.pix, r.path, r.d);
-                r.thr = r.thr * weight;
-                active = weight > 0.f;          // zero-weight samples cannot contribute: not traced
+                const float4 q2 = a.in_fans.q2[s];
+                r.meta = __float_as_uint(q2.w);
+                if (r.meta == SP_META_DEAD) {
+                    active = false;
+                } else {
+                    const float4 q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
+                    r.o = xyz(q0); r.thr = xyz(q2);
+                    r.pix = __float_as_uint(q0.w);
+                    r.path = sp_child_path(__float_as_uint(q1.w), child);
+                    const float w_cos = __ldg(&sc.col_info[meta_src(r.meta)].w_cos);
+                    const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), w_cos, r.pix, r.path, r.d);
+                    r.thr = r.thr * weight;
+                    active = weight > 0.f;          // zero-weight samples cannot contribute: not traced
+                }
             }
         }
         if (a.run == SP_RUN_DUMP_RAYS) {
@@ -127,67 +157,174 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
 
         // ---- 2. nearest hit over all colliders ------------------------------------------------------
         HitRec hit; hit.t = SP_INF; hit.id = -1; hit.orient = 0;
-        const uint32_t src = meta_src(r.meta), mode = meta_mode(r.meta);
-        int2 where = make_int2(-1, -1);
-        bool need_test = active;
-        if (active && src != SP_SRC_NONE) {
-            if (mode == SP_SELF_ZERO) {
-                // the ray dives back into the surface it starts on: the reference re-hits it after
-                // ~1e-6 (its nudge); here that is an immediate hit at t = 0
-                const DCollider& c0 = sc.colliders[src];
-                float3 Nc = to_f3(sp_collider_normal<float>(c0.type, c0.p, from_f3<float>(r.o)));
-                hit.t = 0.f; hit.id = (int)src; hit.orient = dot(r.d, Nc) < 0.f ? 1 : -1;
-                need_test = false;
-            } else {
-                where = __ldg(a.all_slot + src);
-            }
-        }
-        for (int c = 0; c < n_chunks; ++c) {
-            if (n_chunks > 1) {
-                __syncthreads();
-                sp_stage_chunk(s_geom, sc, sc.all, c);
-                __syncthreads();
-            }
-            if (need_test) {
-                SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = -1; self.mode = mode;
-                if (where.x == c) {
-                    const int ty = where.y >> 28, li = where.y & 0x0FFFFFFF;
-                    if (ty == 0) self.sphere = li; else if (ty == 1) self.plane = li;
-                    else if (ty == 2) self.cuboid = li; else self.tri = li;
+        {
+            const uint32_t src = meta_src(r.meta), mode = meta_mode(r.meta);
+            int2 where = make_int2(-1, -1);
+            bool need_test = active;
+            if (active && src != SP_SRC_NONE) {
+                if (mode == SP_SELF_ZERO) {
+                    // the ray dives back into the surface it starts on: the reference re-hits it after
+                    // ~1e-6 (its nudge); here that is an immediate hit at t = 0
+                    const DCollider& c0 = sc.colliders[src];
+                    float3 Nc = to_f3(sp_collider_normal<float>(c0.type, c0.p, from_f3<float>(r.o)));
+                    hit.t = 0.f; hit.id = (int)src; hit.orient = dot(r.d, Nc) < 0.f ? 1 : -1;
+                    need_test = false;
+                } else {
+                    where = __ldg(a.all_slot + src);
                 }
-                ChunkBest best; best.t = hit.t; best.idx = -1; best.orient = 0;
-                sp_intersect_chunk(s_geom, r.o, r.d, self, best);
-                if (best.idx >= 0) { hit.t = best.t; hit.orient = best.orient; hit.id = sp_chunk_id(s_geom, best.idx); }
+            }
+            for (int c = 0; c < n_chunks; ++c) {
+                if (n_chunks > 1) {
+                    __syncthreads();
+                    sp_stage_chunk(s_geom, sc, sc.all, c);
+                    __syncthreads();
+                }
+                if (need_test) {
+                    SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = -1; self.mode = mode;
+                    if (where.x == c) {
+                        const int ty = where.y >> 28, li = where.y & 0x0FFFFFFF;
+                        if (ty == 0) self.sphere = li; else if (ty == 1) self.plane = li;
+                        else if (ty == 2) self.cuboid = li; else self.tri = li;
+                    }
+                    ChunkBest best; best.t = hit.t; best.idx = -1; best.orient = 0;
+                    sp_intersect_chunk(s_geom, r.o, r.d, self, best);
+                    if (best.idx >= 0) { hit.t = best.t; hit.orient = best.orient; hit.id = sp_chunk_id(s_geom, best.idx); }
+                }
             }
         }
-        if (!active) continue;
-        traced += 1;
-
-        if (a.level == 0) {
-            const size_t oi = (a.source == SP_SRC_USER) ? (size_t)a.user_base + (size_t)item : (size_t)item;
-            if (a.out_hit) a.out_hit[oi] = hit.id;
-            if (a.out_t) a.out_t[oi] = hit.t;
+        if (active) {
+            traced += 1;
+            if (a.level == 0) {
+                const size_t oi = (a.source == SP_SRC_USER) ? (size_t)a.user_base + (size_t)item : (size_t)item;
+                if (a.out_hit) a.out_hit[oi] = hit.id;
+                if (a.out_t) a.out_t[oi] = hit.t;
+            }
         }
-        if (a.run == SP_RUN_DISTANCES || hit.id < 0) continue;
+        if (a.run == SP_RUN_DISTANCES) continue;
 
-        // ---- 3. shade, accumulate, emit children ------------------------------------------------------
-        const float3 add = sp_shade(ctx, r, hit);
-        float* px = reinterpret_cast<float*>(a.accum + r.pix);
-        if (add.x != 0.f) atomicAdd(px, add.x);
-        if (add.y != 0.f) atomicAdd(px + 1, add.y);
-        if (add.z != 0.f) atomicAdd(px + 2, add.z);
+        // ---- 3. what the hit will emit; per-warp counts of shading bins and queue records ---------------
+        int bin = SP_N_BINS - 1, n_ray = 0, fan_class = -1;
+        if (active && hit.id >= 0) {
+            const float4 raw = __ldg(reinterpret_cast<const float4*>(sc.col_info + hit.id));
+            const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
+            bin = ci.kind;
+            sp_child_needs(ci, meta_depth(r.meta), meta_dr(r.meta), n_ray, fan_class);
+        }
+        if (lane < 16) sh.warp_cnt[warp][lane] = 0u;
+        __syncwarp();
+        const uint32_t bin_peers = __match_any_sync(0xffffffffu, bin);
+        const uint32_t bin_rank = __popc(bin_peers & lt_mask);
+        if (bin_rank == 0) sh.warp_cnt[warp][bin] = __popc(bin_peers);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, n_ray & 1), b1 = __ballot_sync(0xffffffffu, n_ray & 2);
+        const uint32_t ray_rank = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
+        if (lane == 0) sh.warp_cnt[warp][8] = __popc(b0) + 2u * __popc(b1);
+        uint32_t fan_rank = 0;
+#pragma unroll
+        for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) {
+            if (c < sc.n_fan_classes) {
+                const uint32_t bc = __ballot_sync(0xffffffffu, fan_class == c);
+                if (fan_class == c) fan_rank = __popc(bc & lt_mask);
+                if (lane == 0) sh.warp_cnt[warp][9 + c] = __popc(bc);
+            }
+        }
+        __syncthreads();                                                            // (A) counts visible
+
+        // every warp derives the CTA-wide offsets it needs from the 8 x 16 count table:
+        // lane l < 16 owns column l (a bin or a queue)
+        uint32_t col_total = 0, col_before = 0;
+        if (lane < 16) {
+#pragma unroll
+            for (int w = 0; w < SP_N_WARPS; ++w) {
+                const uint32_t v = sh.warp_cnt[w][lane];
+                if ((uint32_t)w < warp) col_before += v;
+                col_total += v;
+            }
+        }
+        // exclusive scan of the bin totals over lanes 0..6 (bins are laid out one after the other)
+        uint32_t bin_start = (lane < SP_N_BINS) ? col_total : 0u;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, bin_start, o);
+            if (lane >= (uint32_t)o && lane < 8) bin_start += up;
+        }
+        bin_start -= (lane < SP_N_BINS) ? col_total : 0u;
+        const uint32_t my_dest = __shfl_sync(0xffffffffu, bin_start + col_before, bin) + bin_rank;
+        const uint32_t ray_before = __shfl_sync(0xffffffffu, col_before, 8);
+        const uint32_t fan_before = __shfl_sync(0xffffffffu, col_before, 9 + max(fan_class, 0));
+        if (warp == 0) {
+            // one reservation per output queue for the whole CTA
+            if (lane >= 8 && lane < 8 + SP_N_QUEUES) {
+                const int q = (int)lane - 8;
+                const uint32_t cap = (q == 0) ? a.out.rays.capacity : a.out.fan_cap[q - 1];
+                uint32_t first = SP_SLOT_NONE;
+                if (col_total > 0) {
+                    first = atomicAdd(a.out.counts + q, col_total);
+                    if (first + col_total > cap) { first = SP_SLOT_NONE; a.out.stats->overflow = 1u; }
+                    else if (q > 0) first += a.out.fan_base[q - 1];
+                }
+                sh.queue_base[q] = first;
+            }
+            if (lane == SP_N_BINS - 1) sh.n_shade = bin_start;     // start of the "nothing" bin = rays to shade
+        }
+        // park the ray and its hit
+        sh.perm[my_dest] = (uint16_t)tid;
+        sh.state[0][tid] = __float_as_uint(r.o.x); sh.state[1][tid] = __float_as_uint(r.o.y); sh.state[2][tid] = __float_as_uint(r.o.z);
+        sh.state[3][tid] = __float_as_uint(r.d.x); sh.state[4][tid] = __float_as_uint(r.d.y); sh.state[5][tid] = __float_as_uint(r.d.z);
+        sh.state[6][tid] = __float_as_uint(r.thr.x); sh.state[7][tid] = __float_as_uint(r.thr.y); sh.state[8][tid] = __float_as_uint(r.thr.z);
+        sh.state[9][tid] = r.pix; sh.state[10][tid] = r.path; sh.state[11][tid] = r.meta;
+        sh.state[12][tid] = __float_as_uint(hit.t);
+        sh.state[13][tid] = (uint32_t)hit.id | (hit.orient > 0 ? 0x80000000u : 0u);
+        sh.state[14][tid] = (uint32_t)n_ray | ((ray_before + ray_rank) << 2);
+        sh.state[15][tid] = fan_class < 0 ? SP_SLOT_NONE : (((uint32_t)fan_class << 28) | (fan_before + fan_rank));
+        __syncthreads();                                                            // (B) state, perm, bases visible
+
+        // ---- 4. shade in material order, accumulate, write children -----------------------------------------
+        if (tid < sh.n_shade) {
+            const uint32_t j = sh.perm[tid];
+            Ray s;
+            s.o = v3(__uint_as_float(sh.state[0][j]), __uint_as_float(sh.state[1][j]), __uint_as_float(sh.state[2][j]));
+            s.d = v3(__uint_as_float(sh.state[3][j]), __uint_as_float(sh.state[4][j]), __uint_as_float(sh.state[5][j]));
+            s.thr = v3(__uint_as_float(sh.state[6][j]), __uint_as_float(sh.state[7][j]), __uint_as_float(sh.state[8][j]));
+            s.pix = sh.state[9][j]; s.path = sh.state[10][j]; s.meta = sh.state[11][j];
+            HitRec h;
+            h.t = __uint_as_float(sh.state[12][j]);
+            const uint32_t packed = sh.state[13][j];
+            h.id = (int)(packed & 0x7FFFFFFFu); h.orient = (packed & 0x80000000u) ? 1 : -1;
+            const uint32_t rs = sh.state[14][j], fs = sh.state[15][j];
+            const uint32_t need_ray = rs & 3u;
+            const uint32_t rbase = sh.queue_base[0];
+            ctx.ray_slot = (need_ray && rbase != SP_SLOT_NONE) ? rbase + (rs >> 2) : SP_SLOT_NONE;
+            ctx.ray_used = 0u;
+            ctx.fan_slot = SP_SLOT_NONE;
+            if (fs != SP_SLOT_NONE) {
+                const uint32_t fbase = sh.queue_base[1 + (fs >> 28)];
+                if (fbase != SP_SLOT_NONE) ctx.fan_slot = fbase + (fs & 0x0FFFFFFFu);
+            }
+            const float3 add = sp_shade(ctx, s, h);
+            float* px = reinterpret_cast<float*>(a.accum + s.pix);
+            if (add.x != 0.f) atomicAdd(px, add.x);
+            if (add.y != 0.f) atomicAdd(px + 1, add.y);
+            if (add.z != 0.f) atomicAdd(px + 2, add.z);
+            // reserved but unused slots become dead records
+            if (ctx.ray_slot != SP_SLOT_NONE)
+                for (uint32_t k = ctx.ray_used; k < need_ray; ++k) sp_write_dead(a.out.rays, ctx.ray_slot + k);
+            if (ctx.fan_slot != SP_SLOT_NONE) sp_write_dead(a.out.fans, ctx.fan_slot);
+        }
+        // the next iteration's writes to `sh` happen after its own barrier (A) ... except warp_cnt and
+        // perm/state, which a fast warp could overwrite while a slow one still shades: fence here
+        __syncthreads();                                                            // (C)
     }
 
     // ---- counters: one atomic per warp -------------------------------------------------------------
-    unsigned long long sh = ctx.shadow_rays;
+    unsigned long long shr = ctx.shadow_rays;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         traced += __shfl_down_sync(0xffffffffu, traced, o);
-        sh += __shfl_down_sync(0xffffffffu, sh, o);
+        shr += __shfl_down_sync(0xffffffffu, shr, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (traced) atomicAdd(&a.out.stats->rays[a.level], traced);
-        if (sh) atomicAdd(&a.out.stats->shadow_rays, sh);
+        if (shr) atomicAdd(&a.out.stats->shadow_rays, shr);
     }
 }
 

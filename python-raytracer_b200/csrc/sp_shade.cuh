@@ -8,12 +8,10 @@
 // diffuse.py:25-124 (its sampling half lives in sp_sampling.cuh), emissive.py:21-23,
 // skybox.py:51-94, material.py:18-36, lights.py:25-52.
 #pragma once
-#include <cooperative_groups.h>
 #include "sp_geometry.cuh"
 #include "sp_rng.cuh"
 #include "sp_surface.cuh"
 
-namespace cg = cooperative_groups;
 
 __constant__ float c_decode[2][256];      // texel byte -> value (SP_DECODE_PLAIN / SP_DECODE_LINEAR)
 
@@ -23,24 +21,38 @@ struct Ray {
 };
 
 
-// ---- queue append with warp-aggregated slot allocation (one atomic per converged group) --------
-SP_DEV void sp_push(const RayQueue& q, uint32_t* counter, uint32_t base, uint32_t cap, DeviceStats* stats,
-                    float3 o, float3 v, float3 thr, uint32_t pix, uint32_t path, uint32_t meta) {
-    // lanes that arrive here together may target different queues (ray queue / fan class):
-    // aggregate per distinct counter
-    const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, (unsigned long long)counter);
-    const unsigned lane = threadIdx.x & 31u;
-    const int leader = __ffs(peers) - 1;
-    uint32_t first = 0;
-    if ((int)lane == leader) first = atomicAdd(counter, (uint32_t)__popc(peers));
-    first = __shfl_sync(peers, first, leader);
-    uint32_t slot = first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    if (slot >= cap) { stats->overflow = 1u; return; }
-    slot += base;
+// ---- queue records ---------------------------------------------------------------------------------
+// Slots are reserved per CTA *before* shading from an upper bound of what each hit can emit
+// (sp_child_needs); a reserved slot whose child is not produced after all (zero throughput, total
+// internal reflection) is filled with a dead record that the consumer skips.
+#define SP_SLOT_NONE 0xFFFFFFFFu
+#define SP_META_DEAD 0xFFFFFFFFu
+
+SP_DEV void sp_write_record(const RayQueue& q, uint32_t slot, float3 o, float3 v, float3 thr, uint32_t pix,
+                            uint32_t path, uint32_t meta) {
     q.q0[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(pix));
     q.q1[slot] = make_float4(v.x, v.y, v.z, __uint_as_float(path));
     q.q2[slot] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(meta));
+}
+SP_DEV void sp_write_dead(const RayQueue& q, uint32_t slot) {
+    q.q2[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(SP_META_DEAD));
+}
+
+// Upper bound of the records a hit emits: n_ray explicit rays (0..2) and at most one fan record of
+// class fan_class (-1 = none).  Must stay in step with sp_shade below.
+SP_DEV void sp_child_needs(const DColInfo& ci, uint32_t depth, uint32_t dr, int& n_ray, int& fan_class) {
+    n_ray = 0; fan_class = -1;
+    const bool alive = (int)depth < (int)ci.max_ray_depth;
+    switch (ci.kind) {
+    case SP_MAT_GLOSSY: n_ray = alive ? 1 : 0; break;
+    case SP_MAT_REFRACTIVE: n_ray = alive ? (ci.mc ? 1 : 2) : 0; break;
+    case SP_MAT_THINFILM: n_ray = alive ? 2 : 0; break;
+    case SP_MAT_DIFFUSE:
+        if (dr < 1u) fan_class = ci.fan_class;
+        else if ((int)dr < (int)ci.max_dr) fan_class = 0;
+        break;
+    default: break;
+    }
 }
 
 SP_DEV float3 sp_fetch_texel(const DTexture& t, int offset) {
@@ -155,17 +167,20 @@ SP_DEV float sp_shadow_nearest(const DScene& sc, float3 o, float3 d, int src_id,
 struct ShadeCtx {
     const DScene* sc;
     LevelOut out;
-    const int2* all_slot;       // collider id -> (chunk, type << 28 | local index) in the full stream
-    const int2* shadow_slot;    // same for the shadow-caster stream ((-1,-1) if not a caster)
+    const int2* shadow_slot;    // collider id -> (chunk, type << 28 | local index) in the shadow-caster stream
     unsigned long long shadow_rays;
+    // slots reserved for the hit being shaded
+    uint32_t ray_slot, ray_used, fan_slot;
 };
 
 SP_DEV void sp_emit_ray(ShadeCtx& cx_, const Ray& r, float3 o, float3 d, float3 thr, uint32_t k,
                         uint32_t medium, uint32_t dr, int src, uint32_t mode) {
     if (!any_nonzero(thr)) return;          // zero-weight children cannot contribute
+    const uint32_t slot = cx_.ray_slot;
+    if (slot == SP_SLOT_NONE) return;       // the CTA's reservation overflowed the queue (reported to the host)
     uint32_t meta = sp_pack_meta(meta_depth(r.meta) + 1u, dr, medium, (uint32_t)src, mode);
-    sp_push(cx_.out.rays, cx_.out.counts, 0u, cx_.out.rays.capacity, cx_.out.stats, o, d, thr, r.pix,
-            sp_child_path(r.path, k), meta);
+    sp_write_record(cx_.out.rays, slot + cx_.ray_used, o, d, thr, r.pix, sp_child_path(r.path, k), meta);
+    cx_.ray_used += 1u;
 }
 
 // Shade one hit.  Returns the radiance to add to the ray's pixel (already times throughput).
@@ -222,8 +237,10 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
                 bool planar = (ctype == SP_COLLIDER_PLANE || ctype == SP_COLLIDER_TRIANGLE);
                 uint32_t mode = (planar || side_plus > 0.f) ? SP_SELF_SKIP : SP_SELF_FAR;
                 uint32_t meta = sp_pack_meta(depth + 1u, dr + 1u, medium, (uint32_t)h.id, mode);
-                sp_push(cx_.out.fans, cx_.out.counts + 1 + cls, cx_.out.fan_base[cls], cx_.out.fan_cap[cls],
-                        cx_.out.stats, nudged, N, thr, r.pix, r.path, meta);
+                if (cx_.fan_slot != SP_SLOT_NONE) {
+                    sp_write_record(cx_.out.fans, cx_.fan_slot, nudged, N, thr, r.pix, r.path, meta);
+                    cx_.fan_slot = SP_SLOT_NONE;            // consumed
+                }
             }
         }
         return add;

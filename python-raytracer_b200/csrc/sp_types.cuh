@@ -13,7 +13,7 @@
 // cuboid   : (B0.xyz, lo.x) (B1.xyz, lo.y) (B2.xyz, lo.z) (C.xyz, hi.x) (hi.y, hi.z, -, -)
 //            B = basis rows, lo/hi = box corners relative to B*C (so tests run on O - C)
 // triangle : 24 floats N, centroid, n31, p1, n12, p2, n23, p3
-#define SP_CHUNK_VEC4 2048            // 32 KB staging buffer
+#define SP_CHUNK_VEC4 1536            // 24 KB staging buffer (static shared memory is capped at 48 KB)
 #define SP_V4_SPHERE 1
 #define SP_V4_PLANE 4
 #define SP_V4_CUBOID 5
@@ -55,6 +55,16 @@ struct DMaterial {
     float thickness, noise_factor, ambient_weight, light_intensity;
 };
 
+// Everything the level kernel needs to know about the collider a ray hit before it shades it
+// (one 16-byte load): material kind, recursion limits, fan class, the cosine-pdf weight.
+struct DColInfo {
+    uint8_t type, kind, mc, fan_class;
+    int16_t max_ray_depth, max_dr;
+    int32_t mat;
+    float w_cos;
+};
+static_assert(sizeof(DColInfo) == 16, "one float4");
+
 struct DTexture {
     const uint32_t* texels;    // r | g << 8 | b << 16
     int H, W, decode, pad;
@@ -77,6 +87,7 @@ struct DCamera {
 struct DScene {
     GeomStream all, shadow;
     const DCollider* colliders;
+    const DColInfo* col_info;
     const double* colliders_d;     // [n][40] double payloads for the precise hit path
     const DPrimitive* prims;
     const DMaterial* mats;
