@@ -459,6 +459,10 @@ int sp_scene_commit(sp_scene* s) {
             }
         }
     }
+    for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) {
+        const unsigned long long mult = (unsigned long long)std::max(d.fan_mult[c], 1);
+        d.fan_magic[c] = mult == 1 ? 0ull : (~0ull) / mult + 1ull;         // ceil(2^64 / mult); mult == 1 is special-cased below
+    }
     CUDA_TRY(s->d_mats.upload(dm));
 
     std::vector<DPrimitive> dp((size_t)n_prim);
@@ -527,6 +531,8 @@ int sp_scene_commit(sp_scene* s) {
     CUDA_TRY(s->slot_shadow.upload(shadow.slot));
     d.all.data = s->geom_all.p; d.all.chunk_off = s->off_all.p;
     d.all.n_chunks = (int)all.chunk_off.size() - 1; d.all.n_items = all.n_items;
+    for (size_t c = 0; c + 1 < all.chunk_off.size(); ++c)
+        d.all.max_chunk_vec4 = std::max(d.all.max_chunk_vec4, all.chunk_off[c + 1] - all.chunk_off[c]);
     d.shadow.data = s->geom_shadow.p; d.shadow.chunk_off = s->off_shadow.p;
     d.shadow.n_chunks = (int)shadow.chunk_off.size() - 1; d.shadow.n_items = shadow.n_items;
 
@@ -537,6 +543,7 @@ int sp_scene_commit(sp_scene* s) {
         d.lights[i].kind = s->lights[i].kind; d.lights[i].vec = f3(s->lights[i].vec); d.lights[i].color = f3(s->lights[i].color);
     }
     d.n_importance = (int)s->importance.size();
+    d.inv_n_importance = d.n_importance ? 1.f / (float)d.n_importance : 0.f;
     for (int i = 0; i < d.n_importance; ++i) {
         const sp_primitive& p = s->prims[s->importance[i]];
         d.importance[i].center = f3(p.center); d.importance[i].radius = (float)p.bounded_sphere_radius;
@@ -555,7 +562,7 @@ int sp_scene_commit(sp_scene* s) {
     CUDA_TRY(s->d_stats.alloc(1));
     s->events.resize((size_t)s->n_levels + 1);
     for (auto& e : s->events) CUDA_TRY(cudaEventCreate(&e));
-    s->grid = sp_level_grid(g_device);
+    s->grid = sp_level_grid(g_device, s->d);
     s->use_ray = s->use_fan = 0.0;
     s->committed = true;
     return 0;

@@ -63,7 +63,7 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
             float nd = dot(N, D);
             nd = (nd == 0.f) ? 1e-4f : nd;
             float k = -dot(N, oc);
-            float t = k / nd;
+            float t = __fdividef(k, nd);
             float u = fmaf(t, dot(xyz(u4), D), dot(xyz(u4), oc));
             float v = fmaf(t, dot(xyz(v4), D), dot(xyz(v4), oc));
             bool ok = (fabsf(u) <= a.w) && (fabsf(v) <= c.w) && (k * nd > 0.f) && (i != self.plane);
@@ -78,7 +78,7 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
             float3 oc = O - xyz(c);
             float3 Ol = v3(dot(xyz(r0), oc), dot(xyz(r1), oc), dot(xyz(r2), oc));
             float3 Dl = v3(dot(xyz(r0), D), dot(xyz(r1), D), dot(xyz(r2), D));
-            float ix = 1.f / Dl.x, iy = 1.f / Dl.y, iz = 1.f / Dl.z;
+            float ix = __frcp_rn(Dl.x), iy = __frcp_rn(Dl.y), iz = __frcp_rn(Dl.z);   // +-inf for axis-parallel rays, as 1/0
             float t1 = (r0.w - Ol.x) * ix, t2 = (c.w - Ol.x) * ix;
             float t3 = (r1.w - Ol.y) * iy, t4 = (e.x - Ol.y) * iy;
             float t5 = (r2.w - Ol.z) * iz, t6 = (e.y - Ol.z) * iz;
@@ -105,7 +105,7 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
             float nd = dot(N, D);
             nd = (nd == 0.f) ? 1e-4f : nd;
             float k = -dot(N, O - cen);
-            float t = k / nd;
+            float t = __fdividef(k, nd);
             float e1 = fmaf(t, dot(n31, D), dot(n31, O - p1));
             float e2 = fmaf(t, dot(n12, D), dot(n12, O - p2));
             float e3 = fmaf(t, dot(n23, D), dot(n23, O - p3));

@@ -20,8 +20,12 @@
 #include "sp_sampling.cuh"
 #include "sp_shade.cuh"
 
+#ifndef SP_BLOCK
 #define SP_BLOCK 256
-#define SP_CTAS_PER_SM 2
+#endif
+#ifndef SP_CTAS_PER_SM
+#define SP_CTAS_PER_SM 3
+#endif
 
 SP_DEV void sp_stage_chunk(float4* __restrict__ dst, const DScene& sc, const GeomStream& gs, int c) {
     const int lo = __ldg(gs.chunk_off + c), hi = __ldg(gs.chunk_off + c + 1);
@@ -47,12 +51,12 @@ struct IterShared {
 
 __global__ void __launch_bounds__(SP_BLOCK, SP_CTAS_PER_SM)
 sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
-    __shared__ float4 s_geom[SP_CHUNK_VEC4];
-    __shared__ IterShared sh;
+    extern __shared__ float4 s_geom[];                 // sized by the host to the scene's largest chunk
+    __shared__ IterShared sh_buf[2];                   // double-buffered: no barrier at the end of an iteration
 
     // ---- work items of this launch ---------------------------------------------------------
     uint32_t n_rays = 0, fan_n[SP_MAX_FAN_CLASSES];
-    unsigned long long total;
+    uint32_t total;                                    // < 2^32 work items per launch (checked by the host)
 #pragma unroll
     for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) fan_n[c] = 0;
     if (a.source == SP_SRC_QUEUES) {
@@ -62,7 +66,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) {
             if (c < sc.n_fan_classes) {
                 fan_n[c] = min(__ldg(a.in_counts + 1 + c), a.in_fan_cap[c]);
-                total += (unsigned long long)fan_n[c] * (unsigned)sc.fan_mult[c];
+                total += fan_n[c] * (uint32_t)sc.fan_mult[c];
             }
         }
     } else {
@@ -79,14 +83,17 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     ShadeCtx ctx;
-    ctx.sc = &sc; ctx.out = a.out; ctx.shadow_slot = a.shadow_slot;
+    ctx.sc = &sc; ctx.out = &a.out; ctx.shadow_slot = a.shadow_slot;
     ctx.shadow_rays = 0;
     unsigned long long traced = 0;
 
-    for (unsigned long long base = (unsigned long long)blockIdx.x * SP_BLOCK; base < total;
-         base += (unsigned long long)gridDim.x * SP_BLOCK) {
-        const unsigned long long item = base + tid;
-        bool active = item < total;
+    uint32_t parity = 0;
+    for (unsigned long long base64 = (unsigned long long)blockIdx.x * SP_BLOCK; base64 < total;
+         base64 += (unsigned long long)gridDim.x * SP_BLOCK, parity ^= 1u) {
+        IterShared& sh = sh_buf[parity];
+        const uint32_t base = (uint32_t)base64;
+        const uint32_t item = base + tid;
+        bool active = (unsigned long long)base + tid < total;
         Ray r;
         r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
 
@@ -120,15 +127,16 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                     r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
                 }
             } else {
-                unsigned long long local = item - n_rays;
+                uint32_t local = item - n_rays;
                 int c = 0;
 #pragma unroll
                 for (int k = 0; k < SP_MAX_FAN_CLASSES - 1; ++k) {
-                    unsigned long long span = (unsigned long long)fan_n[k] * (unsigned)sc.fan_mult[k];
+                    const uint32_t span = fan_n[k] * (uint32_t)sc.fan_mult[k];
                     if (c == k && local >= span) { local -= span; c = k + 1; }
                 }
                 const uint32_t m = (uint32_t)sc.fan_mult[c];
-                const uint32_t rec = (uint32_t)local / m, child = (uint32_t)local % m;
+                const uint32_t rec = (m == 1u) ? local : (uint32_t)__umul64hi((unsigned long long)local, sc.fan_magic[c]);
+                const uint32_t child = local - rec * m;
                 const uint32_t s = a.in_fan_base[c] + rec;
                 const float4 q2 = a.in_fans.q2[s];
                 r.meta = __float_as_uint(q2.w);
@@ -310,9 +318,8 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 for (uint32_t k = ctx.ray_used; k < need_ray; ++k) sp_write_dead(a.out.rays, ctx.ray_slot + k);
             if (ctx.fan_slot != SP_SLOT_NONE) sp_write_dead(a.out.fans, ctx.fan_slot);
         }
-        // the next iteration's writes to `sh` happen after its own barrier (A) ... except warp_cnt and
-        // perm/state, which a fast warp could overwrite while a slow one still shades: fence here
-        __syncthreads();                                                            // (C)
+        // no barrier here: the next iteration works in the other IterShared buffer, and nobody can
+        // come back to this one before passing that iteration's barriers (A) and (B)
     }
 
     // ---- counters: one atomic per warp -------------------------------------------------------------
@@ -385,17 +392,20 @@ __global__ void __launch_bounds__(256) sp_copy_kernel(const float4* __restrict__
 // =================================================================================================
 // launchers
 // =================================================================================================
-int sp_level_grid(int device) {
+static size_t geom_smem_bytes(const DScene& sc) { return (size_t)sc.all.max_chunk_vec4 * sizeof(float4); }
+
+int sp_level_grid(int device, const DScene& sc) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaFuncSetAttribute(sp_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
     int per_sm = SP_CTAS_PER_SM;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_level_kernel, SP_BLOCK, 0) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_level_kernel, SP_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
         per_sm = 1;
     return sms * per_sm;
 }
 
 cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, int grid, cudaStream_t st) {
-    sp_level_kernel<<<grid, SP_BLOCK, 0, st>>>(sc, a);
+    sp_level_kernel<<<grid, SP_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
     return cudaGetLastError();
 }
 

@@ -37,7 +37,7 @@ struct ResolveArgs {
     uint8_t* out_srgb8;            // n_pix * 3 interleaved (nullable)
 };
 
-int sp_level_grid(int device);                       // CTAs of a persistent level launch
+int sp_level_grid(int device, const DScene& sc);      // CTAs of a persistent level launch
 cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, int grid, cudaStream_t st);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
 cudaError_t sp_upload_decode_tables(const float* plain256, const float* linear256);

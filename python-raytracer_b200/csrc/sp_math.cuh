@@ -49,7 +49,7 @@ SP_DEV cplx operator-(cplx a, cplx b) { return cx(a.re - b.re, a.im - b.im); }
 SP_DEV cplx operator*(cplx a, cplx b) { return cx(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
 SP_DEV cplx operator*(cplx a, float s) { return cx(a.re * s, a.im * s); }
 SP_DEV cplx operator/(cplx a, cplx b) {
-    float d = 1.f / (b.re * b.re + b.im * b.im);
+    float d = __frcp_rn(b.re * b.re + b.im * b.im);
     return cx((a.re * b.re + a.im * b.im) * d, (a.im * b.re - a.re * b.im) * d);
 }
 SP_DEV float cabs2(cplx a) { return a.re * a.re + a.im * a.im; }

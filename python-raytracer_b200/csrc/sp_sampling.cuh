@@ -74,9 +74,9 @@ SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float 
             float inv = rsqrtf(d2);
             float ratio = clamp01(sc.importance[i].radius * inv);
             float cmax = sqrtf(1.f - ratio * ratio);
-            if (dot(dir, to_c) * inv > cmax) caps += 1.f / ((1.f - cmax) * 2.f * SP_PI);
+            if (dot(dir, to_c) * inv > cmax) caps += __fdividef(1.f, (1.f - cmax) * 2.f * SP_PI);
         }
-        pdf = pdf * w_cos + (caps / (float)l) * (1.f - w_cos);
+        pdf = pdf * w_cos + (caps * sc.inv_n_importance) * (1.f - w_cos);
     }
-    return ndl / pdf * (1.f / SP_PI);
+    return __fdividef(ndl, pdf) * (1.f / SP_PI);
 }

@@ -166,7 +166,7 @@ SP_DEV float sp_shadow_nearest(const DScene& sc, float3 o, float3 d, int src_id,
 
 struct ShadeCtx {
     const DScene* sc;
-    LevelOut out;
+    const LevelOut* out;       // kernel parameter (constant bank), not copied into registers
     const int2* shadow_slot;    // collider id -> (chunk, type << 28 | local index) in the shadow-caster stream
     unsigned long long shadow_rays;
     // slots reserved for the hit being shaded
@@ -179,7 +179,7 @@ SP_DEV void sp_emit_ray(ShadeCtx& cx_, const Ray& r, float3 o, float3 d, float3 
     const uint32_t slot = cx_.ray_slot;
     if (slot == SP_SLOT_NONE) return;       // the CTA's reservation overflowed the queue (reported to the host)
     uint32_t meta = sp_pack_meta(meta_depth(r.meta) + 1u, dr, medium, (uint32_t)src, mode);
-    sp_write_record(cx_.out.rays, slot + cx_.ray_used, o, d, thr, r.pix, sp_child_path(r.path, k), meta);
+    sp_write_record(cx_.out->rays, slot + cx_.ray_used, o, d, thr, r.pix, sp_child_path(r.path, k), meta);
     cx_.ray_used += 1u;
 }
 
@@ -238,7 +238,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
                 uint32_t mode = (planar || side_plus > 0.f) ? SP_SELF_SKIP : SP_SELF_FAR;
                 uint32_t meta = sp_pack_meta(depth + 1u, dr + 1u, medium, (uint32_t)h.id, mode);
                 if (cx_.fan_slot != SP_SLOT_NONE) {
-                    sp_write_record(cx_.out.fans, cx_.fan_slot, nudged, N, thr, r.pix, r.path, meta);
+                    sp_write_record(cx_.out->fans, cx_.fan_slot, nudged, N, thr, r.pix, r.path, meta);
                     cx_.fan_slot = SP_SLOT_NONE;            // consumed
                 }
             }
@@ -326,12 +326,14 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
             cplx a = cx(re1[c], im1[c]), b = cx(re2[c], im2[c]);
             cplx ratio = a / b;
             cplx cos_t = csqrt(cx(1.f) - ratio * ratio * s2);
-            cplx r_per = (a * cos_i - b * cos_t) / (a * cos_i + b * cos_t);
-            cplx r_par = (a * cos_t - b * cos_i) / (a * cos_t + b * cos_i);
-            Fc[c] = 0.5f * (cabs2(r_per) + cabs2(r_par));
+            // |r|^2 = |numerator|^2 / |denominator|^2: no complex division needed
+            cplx aci = a * cos_i, bct = b * cos_t, act = a * cos_t, bci = b * cos_i;
+            float per = __fdividef(cabs2(aci - bct), cabs2(aci + bct));
+            float par = __fdividef(cabs2(act - bci), cabs2(act + bci));
+            Fc[c] = 0.5f * (per + par);
         }
         float3 F = v3(Fc[0], Fc[1], Fc[2]);
-        float eta = (re1[0] / re2[0] + re1[1] / re2[1] + re1[2] / re2[2]) / 3.f;
+        float eta = (__fdividef(re1[0], re2[0]) + __fdividef(re1[1], re2[1]) + __fdividef(re1[2], re2[2])) * (1.f / 3.f);
         float sin2_t = eta * eta * s2;
         bool non_tir = sin2_t <= 1.f;
         float3 Tdir = normalize0(fma3(N, eta * cos_i - sqrtf(1.f - clamp01(sin2_t)), r.d * eta));

@@ -13,7 +13,7 @@
 // cuboid   : (B0.xyz, lo.x) (B1.xyz, lo.y) (B2.xyz, lo.z) (C.xyz, hi.x) (hi.y, hi.z, -, -)
 //            B = basis rows, lo/hi = box corners relative to B*C (so tests run on O - C)
 // triangle : 24 floats N, centroid, n31, p1, n12, p2, n23, p3
-#define SP_CHUNK_VEC4 1536            // 24 KB staging buffer (static shared memory is capped at 48 KB)
+#define SP_CHUNK_VEC4 2048            // at most 32 KB of (dynamic) shared memory per staged chunk
 #define SP_V4_SPHERE 1
 #define SP_V4_PLANE 4
 #define SP_V4_CUBOID 5
@@ -32,6 +32,8 @@ struct GeomStream {
     const int* chunk_off;      // n_chunks + 1 offsets (float4 units)
     int n_chunks;
     int n_items;
+    int max_chunk_vec4;        // largest chunk (float4 units): the kernel's dynamic shared memory
+    int pad;
 };
 
 // ---- full records used at shading time (one per collider / primitive / material) -------------
@@ -98,6 +100,8 @@ struct DScene {
     DCamera cam;
     float3 ambient;
     int n_lights, n_importance, n_colliders, n_fan_classes;
+    float inv_n_importance;
+    unsigned long long fan_magic[SP_MAX_FAN_CLASSES];   // ceil(2^64 / fan_mult): n / mult == __umul64hi(n, magic) for n < 2^32
     int fan_mult[SP_MAX_FAN_CLASSES];     // rays per fan record of each class (class 0: 1)
     uint32_t seed_lo, seed_hi;
 };
