@@ -44,7 +44,7 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
             float3 q = fma3(D, -b, oc);
             float disc = s.w - dot(q, q);
             if (disc > 0.f) {
-                float sq = sqrtf(disc);
+                float sq = fast_sqrt(disc);
                 float h0 = -b - sq, h1 = -b + sq;
                 bool is_self = (i == self.sphere);
                 bool near_ok = (h0 > 0.f) && !is_self;             // SP_SELF_FAR: only the far root
@@ -57,6 +57,7 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
     // ---- bounded planes ------------------------------------------------------------------------
     {
         const float4* pl = ch + h->off_plane;
+#pragma unroll 2
         for (int i = 0; i < n_plane; ++i) {
             float4 a = pl[4 * i], c = pl[4 * i + 1], u4 = pl[4 * i + 2], v4 = pl[4 * i + 3];
             float3 N = xyz(a), oc = O - xyz(c);

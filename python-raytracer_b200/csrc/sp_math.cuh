@@ -30,6 +30,15 @@ SP_DEV float3 normalize0(float3 a) {
     float inv = m2 > 0.f ? rsqrtf(m2) : 1.f;
     return a * inv;
 }
+// sqrt.approx / sin.approx / cos.approx (MUFU, ~1e-6 relative): used where the result feeds a random
+// direction or a hit distance, never a texel index
+SP_DEV float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// sin and cos of 2*pi*u for u in [0, 1): evaluated at 2*pi*(u - 0.5), where the MUFU approximations are
+// accurate to ~5e-7 absolute, and negated (sin(x + pi) = -sin x)
+SP_DEV void fast_sincos_2pi(float u, float& sn, float& cs) {
+    const float x = (u - 0.5f) * 6.28318530717958647692f;
+    sn = -__sinf(x); cs = -__cosf(x);
+}
 SP_DEV float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
 SP_DEV float3 xyz(float4 a) { return v3(a.x, a.y, a.z); }
 SP_DEV bool any_nonzero(float3 a) { return a.x != 0.f || a.y != 0.f || a.z != 0.f; }

@@ -42,25 +42,25 @@ SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float 
     float u[4];
     sp_draw4(pix, path, SP_BLOCK_DIRECTION, sc.seed_lo, sc.seed_hi, u);
     float sn, cs;
-    sincospif(2.f * u[1], &sn, &cs);
+    fast_sincos_2pi(u[1], sn, cs);
     const int l = sc.n_importance;
     bool use_cos = (l == 0) || (u[0] < w_cos);
     if (use_cos) {                                           // cosine_pdf.generate
         float3 au, av;
         sp_onb(N, au, av);
-        float s = sqrtf(u[2]);
-        dir = au * (cs * s) + av * (sn * s) + N * sqrtf(1.f - u[2]);
+        float s = fast_sqrt(u[2]);
+        dir = au * (cs * s) + av * (sn * s) + N * fast_sqrt(1.f - u[2]);
     } else {                                                 // spherical_caps_pdf.generate
         int pick = min((int)(u[3] * (float)l), l - 1);
         float3 to_c = sc.importance[pick].center - origin;
         float d2 = dot(to_c, to_c);
         float3 w = to_c * rsqrtf(d2);
         float ratio = clamp01(sc.importance[pick].radius * rsqrtf(d2));
-        float cmax = sqrtf(1.f - ratio * ratio);
+        float cmax = fast_sqrt(1.f - ratio * ratio);
         float3 au, av;
         sp_onb(w, au, av);
         float z = 1.f + u[2] * (cmax - 1.f);
-        float s = sqrtf(fmaxf(1.f - z * z, 0.f));
+        float s = fast_sqrt(fmaxf(1.f - z * z, 0.f));
         dir = au * (cs * s) + av * (sn * s) + w * z;
     }
     float ndl = clamp01(dot(dir, N));
@@ -73,7 +73,7 @@ SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float 
             float d2 = dot(to_c, to_c);
             float inv = rsqrtf(d2);
             float ratio = clamp01(sc.importance[i].radius * inv);
-            float cmax = sqrtf(1.f - ratio * ratio);
+            float cmax = fast_sqrt(1.f - ratio * ratio);
             if (dot(dir, to_c) * inv > cmax) caps += __fdividef(1.f, (1.f - cmax) * 2.f * SP_PI);
         }
         pdf = pdf * w_cos + (caps * sc.inv_n_importance) * (1.f - w_cos);
