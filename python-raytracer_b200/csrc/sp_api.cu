@@ -103,7 +103,8 @@ struct sp_scene {
     uint32_t ray_cap = 0, fan_cap = 0;
     uint32_t chunk_primaries = 0;
     double use_ray = 0.0, use_fan = 0.0;         // peak records per primary seen so far
-    int grid = 0;
+    int grid0 = 0, grid_q = 0;                   // CTAs of level-0 / queue-fed launches
+    uint32_t material_set = 0;                   // compiled kernel variant (sp_pick_material_set)
 
     ~sp_scene() { release_device(); }
     void release_device() {
@@ -562,7 +563,22 @@ int sp_scene_commit(sp_scene* s) {
     CUDA_TRY(s->d_stats.alloc(1));
     s->events.resize((size_t)s->n_levels + 1);
     for (auto& e : s->events) CUDA_TRY(cudaEventCreate(&e));
-    s->grid = sp_level_grid(g_device, s->d);
+    uint32_t needed = 0;
+    for (int i = 0; i < n_col; ++i) {
+        const sp_material& m = s->mats[s->prims[s->cols[i].primitive].material];
+        if (m.color_tex >= 0 || m.normalmap_tex >= 0) needed |= SP_F_TEX;
+        switch (m.kind) {
+        case SP_MAT_GLOSSY: needed |= SP_F_GLOSSY; break;
+        case SP_MAT_REFRACTIVE: needed |= SP_F_REFR; break;
+        case SP_MAT_THINFILM: needed |= SP_F_THIN | SP_F_TEX; break;
+        case SP_MAT_DIFFUSE: needed |= SP_F_DIFFUSE; break;
+        case SP_MAT_SKYBOX: needed |= SP_F_SKY | SP_F_TEX; break;
+        default: break;
+        }
+    }
+    s->material_set = sp_pick_material_set(needed);
+    s->grid0 = sp_level_grid(g_device, s->d, s->material_set, true);
+    s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false);
     s->use_ray = s->use_fan = 0.0;
     s->committed = true;
     return 0;
@@ -626,7 +642,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
         a.out_hit = job.out_hit; a.out_t = job.out_t; a.out_o = job.out_o; a.out_d = job.out_d;
         a.all_slot = s->slot_all.p; a.shadow_slot = s->slot_shadow.p;
         CUDA_TRY(cudaEventRecord(s->events[L], s->stream));
-        CUDA_TRY(sp_launch_level(s->d, a, s->grid, s->stream));
+        CUDA_TRY(sp_launch_level(s->d, a, s->material_set, L == 0 ? s->grid0 : s->grid_q, s->stream));
     }
     CUDA_TRY(cudaEventRecord(s->events[n_levels], s->stream));
     std::vector<uint32_t> counts((size_t)(n_levels + 1) * ncl);

@@ -23,9 +23,15 @@
 #ifndef SP_BLOCK
 #define SP_BLOCK 256
 #endif
-#ifndef SP_CTAS_PER_SM
-#define SP_CTAS_PER_SM 3
+// resident CTAs per SM the register allocation aims for: the lean Monte-Carlo variant fits 64
+// registers (4 CTAs) with a handful of spills, the textured / glossy variants need 80 (3 CTAs)
+#ifndef SP_CTAS_MC
+#define SP_CTAS_MC 4
 #endif
+#ifndef SP_CTAS_FULL
+#define SP_CTAS_FULL 3
+#endif
+#define SP_CTAS_PER_SM(FEAT) ((((FEAT) & (SP_F_TEX | SP_F_GLOSSY | SP_F_THIN | SP_F_SKY)) == 0u) ? SP_CTAS_MC : SP_CTAS_FULL)
 
 SP_DEV void sp_stage_chunk(float4* __restrict__ dst, const DScene& sc, const GeomStream& gs, int c) {
     const int lo = __ldg(gs.chunk_off + c), hi = __ldg(gs.chunk_off + c + 1);
@@ -49,7 +55,8 @@ struct IterShared {
     uint32_t n_shade;                              // rays with something to shade this iteration
 };
 
-__global__ void __launch_bounds__(SP_BLOCK, SP_CTAS_PER_SM)
+template <uint32_t FEAT>
+__global__ void __launch_bounds__(SP_BLOCK, SP_CTAS_PER_SM(FEAT))
 sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
     extern __shared__ float4 s_geom[];                 // sized by the host to the scene's largest chunk
     __shared__ IterShared sh_buf[2];                   // double-buffered: no barrier at the end of an iteration
@@ -59,7 +66,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     uint32_t total;                                    // < 2^32 work items per launch (checked by the host)
 #pragma unroll
     for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) fan_n[c] = 0;
-    if (a.source == SP_SRC_QUEUES) {
+    if ((FEAT & SP_F_QUEUES) && a.source == SP_SRC_QUEUES) {
         n_rays = min(__ldg(a.in_counts), a.in_rays.capacity);
         total = n_rays;
 #pragma unroll
@@ -99,7 +106,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
 
         // ---- 1. the ray of this item ---------------------------------------------------------
         if (active) {
-            if (a.source == SP_SRC_CAMERA) {
+            if ((FEAT & SP_F_LEVEL0) && a.source == SP_SRC_CAMERA) {
                 uint32_t i = (uint32_t)item;
                 uint32_t sample = a.sample_begin + i / a.n_pix;
                 r.pix = a.pix_begin + i % a.n_pix;
@@ -107,7 +114,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 sp_camera_ray(sc.cam, r.pix, sample, sc.seed_lo, sc.seed_hi, r.o, r.d);
                 r.thr = v3(1.f);
                 r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
-            } else if (a.source == SP_SRC_USER) {
+            } else if ((FEAT & SP_F_LEVEL0) && a.source == SP_SRC_USER) {
                 uint32_t i = a.user_base + (uint32_t)item;
                 r.pix = i;
                 r.path = sp_root_path(0u);
@@ -115,6 +122,8 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 r.d = v3(__ldg(a.user_d + 3 * (size_t)i), __ldg(a.user_d + 3 * (size_t)i + 1), __ldg(a.user_d + 3 * (size_t)i + 2));
                 r.thr = v3(1.f);
                 r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
+            } else if (!(FEAT & SP_F_QUEUES)) {
+                active = false;
             } else if (item < n_rays) {
                 const uint32_t s = (uint32_t)item;
                 const float4 q2 = a.in_rays.q2[s];
@@ -126,6 +135,8 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                     r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
                     r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
                 }
+            } else if (!(FEAT & SP_F_DIFFUSE)) {
+                active = false;
             } else {
                 uint32_t local = item - n_rays;
                 int c = 0;
@@ -154,7 +165,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 }
             }
         }
-        if (a.run == SP_RUN_DUMP_RAYS) {
+        if ((FEAT & SP_F_LEVEL0) && a.run == SP_RUN_DUMP_RAYS) {
             if (active) {
                 const size_t i = (size_t)item;
                 a.out_o[3 * i] = r.o.x; a.out_o[3 * i + 1] = r.o.y; a.out_o[3 * i + 2] = r.o.z;
@@ -202,13 +213,13 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         }
         if (active) {
             traced += 1;
-            if (a.level == 0) {
+            if ((FEAT & SP_F_LEVEL0) && a.level == 0) {
                 const size_t oi = (a.source == SP_SRC_USER) ? (size_t)a.user_base + (size_t)item : (size_t)item;
                 if (a.out_hit) a.out_hit[oi] = hit.id;
                 if (a.out_t) a.out_t[oi] = hit.t;
             }
         }
-        if (a.run == SP_RUN_DISTANCES) continue;
+        if ((FEAT & SP_F_LEVEL0) && a.run == SP_RUN_DISTANCES) continue;
 
         // ---- 3. what the hit will emit; per-warp counts of shading bins and queue records ---------------
         int bin = SP_N_BINS - 1, n_ray = 0, fan_class = -1;
@@ -308,7 +319,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 const uint32_t fbase = sh.queue_base[1 + (fs >> 28)];
                 if (fbase != SP_SLOT_NONE) ctx.fan_slot = fbase + (fs & 0x0FFFFFFFu);
             }
-            const float3 add = sp_shade(ctx, s, h);
+            const float3 add = sp_shade<FEAT>(ctx, s, h);
             float* px = reinterpret_cast<float*>(a.accum + s.pix);
             if (add.x != 0.f) atomicAdd(px, add.x);
             if (add.y != 0.f) atomicAdd(px + 1, add.y);
@@ -394,18 +405,40 @@ __global__ void __launch_bounds__(256) sp_copy_kernel(const float4* __restrict__
 // =================================================================================================
 static size_t geom_smem_bytes(const DScene& sc) { return (size_t)sc.all.max_chunk_vec4 * sizeof(float4); }
 
-int sp_level_grid(int device, const DScene& sc) {
+// Instantiated material sets, smallest first; a scene runs the first one that covers its materials.
+#define SP_SET_MC      (SP_F_DIFFUSE | SP_F_REFR)                                        /* Cornell box */
+#define SP_SET_WHITTED (SP_F_TEX | SP_F_GLOSSY | SP_F_REFR | SP_F_THIN | SP_F_SKY)       /* examples 1-4 */
+#define SP_SET_ALL     (SP_F_MATERIALS)
+static const uint32_t kMaterialSets[] = {SP_SET_MC, SP_SET_WHITTED, SP_SET_ALL};
+
+uint32_t sp_pick_material_set(uint32_t needed) {
+    for (uint32_t set : kMaterialSets)
+        if ((needed & ~set) == 0u) return set;
+    return SP_SET_ALL;
+}
+
+typedef void (*LevelKernel)(const DScene, const LevelArgs);
+static LevelKernel level_kernel(uint32_t material_set, bool level0) {
+    switch (material_set) {
+    case SP_SET_MC: return level0 ? sp_level_kernel<SP_SET_MC | SP_F_LEVEL0> : sp_level_kernel<SP_SET_MC | SP_F_QUEUES>;
+    case SP_SET_WHITTED: return level0 ? sp_level_kernel<SP_SET_WHITTED | SP_F_LEVEL0> : sp_level_kernel<SP_SET_WHITTED | SP_F_QUEUES>;
+    default: return level0 ? sp_level_kernel<SP_SET_ALL | SP_F_LEVEL0> : sp_level_kernel<SP_SET_ALL | SP_F_QUEUES>;
+    }
+}
+
+int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaFuncSetAttribute(sp_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
-    int per_sm = SP_CTAS_PER_SM;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_level_kernel, SP_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
+    LevelKernel k = level_kernel(material_set, level0);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SP_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
         per_sm = 1;
     return sms * per_sm;
 }
 
-cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, int grid, cudaStream_t st) {
-    sp_level_kernel<<<grid, SP_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
+cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st) {
+    level_kernel(material_set, a.source != SP_SRC_QUEUES)<<<grid, SP_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
     return cudaGetLastError();
 }
 

@@ -37,8 +37,9 @@ struct ResolveArgs {
     uint8_t* out_srgb8;            // n_pix * 3 interleaved (nullable)
 };
 
-int sp_level_grid(int device, const DScene& sc);      // CTAs of a persistent level launch
-cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, int grid, cudaStream_t st);
+uint32_t sp_pick_material_set(uint32_t needed_features);          // smallest compiled kernel variant covering them
+int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0);   // CTAs of a persistent launch
+cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
 cudaError_t sp_upload_decode_tables(const float* plain256, const float* linear256);
 cudaError_t sp_bench_ffma(double* tflops, cudaStream_t st);

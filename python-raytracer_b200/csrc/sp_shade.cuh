@@ -70,7 +70,7 @@ struct HitGeom {
     int off_color, off_normal, off_aux0, off_aux1;   // texel offsets (valid where the texture exists)
 };
 
-template <typename T>
+template <typename T, uint32_t FEAT>
 SP_DEV HitGeom sp_eval_hit(const DScene& sc, const DMaterial& m, const DPrimitive& prim, const T* cp, int ctype,
                            const Ray& r, const HitRec& h) {
     HitGeom g;
@@ -83,7 +83,7 @@ SP_DEV HitGeom sp_eval_hit(const DScene& sc, const DMaterial& m, const DPrimitiv
     g.cos_i = (float)(-(tdot(D, Nc)) * (T)h.orient);
     g.off_color = g.off_normal = g.off_aux0 = g.off_aux1 = 0;
     bool need_uv = (m.color_tex >= 0) || (m.normalmap_tex >= 0) || (m.kind == SP_MAT_THINFILM);
-    if (need_uv) {
+    if ((FEAT & SP_F_TEX) && need_uv) {
         T u, v;
         sp_collider_uv<T>(ctype, cp, P, Nc, prim.uv_cross != 0, u, v);
         if (m.color_tex >= 0) {
@@ -94,11 +94,11 @@ SP_DEV HitGeom sp_eval_hit(const DScene& sc, const DMaterial& m, const DPrimitiv
             const DTexture& tx = sc.textures[m.normalmap_tex];
             g.off_normal = sp_texel_offset<T>(u, v, tx.H, tx.W, (T)m.normalmap_repeat, tx.H, tx.W);
         }
-        if (m.kind == SP_MAT_SKYBOX && m.aux_tex0 >= 0) {       // lightmap indexed with the env shape
+        if ((FEAT & SP_F_SKY) && m.kind == SP_MAT_SKYBOX && m.aux_tex0 >= 0) {       // lightmap indexed with the env shape
             const DTexture& tx = sc.textures[m.aux_tex0];
             g.off_aux0 = sp_texel_offset<T>(u, v, m.index_h, m.index_w, (T)m.color_repeat, tx.H, tx.W);
         }
-        if (m.kind == SP_MAT_THINFILM) {
+        if ((FEAT & SP_F_THIN) && m.kind == SP_MAT_THINFILM) {
             // thickness noise, then the reflectance LUT row/column (thin_film_interference.py:46-72)
             T thick = (T)m.thickness;
             if (m.noise_factor != 0.f) {
@@ -184,6 +184,7 @@ SP_DEV void sp_emit_ray(ShadeCtx& cx_, const Ray& r, float3 o, float3 d, float3 
 }
 
 // Shade one hit.  Returns the radiance to add to the ray's pixel (already times throughput).
+template <uint32_t FEAT>
 SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
     const DScene& sc = *cx_.sc;
     const DCollider& col = sc.colliders[h.id];
@@ -192,16 +193,17 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
     const DMaterial& m = sc.mats[prim.material];
     const uint32_t depth = meta_depth(r.meta), dr = meta_dr(r.meta), medium = meta_medium(r.meta);
 
-    HitGeom g = m.precise ? sp_eval_hit<double>(sc, m, prim, sc.colliders_d + (size_t)h.id * 40, ctype, r, h)
-                          : sp_eval_hit<float>(sc, m, prim, col.p, ctype, r, h);
+    HitGeom g = ((FEAT & SP_F_TEX) && m.precise)
+                    ? sp_eval_hit<double, FEAT>(sc, m, prim, sc.colliders_d + (size_t)h.id * 40, ctype, r, h)
+                    : sp_eval_hit<float, FEAT>(sc, m, prim, col.p, ctype, r, h);
     const float orient = (float)h.orient;
 
     // ---- terminal materials ---------------------------------------------------------------------
     if (m.kind == SP_MAT_EMISSIVE) {                                     // emissive.py:21-23
-        float3 c = m.color_tex >= 0 ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color;
+        float3 c = ((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color;
         return r.thr * c;
     }
-    if (m.kind == SP_MAT_SKYBOX) {                                       // skybox.py:51-94
+    if ((FEAT & SP_F_SKY) && m.kind == SP_MAT_SKYBOX) {                                   // skybox.py:51-94
         float3 c = sp_fetch_texel(sc.textures[m.color_tex], g.off_color);
         if (depth != 0u && m.light_intensity != 0.f)
             c += sp_fetch_texel(sc.textures[m.aux_tex0], g.off_aux0) * m.light_intensity;
@@ -210,7 +212,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
 
     // ---- shading normal (material.py:18-36) ----------------------------------------------------------
     float3 N;
-    if (m.normalmap_tex >= 0) {
+    if ((FEAT & SP_F_TEX) && m.normalmap_tex >= 0) {
         float3 tx = sp_fetch_texel(sc.textures[m.normalmap_tex], g.off_normal);
         float3 nm = (tx - v3(0.5f)) * 2.f;
         const float* ib = col.p + (ctype == SP_COLLIDER_PLANE ? SP_PL_INVB : SP_CB_INVB);
@@ -224,8 +226,8 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
     float3 add = v3(0.f);
     int zo;
 
-    if (m.kind == SP_MAT_DIFFUSE) {                                      // diffuse.py:25-124
-        float3 diff = m.color_tex >= 0 ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color;
+    if ((FEAT & SP_F_DIFFUSE) && m.kind == SP_MAT_DIFFUSE) {                                // diffuse.py:25-124
+        float3 diff = ((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color;
         int cls = -1; float inv_m = 1.f;
         if (dr < 1u) { cls = m.fan_class; inv_m = 1.f / (float)m.diffuse_rays; }
         else if ((int)dr < m.max_dr) { cls = 0; }
@@ -246,8 +248,8 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
         return add;
     }
 
-    if (m.kind == SP_MAT_GLOSSY) {                                       // glossy.py:25-110
-        float3 diff = (m.color_tex >= 0 ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color)
+    if ((FEAT & SP_F_GLOSSY) && m.kind == SP_MAT_GLOSSY) {                                // glossy.py:25-110
+        float3 diff = (((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color)
                       * m.diff_coeff;
         float3 color = sc.ambient * diff;
         const DMedium med = sc.media[medium];
@@ -296,13 +298,14 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
         return add;
     }
 
+    if (!(FEAT & (SP_F_REFR | SP_F_THIN))) return add;
     if ((int)depth >= prim.max_ray_depth) return add;                   // refractive.py:38, thin_film...py:34
 
     float3 R = normalize0(fma3(N, -2.f * dot(r.d, N), r.d));
     const float3 nudged_in = fma3(N, -1e-6f, g.P);
     const uint32_t mode_refl = sp_self_mode(ctype, side_plus, dot(R, g.Nc), zo);
 
-    if (m.kind == SP_MAT_THINFILM) {                                     // thin_film_interference.py:24-115
+    if ((FEAT & SP_F_THIN) && m.kind == SP_MAT_THINFILM) {                               // thin_film_interference.py:24-115
         float3 F = sp_fetch_texel(sc.textures[m.aux_tex0], g.off_aux0);
         add = r.thr * sc.ambient * F;
         sp_emit_ray(cx_, r, nudged, R, r.thr * F, 0u, medium, dr, h.id, mode_refl);
@@ -312,7 +315,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
     }
 
     // ---- Refractive (refractive.py:24-123) ----------------------------------------------------------
-    {
+    if (FEAT & SP_F_REFR) {
         const DMedium n1 = sc.media[medium];
         const uint32_t med2 = h.orient > 0 ? (uint32_t)m.medium : 0u;
         const DMedium n2 = sc.media[med2];

@@ -106,6 +106,22 @@ struct DScene {
     uint32_t seed_lo, seed_hi;
 };
 
+// ---- kernel specialisation ------------------------------------------------------------------------
+// The level kernel is compiled for a few sets of scene features; a scene runs the smallest set that
+// covers it.  Leaving out whole materials (and the double-precision texel path) shrinks the code the
+// warps of an SM fight over in the instruction cache and the registers every thread must reserve.
+enum : uint32_t {
+    SP_F_TEX = 1u,        // image textures, normal maps, thin-film LUTs, sky boxes: uv + texel addressing (double path)
+    SP_F_GLOSSY = 2u,     // Glossy (lights, shadow rays)
+    SP_F_REFR = 4u,       // Refractive
+    SP_F_THIN = 8u,       // ThinFilmInterference
+    SP_F_DIFFUSE = 16u,   // Diffuse (fan records, importance sampling)
+    SP_F_SKY = 32u,       // SkyBox / Panorama materials
+    SP_F_LEVEL0 = 64u,    // sources of a level-0 launch (camera, caller rays) and its per-ray outputs
+    SP_F_QUEUES = 128u,   // source of a level >= 1 launch
+    SP_F_MATERIALS = 63u,
+};
+
 // ---- wavefront records --------------------------------------------------------------------------
 // One record = three float4 in three SoA arrays (coalesced 16-byte accesses):
 //   q0 = (O.xyz, pixel)   q1 = (V.xyz, path)   q2 = (throughput.rgb, meta)
