@@ -39,27 +39,37 @@ SP_DEV void sp_stage_chunk(float4* __restrict__ dst, const DScene& sc, const Geo
     for (int i = threadIdx.x; i < hi - lo; i += SP_BLOCK) dst[i] = __ldg(src + i);
 }
 
-// Per-CTA exchange area of one iteration (256 rays): the rays and their hits are parked here after
-// the intersection phase, regrouped by the material kind they hit, and picked up again by the
-// shading phase, so that the lanes of a warp shade the same material (the fused kernel would
-// otherwise run Diffuse / Refractive / Emissive code with a third of its lanes each).
+// Per-CTA exchange area of one iteration (SP_BATCH rays, SP_RPT per thread): the rays and their
+// hits are parked here after the intersection phase, regrouped by the material kind they hit
+// (most expensive kind first), and picked up again in 32-ray chunks by whichever warp is free, so
+// that the lanes of a warp shade the same material and the warps of a CTA finish together (the
+// fused kernel would otherwise run Diffuse / Refractive / Emissive code with a third of its lanes
+// each, and the warp that drew the glass hits would keep the other seven waiting).
+#ifndef SP_RPT
+#define SP_RPT 2
+#endif
+#define SP_BATCH (SP_BLOCK * SP_RPT)
 #define SP_STATE_WORDS 16
 #define SP_N_BINS 7              // the six material kinds + "nothing to shade"
 #define SP_N_QUEUES (1 + SP_MAX_FAN_CLASSES)
 #define SP_N_WARPS (SP_BLOCK / 32)
+#define SP_N_VWARPS (SP_N_WARPS * SP_RPT)
+// material kind -> shading bin, dearest first: Refractive, Glossy, ThinFilm, Diffuse, SkyBox, Emissive
+#define SP_BIN_OF_KIND(kind) ((0x453201u >> (4u * (kind))) & 15u)
 struct IterShared {
-    uint32_t state[SP_STATE_WORDS][SP_BLOCK];      // SoA: o d thr pix path meta t (id|orient) ray_slot fan_slot
-    uint16_t perm[SP_BLOCK];                       // perm[j] = thread whose ray is shaded by thread j
-    uint32_t warp_cnt[SP_N_WARPS][16];             // per warp: [0..6] bins, [8..12] queue records
+    uint32_t state[SP_STATE_WORDS][SP_BATCH];      // SoA: o d thr pix path meta t (id|orient) ray_slot fan_slot
+    uint16_t perm[SP_BATCH];                       // perm[k] = batch slot of the k-th ray in shading order
+    uint32_t warp_cnt[SP_N_VWARPS][16];            // per (pass, warp): [0..6] bins, [8..12] queue records
     uint32_t queue_base[SP_N_QUEUES];              // CTA's reservation in each output queue
     uint32_t n_shade;                              // rays with something to shade this iteration
+    uint32_t next_chunk;                           // next 32-ray shading chunk up for grabs
 };
 
 template <uint32_t FEAT>
 __global__ void __launch_bounds__(SP_BLOCK, SP_CTAS_PER_SM(FEAT))
 sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
     extern __shared__ float4 s_geom[];                 // sized by the host to the scene's largest chunk
-    __shared__ IterShared sh_buf[2];                   // double-buffered: no barrier at the end of an iteration
+    __shared__ IterShared sh;
 
     // ---- work items of this launch ---------------------------------------------------------
     uint32_t n_rays = 0, fan_n[SP_MAX_FAN_CLASSES];
@@ -94,13 +104,16 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     ctx.shadow_rays = 0;
     unsigned long long traced = 0;
 
-    uint32_t parity = 0;
-    for (unsigned long long base64 = (unsigned long long)blockIdx.x * SP_BLOCK; base64 < total;
-         base64 += (unsigned long long)gridDim.x * SP_BLOCK, parity ^= 1u) {
-        IterShared& sh = sh_buf[parity];
+    for (unsigned long long base64 = (unsigned long long)blockIdx.x * SP_BATCH; base64 < total;
+         base64 += (unsigned long long)gridDim.x * SP_BATCH) {
         const uint32_t base = (uint32_t)base64;
-        const uint32_t item = base + tid;
-        bool active = (unsigned long long)base + tid < total;
+        // the pass loop is deliberately not unrolled: one copy of the generate/intersect code in the
+        // instruction cache
+#pragma unroll 1
+        for (int pass = 0; pass < SP_RPT; ++pass) {
+        const uint32_t slot = (uint32_t)pass * SP_BLOCK + tid;
+        const uint32_t item = base + slot;
+        bool active = (unsigned long long)base + slot < total;
         Ray r;
         r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
 
@@ -221,43 +234,53 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         }
         if ((FEAT & SP_F_LEVEL0) && a.run == SP_RUN_DISTANCES) continue;
 
-        // ---- 3. what the hit will emit; per-warp counts of shading bins and queue records ---------------
+        // ---- 3. park the ray; what the hit will emit; per-warp counts of bins and queue records ---------
+        sh.state[0][slot] = __float_as_uint(r.o.x); sh.state[1][slot] = __float_as_uint(r.o.y); sh.state[2][slot] = __float_as_uint(r.o.z);
+        sh.state[3][slot] = __float_as_uint(r.d.x); sh.state[4][slot] = __float_as_uint(r.d.y); sh.state[5][slot] = __float_as_uint(r.d.z);
+        sh.state[6][slot] = __float_as_uint(r.thr.x); sh.state[7][slot] = __float_as_uint(r.thr.y); sh.state[8][slot] = __float_as_uint(r.thr.z);
+        sh.state[9][slot] = r.pix; sh.state[10][slot] = r.path; sh.state[11][slot] = r.meta;
+        sh.state[12][slot] = __float_as_uint(hit.t);
+        sh.state[13][slot] = (uint32_t)hit.id | (hit.orient > 0 ? 0x80000000u : 0u);
         int bin = SP_N_BINS - 1, n_ray = 0, fan_class = -1;
         if (active && hit.id >= 0) {
             const float4 raw = __ldg(reinterpret_cast<const float4*>(sc.col_info + hit.id));
             const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
-            bin = ci.kind;
+            bin = (int)SP_BIN_OF_KIND(ci.kind);
             sp_child_needs(ci, meta_depth(r.meta), meta_dr(r.meta), n_ray, fan_class);
         }
-        if (lane < 16) sh.warp_cnt[warp][lane] = 0u;
+        const uint32_t vwarp = (uint32_t)pass * SP_N_WARPS + warp;
+        if (lane < 16) sh.warp_cnt[vwarp][lane] = 0u;
         __syncwarp();
         const uint32_t bin_peers = __match_any_sync(0xffffffffu, bin);
         const uint32_t bin_rank = __popc(bin_peers & lt_mask);
-        if (bin_rank == 0) sh.warp_cnt[warp][bin] = __popc(bin_peers);
+        if (bin_rank == 0) sh.warp_cnt[vwarp][bin] = __popc(bin_peers);
         const uint32_t b0 = __ballot_sync(0xffffffffu, n_ray & 1), b1 = __ballot_sync(0xffffffffu, n_ray & 2);
         const uint32_t ray_rank = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
-        if (lane == 0) sh.warp_cnt[warp][8] = __popc(b0) + 2u * __popc(b1);
+        if (lane == 0) sh.warp_cnt[vwarp][8] = __popc(b0) + 2u * __popc(b1);
         uint32_t fan_rank = 0;
 #pragma unroll
         for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) {
             if (c < sc.n_fan_classes) {
                 const uint32_t bc = __ballot_sync(0xffffffffu, fan_class == c);
                 if (fan_class == c) fan_rank = __popc(bc & lt_mask);
-                if (lane == 0) sh.warp_cnt[warp][9 + c] = __popc(bc);
+                if (lane == 0) sh.warp_cnt[vwarp][9 + c] = __popc(bc);
             }
         }
+        // ranks inside the warp, parked until the CTA-wide offsets are known:
+        // bin[0:3) bin_rank[3:8) n_ray[8:10) ray_rank[10:17) fan_class+1[17:20) fan_rank[20:25)
+        sh.state[14][slot] = (uint32_t)bin | (bin_rank << 3) | ((uint32_t)n_ray << 8) | (ray_rank << 10) |
+                             ((uint32_t)(fan_class + 1) << 17) | (fan_rank << 20);
+        }   // pass
+        if ((FEAT & SP_F_LEVEL0) && a.run != SP_RUN_FULL) continue;
+        if (tid == 0) sh.next_chunk = 0u;
         __syncthreads();                                                            // (A) counts visible
 
-        // every warp derives the CTA-wide offsets it needs from the 8 x 16 count table:
+        // every warp derives the CTA-wide offsets it needs from the (pass, warp) x 16 count table:
         // lane l < 16 owns column l (a bin or a queue)
-        uint32_t col_total = 0, col_before = 0;
+        uint32_t col_total = 0;
         if (lane < 16) {
 #pragma unroll
-            for (int w = 0; w < SP_N_WARPS; ++w) {
-                const uint32_t v = sh.warp_cnt[w][lane];
-                if ((uint32_t)w < warp) col_before += v;
-                col_total += v;
-            }
+            for (int w = 0; w < SP_N_VWARPS; ++w) col_total += sh.warp_cnt[w][lane];
         }
         // exclusive scan of the bin totals over lanes 0..6 (bins are laid out one after the other)
         uint32_t bin_start = (lane < SP_N_BINS) ? col_total : 0u;
@@ -267,9 +290,6 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
             if (lane >= (uint32_t)o && lane < 8) bin_start += up;
         }
         bin_start -= (lane < SP_N_BINS) ? col_total : 0u;
-        const uint32_t my_dest = __shfl_sync(0xffffffffu, bin_start + col_before, bin) + bin_rank;
-        const uint32_t ray_before = __shfl_sync(0xffffffffu, col_before, 8);
-        const uint32_t fan_before = __shfl_sync(0xffffffffu, col_before, 9 + max(fan_class, 0));
         if (warp == 0) {
             // one reservation per output queue for the whole CTA
             if (lane >= 8 && lane < 8 + SP_N_QUEUES) {
@@ -285,52 +305,66 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
             }
             if (lane == SP_N_BINS - 1) sh.n_shade = bin_start;     // start of the "nothing" bin = rays to shade
         }
-        // park the ray and its hit
-        sh.perm[my_dest] = (uint16_t)tid;
-        sh.state[0][tid] = __float_as_uint(r.o.x); sh.state[1][tid] = __float_as_uint(r.o.y); sh.state[2][tid] = __float_as_uint(r.o.z);
-        sh.state[3][tid] = __float_as_uint(r.d.x); sh.state[4][tid] = __float_as_uint(r.d.y); sh.state[5][tid] = __float_as_uint(r.d.z);
-        sh.state[6][tid] = __float_as_uint(r.thr.x); sh.state[7][tid] = __float_as_uint(r.thr.y); sh.state[8][tid] = __float_as_uint(r.thr.z);
-        sh.state[9][tid] = r.pix; sh.state[10][tid] = r.path; sh.state[11][tid] = r.meta;
-        sh.state[12][tid] = __float_as_uint(hit.t);
-        sh.state[13][tid] = (uint32_t)hit.id | (hit.orient > 0 ? 0x80000000u : 0u);
-        sh.state[14][tid] = (uint32_t)n_ray | ((ray_before + ray_rank) << 2);
-        sh.state[15][tid] = fan_class < 0 ? SP_SLOT_NONE : (((uint32_t)fan_class << 28) | (fan_before + fan_rank));
+#pragma unroll 1
+        for (int pass = 0; pass < SP_RPT; ++pass) {
+            const uint32_t slot = (uint32_t)pass * SP_BLOCK + tid, pr = sh.state[14][slot];
+            const uint32_t vwarp = (uint32_t)pass * SP_N_WARPS + warp;
+            uint32_t col_before = 0;                    // records / rays of this column in earlier (pass, warp)s
+            if (lane < 16)
+                for (uint32_t w = 0; w < vwarp; ++w) col_before += sh.warp_cnt[w][lane];
+            const uint32_t bin = pr & 7u, bin_rank = (pr >> 3) & 31u, n_ray = (pr >> 8) & 3u, ray_rank = (pr >> 10) & 127u;
+            const int fan_class = (int)((pr >> 17) & 7u) - 1;
+            const uint32_t fan_rank = (pr >> 20) & 31u;
+            const uint32_t my_dest = __shfl_sync(0xffffffffu, bin_start + col_before, bin) + bin_rank;
+            const uint32_t ray_before = __shfl_sync(0xffffffffu, col_before, 8);
+            const uint32_t fan_before = __shfl_sync(0xffffffffu, col_before, 9 + max(fan_class, 0));
+            sh.perm[my_dest] = (uint16_t)slot;
+            sh.state[14][slot] = n_ray | ((ray_before + ray_rank) << 2);
+            sh.state[15][slot] = fan_class < 0 ? SP_SLOT_NONE : (((uint32_t)fan_class << 28) | (fan_before + fan_rank));
+        }
         __syncthreads();                                                            // (B) state, perm, bases visible
 
-        // ---- 4. shade in material order, accumulate, write children -----------------------------------------
-        if (tid < sh.n_shade) {
-            const uint32_t j = sh.perm[tid];
-            Ray s;
-            s.o = v3(__uint_as_float(sh.state[0][j]), __uint_as_float(sh.state[1][j]), __uint_as_float(sh.state[2][j]));
-            s.d = v3(__uint_as_float(sh.state[3][j]), __uint_as_float(sh.state[4][j]), __uint_as_float(sh.state[5][j]));
-            s.thr = v3(__uint_as_float(sh.state[6][j]), __uint_as_float(sh.state[7][j]), __uint_as_float(sh.state[8][j]));
-            s.pix = sh.state[9][j]; s.path = sh.state[10][j]; s.meta = sh.state[11][j];
-            HitRec h;
-            h.t = __uint_as_float(sh.state[12][j]);
-            const uint32_t packed = sh.state[13][j];
-            h.id = (int)(packed & 0x7FFFFFFFu); h.orient = (packed & 0x80000000u) ? 1 : -1;
-            const uint32_t rs = sh.state[14][j], fs = sh.state[15][j];
-            const uint32_t need_ray = rs & 3u;
-            const uint32_t rbase = sh.queue_base[0];
-            ctx.ray_slot = (need_ray && rbase != SP_SLOT_NONE) ? rbase + (rs >> 2) : SP_SLOT_NONE;
-            ctx.ray_used = 0u;
-            ctx.fan_slot = SP_SLOT_NONE;
-            if (fs != SP_SLOT_NONE) {
-                const uint32_t fbase = sh.queue_base[1 + (fs >> 28)];
-                if (fbase != SP_SLOT_NONE) ctx.fan_slot = fbase + (fs & 0x0FFFFFFFu);
+        // ---- 4. shade in material order (chunks of 32 handed out on demand), accumulate, write children ------
+        const uint32_t n_shade = sh.n_shade;
+        while (true) {
+            uint32_t chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&sh.next_chunk, 1u);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk * 32u >= n_shade) break;
+            const uint32_t k = chunk * 32u + lane;
+            if (k < n_shade) {
+                const uint32_t j = sh.perm[k];
+                Ray s;
+                s.o = v3(__uint_as_float(sh.state[0][j]), __uint_as_float(sh.state[1][j]), __uint_as_float(sh.state[2][j]));
+                s.d = v3(__uint_as_float(sh.state[3][j]), __uint_as_float(sh.state[4][j]), __uint_as_float(sh.state[5][j]));
+                s.thr = v3(__uint_as_float(sh.state[6][j]), __uint_as_float(sh.state[7][j]), __uint_as_float(sh.state[8][j]));
+                s.pix = sh.state[9][j]; s.path = sh.state[10][j]; s.meta = sh.state[11][j];
+                HitRec h;
+                h.t = __uint_as_float(sh.state[12][j]);
+                const uint32_t packed = sh.state[13][j];
+                h.id = (int)(packed & 0x7FFFFFFFu); h.orient = (packed & 0x80000000u) ? 1 : -1;
+                const uint32_t rs = sh.state[14][j], fs = sh.state[15][j];
+                const uint32_t need_ray = rs & 3u;
+                const uint32_t rbase = sh.queue_base[0];
+                ctx.ray_slot = (need_ray && rbase != SP_SLOT_NONE) ? rbase + (rs >> 2) : SP_SLOT_NONE;
+                ctx.ray_used = 0u;
+                ctx.fan_slot = SP_SLOT_NONE;
+                if (fs != SP_SLOT_NONE) {
+                    const uint32_t fbase = sh.queue_base[1 + (fs >> 28)];
+                    if (fbase != SP_SLOT_NONE) ctx.fan_slot = fbase + (fs & 0x0FFFFFFFu);
+                }
+                const float3 add = sp_shade<FEAT>(ctx, s, h);
+                float* px = reinterpret_cast<float*>(a.accum + s.pix);
+                if (add.x != 0.f) atomicAdd(px, add.x);
+                if (add.y != 0.f) atomicAdd(px + 1, add.y);
+                if (add.z != 0.f) atomicAdd(px + 2, add.z);
+                // reserved but unused slots become dead records
+                if (ctx.ray_slot != SP_SLOT_NONE)
+                    for (uint32_t q = ctx.ray_used; q < need_ray; ++q) sp_write_dead(a.out.rays, ctx.ray_slot + q);
+                if (ctx.fan_slot != SP_SLOT_NONE) sp_write_dead(a.out.fans, ctx.fan_slot);
             }
-            const float3 add = sp_shade<FEAT>(ctx, s, h);
-            float* px = reinterpret_cast<float*>(a.accum + s.pix);
-            if (add.x != 0.f) atomicAdd(px, add.x);
-            if (add.y != 0.f) atomicAdd(px + 1, add.y);
-            if (add.z != 0.f) atomicAdd(px + 2, add.z);
-            // reserved but unused slots become dead records
-            if (ctx.ray_slot != SP_SLOT_NONE)
-                for (uint32_t k = ctx.ray_used; k < need_ray; ++k) sp_write_dead(a.out.rays, ctx.ray_slot + k);
-            if (ctx.fan_slot != SP_SLOT_NONE) sp_write_dead(a.out.fans, ctx.fan_slot);
         }
-        // no barrier here: the next iteration works in the other IterShared buffer, and nobody can
-        // come back to this one before passing that iteration's barriers (A) and (B)
+        __syncthreads();                                                            // (C) the exchange area is free again
     }
 
     // ---- counters: one atomic per warp -------------------------------------------------------------
