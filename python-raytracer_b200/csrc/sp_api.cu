@@ -127,25 +127,49 @@ struct sp_scene {
 static float3 f3(const double* v) { return make_float3((float)v[0], (float)v[1], (float)v[2]); }
 
 // ---- geometry stream construction (layout documented in sp_types.cuh) ------------------------------
-static int type_vec4(int t) {
-    return t == SP_COLLIDER_SPHERE ? SP_V4_SPHERE : t == SP_COLLIDER_PLANE ? SP_V4_PLANE
-         : t == SP_COLLIDER_CUBOID ? SP_V4_CUBOID : SP_V4_TRIANGLE;
+// stream type of a collider: bounded planes whose normal and edge axes are coordinate axes go to the
+// cheap axis-aligned sections
+static int unit_axis(const double* v) {          // index of the axis v is +-1 along, -1 if none
+    int axis = -1;
+    for (int k = 0; k < 3; ++k) {
+        if (v[k] == 0.0) continue;
+        if (std::fabs(v[k]) != 1.0 || axis >= 0) return -1;
+        axis = k;
+    }
+    return axis;
 }
 
-static void pack_collider(const sp_collider& c, float* out) {
+static int stream_type(const sp_collider& c) {
+    if (c.type != SP_COLLIDER_PLANE) return c.type;          // SP_ST_* == SP_COLLIDER_* for the general shapes
+    const int an = unit_axis(c.p + 9), au = unit_axis(c.p + 3), av = unit_axis(c.p + 6);
+    if (an < 0 || au < 0 || av < 0 || an == au || an == av || au == av) return SP_ST_PLANE;
+    return SP_ST_AAX + an;
+}
+
+static int type_vec4(int st) {
+    switch (st) {
+    case SP_ST_SPHERE: return SP_V4_SPHERE;
+    case SP_ST_PLANE: return SP_V4_PLANE;
+    case SP_ST_CUBOID: return SP_V4_CUBOID;
+    case SP_ST_TRI: return SP_V4_TRIANGLE;
+    default: return SP_V4_AARECT;
+    }
+}
+
+static void pack_collider(const sp_collider& c, int st, float* out) {
     const double* p = c.p;
     auto put3 = [&](int at, double x, double y, double z) { out[at] = (float)x; out[at + 1] = (float)y; out[at + 2] = (float)z; };
-    switch (c.type) {
-    case SP_COLLIDER_SPHERE:
+    switch (st) {
+    case SP_ST_SPHERE:
         put3(0, p[0], p[1], p[2]); out[3] = (float)(p[3] * p[3]);
         break;
-    case SP_COLLIDER_PLANE:
+    case SP_ST_PLANE:
         put3(0, p[9], p[10], p[11]);  out[3] = (float)p[12];        // N, w
         put3(4, p[0], p[1], p[2]);    out[7] = (float)p[13];        // C, h
         put3(8, p[3], p[4], p[5]);    out[11] = 0.f;                // U
         put3(12, p[6], p[7], p[8]);   out[15] = 0.f;                // V
         break;
-    case SP_COLLIDER_CUBOID: {
+    case SP_ST_CUBOID: {
         const double* B = p + 21;
         double bc[3], lo[3], hi[3];
         for (int r = 0; r < 3; ++r) {
@@ -160,12 +184,21 @@ static void pack_collider(const sp_collider& c, float* out) {
         out[16] = (float)hi[1]; out[17] = (float)hi[2]; out[18] = 0.f; out[19] = 0.f;
         break;
     }
-    default:   // triangle: N, centroid, n31, p1, n12, p2, n23, p3
+    case SP_ST_TRI:   // N, centroid, n31, p1, n12, p2, n23, p3
         put3(0, p[9], p[10], p[11]);  put3(3, p[12], p[13], p[14]);
         put3(6, p[15], p[16], p[17]); put3(9, p[0], p[1], p[2]);
         put3(12, p[18], p[19], p[20]); put3(15, p[3], p[4], p[5]);
         put3(18, p[21], p[22], p[23]); put3(21, p[6], p[7], p[8]);
         break;
+    default: {        // axis-aligned rectangle: (C, sign of N) (half extents along the in-plane axes, ascending)
+        const int an = st - SP_ST_AAX, au = unit_axis(p + 3);
+        const int b = an == 0 ? 1 : 0;                   // lower in-plane axis
+        put3(0, p[0], p[1], p[2]); out[3] = (float)p[9 + an];
+        out[4] = (float)(au == b ? p[12] : p[13]);       // w belongs to u_axis, h to v_axis
+        out[5] = (float)(au == b ? p[13] : p[12]);
+        out[6] = 0.f; out[7] = 0.f;
+        break;
+    }
     }
 }
 
@@ -180,15 +213,17 @@ static BuiltStream build_stream(const std::vector<sp_collider>& cols, std::vecto
     BuiltStream bs;
     bs.slot.assign(cols.size(), make_int2(-1, -1));
     bs.n_items = (int)ids.size();
-    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return cols[a].type < cols[b].type; });
+    std::vector<int> st(cols.size());
+    for (size_t i = 0; i < cols.size(); ++i) st[i] = stream_type(cols[i]);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return st[a] < st[b]; });
     bs.chunk_off.push_back(0);
     size_t pos = 0;
     while (pos < ids.size()) {
         // greedy fill of one chunk
-        int cnt[4] = {0, 0, 0, 0}, vec4 = 4;
+        int cnt[7] = {0, 0, 0, 0, 0, 0, 0}, vec4 = 4;
         size_t end = pos;
         while (end < ids.size()) {
-            const int t = cols[ids[end]].type;
+            const int t = st[ids[end]];
             const int items = (int)(end - pos) + 1;
             const int need = vec4 + type_vec4(t) + (items + 3) / 4;
             if (need > SP_CHUNK_VEC4) break;
@@ -199,25 +234,31 @@ static BuiltStream build_stream(const std::vector<sp_collider>& cols, std::vecto
         const int items = (int)(end - pos);
         GeomChunkHeader h{};
         h.n_sphere = cnt[0]; h.n_plane = cnt[1]; h.n_cuboid = cnt[2]; h.n_tri = cnt[3];
+        h.n_aax = cnt[4]; h.n_aay = cnt[5]; h.n_aaz = cnt[6];
         h.off_sphere = 4;
         h.off_plane = h.off_sphere + cnt[0] * SP_V4_SPHERE;
         h.off_cuboid = h.off_plane + cnt[1] * SP_V4_PLANE;
         h.off_tri = h.off_cuboid + cnt[2] * SP_V4_CUBOID;
-        h.off_ids = h.off_tri + cnt[3] * SP_V4_TRIANGLE;
+        h.off_aa = h.off_tri + cnt[3] * SP_V4_TRIANGLE;
+        h.off_ids = h.off_aa + (cnt[4] + cnt[5] + cnt[6]) * SP_V4_AARECT;
         h.n_vec4 = h.off_ids + (items + 3) / 4;
         std::vector<float4> chunk((size_t)h.n_vec4, make_float4(0, 0, 0, 0));
         memcpy(chunk.data(), &h, sizeof h);
         float* fl = reinterpret_cast<float*>(chunk.data());
         int* idp = reinterpret_cast<int*>(chunk.data() + h.off_ids);
-        int at = 4 * 4, local[4] = {0, 0, 0, 0};
+        int at = 4 * 4, local[7] = {0, 0, 0, 0, 0, 0, 0};
         const int chunk_index = (int)bs.chunk_off.size() - 1;
         for (size_t k = pos; k < end; ++k) {
             const sp_collider& c = cols[ids[k]];
-            pack_collider(c, fl + at);
-            at += 4 * type_vec4(c.type);
+            const int t = st[ids[k]];
+            pack_collider(c, t, fl + at);
+            at += 4 * type_vec4(t);
             idp[k - pos] = ids[k];
-            bs.slot[ids[k]] = make_int2(chunk_index, (c.type << 28) | local[c.type]);
-            local[c.type]++;
+            // the three axis-aligned sections share one index space (code 4)
+            const int aa_index = t == SP_ST_AAX ? local[4] : t == SP_ST_AAY ? cnt[4] + local[5] : cnt[4] + cnt[5] + local[6];
+            bs.slot[ids[k]] = t >= SP_ST_AAX ? make_int2(chunk_index, (4 << 28) | aa_index)
+                                             : make_int2(chunk_index, (t << 28) | local[t]);
+            local[t]++;
         }
         bs.data.insert(bs.data.end(), chunk.begin(), chunk.end());
         bs.chunk_off.push_back((int)bs.data.size());
@@ -225,7 +266,7 @@ static BuiltStream build_stream(const std::vector<sp_collider>& cols, std::vecto
     }
     if (ids.empty()) {                       // an empty stream still has one (empty) chunk
         GeomChunkHeader h{};
-        h.off_sphere = h.off_plane = h.off_cuboid = h.off_tri = h.off_ids = h.n_vec4 = 4;
+        h.off_sphere = h.off_plane = h.off_cuboid = h.off_tri = h.off_aa = h.off_ids = h.n_vec4 = 4;
         std::vector<float4> chunk(4, make_float4(0, 0, 0, 0));
         memcpy(chunk.data(), &h, sizeof h);
         bs.data = chunk;

@@ -24,7 +24,7 @@ struct HitRec {
 };
 
 // where the ray's source collider sits inside the current chunk (-1 = not in this chunk)
-struct SelfSlot { int sphere, plane, cuboid, tri; uint32_t mode; };
+struct SelfSlot { int sphere, plane, cuboid, tri, aa; uint32_t mode; };
 
 struct ChunkBest { float t; int idx; int orient; };   // idx = position in the chunk's id array
 
@@ -115,6 +115,38 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
                 best.t = t; best.idx = n_sphere + n_plane + n_cuboid + i; best.orient = nd < 0.f ? 1 : -1;
             }
         }
+    }
+    // ---- axis-aligned rectangles -----------------------------------------------------------------
+    {
+        const int n_aax = h->n_aax, n_aay = h->n_aay, n_aaz = h->n_aaz;
+        if (n_aax + n_aay + n_aaz > 0) {
+            const float4* aa = ch + h->off_aa;
+            const int id_base = n_sphere + n_plane + n_cuboid + n_tri;
+            // 1/0 = inf sends the hit point of an axis-parallel ray out of bounds (the reference
+            // substitutes N.D = 1e-4 there and misses all the same)
+            if (n_aax > 0) sp_intersect_aa<0>(aa, 0, n_aax, id_base, O, D, __frcp_rn(D.x), self.aa, best);
+            if (n_aay > 0) sp_intersect_aa<1>(aa, n_aax, n_aay, id_base, O, D, __frcp_rn(D.y), self.aa, best);
+            if (n_aaz > 0) sp_intersect_aa<2>(aa, n_aax + n_aay, n_aaz, id_base, O, D, __frcp_rn(D.z), self.aa, best);
+        }
+    }
+}
+
+// One axis-aligned rectangle section: normal along axis A (0, 1, 2), in-plane axes B < C.
+template <int A>
+SP_DEV void sp_intersect_aa(const float4* __restrict__ aa, int first, int count, int id_base, float3 O, float3 D,
+                            float inv_da, int self_aa, ChunkBest& best) {
+    const float oa = A == 0 ? O.x : (A == 1 ? O.y : O.z), da = A == 0 ? D.x : (A == 1 ? D.y : D.z);
+    const float ob = A == 0 ? O.y : O.x, db = A == 0 ? D.y : D.x;
+    const float oc = A == 2 ? O.y : O.z, dc = A == 2 ? D.y : D.z;
+#pragma unroll 2
+    for (int i = first; i < first + count; ++i) {
+        const float4 r0 = aa[2 * i], r1 = aa[2 * i + 1];
+        const float ca = A == 0 ? r0.x : (A == 1 ? r0.y : r0.z);
+        const float cb = A == 0 ? r0.y : r0.x, cc = A == 2 ? r0.y : r0.z;
+        const float t = (ca - oa) * inv_da;                        // k / N.D with the normal's sign cancelled
+        const float pb = fmaf(t, db, ob) - cb, pc = fmaf(t, dc, oc) - cc;
+        const bool ok = (fabsf(pb) <= r1.x) && (fabsf(pc) <= r1.y) && (t > 0.f) && (i != self_aa);
+        if (ok && t < best.t) { best.t = t; best.idx = id_base + i; best.orient = (r0.w * da < 0.f) ? 1 : -1; }
     }
 }
 

@@ -212,11 +212,11 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                     __syncthreads();
                 }
                 if (need_test) {
-                    SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = -1; self.mode = mode;
+                    SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = self.aa = -1; self.mode = mode;
                     if (where.x == c) {
                         const int ty = where.y >> 28, li = where.y & 0x0FFFFFFF;
                         if (ty == 0) self.sphere = li; else if (ty == 1) self.plane = li;
-                        else if (ty == 2) self.cuboid = li; else self.tri = li;
+                        else if (ty == 2) self.cuboid = li; else if (ty == 3) self.tri = li; else self.aa = li;
                     }
                     ChunkBest best; best.t = hit.t; best.idx = -1; best.orient = 0;
                     sp_intersect_chunk(s_geom, r.o, r.d, self, best);

@@ -153,11 +153,11 @@ SP_DEV float sp_shadow_nearest(const DScene& sc, float3 o, float3 d, int src_id,
     int2 where = (src_id >= 0 && shadow_slot) ? __ldg(shadow_slot + src_id) : make_int2(-1, -1);
     for (int c = 0; c < sc.shadow.n_chunks; ++c) {
         const float4* ch = sc.shadow.data + __ldg(sc.shadow.chunk_off + c);
-        SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = -1; self.mode = mode;
+        SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = self.aa = -1; self.mode = mode;
         if (where.x == c) {
             int ty = where.y >> 28, li = where.y & 0x0FFFFFFF;
             if (ty == 0) self.sphere = li; else if (ty == 1) self.plane = li;
-            else if (ty == 2) self.cuboid = li; else self.tri = li;
+            else if (ty == 2) self.cuboid = li; else if (ty == 3) self.tri = li; else self.aa = li;
         }
         sp_intersect_chunk(ch, o, d, self, best);
     }
