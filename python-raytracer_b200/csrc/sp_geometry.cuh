@@ -28,6 +28,25 @@ struct SelfSlot { int sphere, plane, cuboid, tri, aa; uint32_t mode; };
 
 struct ChunkBest { float t; int idx; int orient; };   // idx = position in the chunk's id array
 
+// One axis-aligned rectangle section: normal along axis A (0, 1, 2), in-plane axes B < C.
+template <int A>
+SP_DEV void sp_intersect_aa(const float4* __restrict__ aa, int first, int count, int id_base, float3 O, float3 D,
+                            float inv_da, int self_aa, ChunkBest& best) {
+    const float oa = A == 0 ? O.x : (A == 1 ? O.y : O.z), da = A == 0 ? D.x : (A == 1 ? D.y : D.z);
+    const float ob = A == 0 ? O.y : O.x, db = A == 0 ? D.y : D.x;
+    const float oc = A == 2 ? O.y : O.z, dc = A == 2 ? D.y : D.z;
+#pragma unroll 2
+    for (int i = first; i < first + count; ++i) {
+        const float4 r0 = aa[2 * i], r1 = aa[2 * i + 1];
+        const float ca = A == 0 ? r0.x : (A == 1 ? r0.y : r0.z);
+        const float cb = A == 0 ? r0.y : r0.x, cc = A == 2 ? r0.y : r0.z;
+        const float t = (ca - oa) * inv_da;                        // k / N.D with the normal's sign cancelled
+        const float pb = fmaf(t, db, ob) - cb, pc = fmaf(t, dc, oc) - cc;
+        const bool ok = (fabsf(pb) <= r1.x) && (fabsf(pc) <= r1.y) && (t > 0.f) && (i != self_aa);
+        if (ok && t < best.t) { best.t = t; best.idx = id_base + i; best.orient = (r0.w * da < 0.f) ? 1 : -1; }
+    }
+}
+
 SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D, SelfSlot self,
                                ChunkBest& best) {
     const GeomChunkHeader* h = reinterpret_cast<const GeomChunkHeader*>(ch);
@@ -128,25 +147,6 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
             if (n_aay > 0) sp_intersect_aa<1>(aa, n_aax, n_aay, id_base, O, D, __frcp_rn(D.y), self.aa, best);
             if (n_aaz > 0) sp_intersect_aa<2>(aa, n_aax + n_aay, n_aaz, id_base, O, D, __frcp_rn(D.z), self.aa, best);
         }
-    }
-}
-
-// One axis-aligned rectangle section: normal along axis A (0, 1, 2), in-plane axes B < C.
-template <int A>
-SP_DEV void sp_intersect_aa(const float4* __restrict__ aa, int first, int count, int id_base, float3 O, float3 D,
-                            float inv_da, int self_aa, ChunkBest& best) {
-    const float oa = A == 0 ? O.x : (A == 1 ? O.y : O.z), da = A == 0 ? D.x : (A == 1 ? D.y : D.z);
-    const float ob = A == 0 ? O.y : O.x, db = A == 0 ? D.y : D.x;
-    const float oc = A == 2 ? O.y : O.z, dc = A == 2 ? D.y : D.z;
-#pragma unroll 2
-    for (int i = first; i < first + count; ++i) {
-        const float4 r0 = aa[2 * i], r1 = aa[2 * i + 1];
-        const float ca = A == 0 ? r0.x : (A == 1 ? r0.y : r0.z);
-        const float cb = A == 0 ? r0.y : r0.x, cc = A == 2 ? r0.y : r0.z;
-        const float t = (ca - oa) * inv_da;                        // k / N.D with the normal's sign cancelled
-        const float pb = fmaf(t, db, ob) - cb, pc = fmaf(t, dc, oc) - cc;
-        const bool ok = (fabsf(pb) <= r1.x) && (fabsf(pc) <= r1.y) && (t > 0.f) && (i != self_aa);
-        if (ok && t < best.t) { best.t = t; best.idx = id_base + i; best.orient = (r0.w * da < 0.f) ? 1 : -1; }
     }
 }
 
