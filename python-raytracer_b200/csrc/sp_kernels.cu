@@ -56,13 +56,19 @@ SP_DEV void sp_stage_chunk(float4* __restrict__ dst, const DScene& sc, const Geo
 #define SP_N_VWARPS (SP_N_WARPS * SP_RPT)
 // material kind -> shading bin, dearest first: Refractive, Glossy, ThinFilm, Diffuse, SkyBox, Emissive
 #define SP_BIN_OF_KIND(kind) ((0x453201u >> (4u * (kind))) & 15u)
+struct IterCounters {
+    uint32_t bin_cnt[8];                           // rays per bin
+    uint32_t queue_cnt[8];                         // records this iteration appends to each output queue
+    uint32_t queue_base[8];                        // the CTA's reservation in each output queue
+    uint32_t arrived;                              // (pass, warp)s that have counted; the last one reserves
+    uint32_t next_chunk;                           // next 32-ray shading chunk up for grabs
+    uint32_t pad[6];
+};
 struct IterShared {
     uint32_t state[SP_STATE_WORDS][SP_BATCH];      // SoA: o d thr pix path meta t (id|orient) ray_slot fan_slot
-    uint16_t perm[SP_BATCH];                       // perm[k] = batch slot of the k-th ray in shading order
-    uint32_t warp_cnt[SP_N_VWARPS][16];            // per (pass, warp): [0..6] bins, [8..12] queue records
-    uint32_t queue_base[SP_N_QUEUES];              // CTA's reservation in each output queue
-    uint32_t n_shade;                              // rays with something to shade this iteration
-    uint32_t next_chunk;                           // next 32-ray shading chunk up for grabs
+    uint16_t list[SP_N_BINS - 1][SP_BATCH];        // per shading bin: batch slots of the rays that hit that kind
+    IterCounters cnt[2];                           // alternate between iterations: the idle set is cleared
+                                                   // while the other is in use, which saves a barrier
 };
 
 template <uint32_t FEAT>
@@ -104,8 +110,12 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     ctx.shadow_rays = 0;
     unsigned long long traced = 0;
 
+    if (tid < sizeof(sh.cnt) / sizeof(uint32_t)) reinterpret_cast<uint32_t*>(sh.cnt)[tid] = 0u;
+    __syncthreads();
+    uint32_t parity = 0;
     for (unsigned long long base64 = (unsigned long long)blockIdx.x * SP_BATCH; base64 < total;
-         base64 += (unsigned long long)gridDim.x * SP_BATCH) {
+         base64 += (unsigned long long)gridDim.x * SP_BATCH, parity ^= 1u) {
+        IterCounters& cn = sh.cnt[parity];
         const uint32_t base = (uint32_t)base64;
         // the pass loop is deliberately not unrolled: one copy of the generate/intersect code in the
         // instruction cache
@@ -248,92 +258,90 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
             bin = (int)SP_BIN_OF_KIND(ci.kind);
             sp_child_needs(ci, meta_depth(r.meta), meta_dr(r.meta), n_ray, fan_class);
         }
-        const uint32_t vwarp = (uint32_t)pass * SP_N_WARPS + warp;
-        if (lane < 16) sh.warp_cnt[vwarp][lane] = 0u;
-        __syncwarp();
-        const uint32_t bin_peers = __match_any_sync(0xffffffffu, bin);
-        const uint32_t bin_rank = __popc(bin_peers & lt_mask);
-        if (bin_rank == 0) sh.warp_cnt[vwarp][bin] = __popc(bin_peers);
-        const uint32_t b0 = __ballot_sync(0xffffffffu, n_ray & 1), b1 = __ballot_sync(0xffffffffu, n_ray & 2);
-        const uint32_t ray_rank = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
-        if (lane == 0) sh.warp_cnt[vwarp][8] = __popc(b0) + 2u * __popc(b1);
-        uint32_t fan_rank = 0;
-#pragma unroll
-        for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) {
-            if (c < sc.n_fan_classes) {
-                const uint32_t bc = __ballot_sync(0xffffffffu, fan_class == c);
-                if (fan_class == c) fan_rank = __popc(bc & lt_mask);
-                if (lane == 0) sh.warp_cnt[vwarp][9 + c] = __popc(bc);
-            }
+        // position inside the bin, and inside this iteration's appends to the output queues: one
+        // shared-memory atomic per warp and distinct bin / queue
+        if (bin < SP_N_BINS - 1) {
+            const uint32_t peers = __match_any_sync(__activemask(), bin);
+            uint32_t pos = 0;
+            const int leader = __ffs(peers) - 1;
+            if ((int)lane == leader) pos = atomicAdd(&cn.bin_cnt[bin], (uint32_t)__popc(peers));
+            pos = __shfl_sync(peers, pos, leader) + __popc(peers & lt_mask);
+            sh.list[bin][pos] = (uint16_t)slot;
         }
-        // ranks inside the warp, parked until the CTA-wide offsets are known:
-        // bin[0:3) bin_rank[3:8) n_ray[8:10) ray_rank[10:17) fan_class+1[17:20) fan_rank[20:25)
-        sh.state[14][slot] = (uint32_t)bin | (bin_rank << 3) | ((uint32_t)n_ray << 8) | (ray_rank << 10) |
-                             ((uint32_t)(fan_class + 1) << 17) | (fan_rank << 20);
+        {
+            const uint32_t b0 = __ballot_sync(0xffffffffu, n_ray & 1), b1 = __ballot_sync(0xffffffffu, n_ray & 2);
+            const uint32_t warp_rays = __popc(b0) + 2u * __popc(b1);
+            uint32_t ray_off = 0;
+            if (warp_rays) {
+                if (lane == 0) ray_off = atomicAdd(&cn.queue_cnt[0], warp_rays);
+                ray_off = __shfl_sync(0xffffffffu, ray_off, 0) + __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
+            }
+            sh.state[14][slot] = (uint32_t)n_ray | (ray_off << 2);
+            uint32_t fan_word = SP_SLOT_NONE;
+            if (FEAT & SP_F_DIFFUSE) {
+                const uint32_t fan_any = __ballot_sync(0xffffffffu, fan_class >= 0);
+                if (fan_any) {
+#pragma unroll
+                    for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) {
+                        const uint32_t bc = __ballot_sync(0xffffffffu, fan_class == c);
+                        if (bc) {
+                            uint32_t off = 0;
+                            if (lane == 0) off = atomicAdd(&cn.queue_cnt[1 + c], (uint32_t)__popc(bc));
+                            off = __shfl_sync(0xffffffffu, off, 0) + __popc(bc & lt_mask);
+                            if (fan_class == c) fan_word = ((uint32_t)c << 28) | off;
+                        }
+                    }
+                }
+            }
+            sh.state[15][slot] = fan_word;
+        }
+        // the last (pass, warp) to get here knows the totals: it reserves the CTA's slots in the
+        // output queues (one global atomic per queue that receives something)
+        __syncwarp();
+        uint32_t ticket = 0;
+        if (lane == 0) { __threadfence_block(); ticket = atomicAdd(&cn.arrived, 1u); }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == SP_N_VWARPS - 1u && lane < SP_N_QUEUES) {
+            __threadfence_block();
+            const uint32_t want = cn.queue_cnt[lane];
+            const uint32_t cap = (lane == 0) ? a.out.rays.capacity : a.out.fan_cap[lane - 1];
+            uint32_t first = SP_SLOT_NONE;
+            if (want > 0) {
+                first = atomicAdd(a.out.counts + lane, want);
+                if (first + want > cap) { first = SP_SLOT_NONE; a.out.stats->overflow = 1u; }
+                else if (lane > 0) first += a.out.fan_base[lane - 1];
+            }
+            cn.queue_base[lane] = first;
+        }
         }   // pass
         if ((FEAT & SP_F_LEVEL0) && a.run != SP_RUN_FULL) continue;
-        if (tid == 0) sh.next_chunk = 0u;
-        __syncthreads();                                                            // (A) counts visible
+        __syncthreads();                                                            // (A) everything parked
+        // clear the other counter set: last touched before barrier (C) of the previous iteration,
+        // next touched after barrier (C) of this one
+        if (tid < sizeof(IterCounters) / sizeof(uint32_t)) reinterpret_cast<uint32_t*>(&sh.cnt[parity ^ 1u])[tid] = 0u;
 
-        // every warp derives the CTA-wide offsets it needs from the (pass, warp) x 16 count table:
-        // lane l < 16 owns column l (a bin or a queue)
-        uint32_t col_total = 0;
-        if (lane < 16) {
+        // ---- 4. shade bin by bin (32-ray chunks handed out on demand), accumulate, write children -----------
+        uint32_t bin_chunks_end[SP_N_BINS - 1];         // running number of chunks up to and including each bin
+        {
+            uint32_t run = 0;
 #pragma unroll
-            for (int w = 0; w < SP_N_VWARPS; ++w) col_total += sh.warp_cnt[w][lane];
+            for (int b = 0; b < SP_N_BINS - 1; ++b) { run += (cn.bin_cnt[b] + 31u) >> 5; bin_chunks_end[b] = run; }
         }
-        // exclusive scan of the bin totals over lanes 0..6 (bins are laid out one after the other)
-        uint32_t bin_start = (lane < SP_N_BINS) ? col_total : 0u;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, bin_start, o);
-            if (lane >= (uint32_t)o && lane < 8) bin_start += up;
-        }
-        bin_start -= (lane < SP_N_BINS) ? col_total : 0u;
-        if (warp == 0) {
-            // one reservation per output queue for the whole CTA
-            if (lane >= 8 && lane < 8 + SP_N_QUEUES) {
-                const int q = (int)lane - 8;
-                const uint32_t cap = (q == 0) ? a.out.rays.capacity : a.out.fan_cap[q - 1];
-                uint32_t first = SP_SLOT_NONE;
-                if (col_total > 0) {
-                    first = atomicAdd(a.out.counts + q, col_total);
-                    if (first + col_total > cap) { first = SP_SLOT_NONE; a.out.stats->overflow = 1u; }
-                    else if (q > 0) first += a.out.fan_base[q - 1];
-                }
-                sh.queue_base[q] = first;
-            }
-            if (lane == SP_N_BINS - 1) sh.n_shade = bin_start;     // start of the "nothing" bin = rays to shade
-        }
-#pragma unroll 1
-        for (int pass = 0; pass < SP_RPT; ++pass) {
-            const uint32_t slot = (uint32_t)pass * SP_BLOCK + tid, pr = sh.state[14][slot];
-            const uint32_t vwarp = (uint32_t)pass * SP_N_WARPS + warp;
-            uint32_t col_before = 0;                    // records / rays of this column in earlier (pass, warp)s
-            if (lane < 16)
-                for (uint32_t w = 0; w < vwarp; ++w) col_before += sh.warp_cnt[w][lane];
-            const uint32_t bin = pr & 7u, bin_rank = (pr >> 3) & 31u, n_ray = (pr >> 8) & 3u, ray_rank = (pr >> 10) & 127u;
-            const int fan_class = (int)((pr >> 17) & 7u) - 1;
-            const uint32_t fan_rank = (pr >> 20) & 31u;
-            const uint32_t my_dest = __shfl_sync(0xffffffffu, bin_start + col_before, bin) + bin_rank;
-            const uint32_t ray_before = __shfl_sync(0xffffffffu, col_before, 8);
-            const uint32_t fan_before = __shfl_sync(0xffffffffu, col_before, 9 + max(fan_class, 0));
-            sh.perm[my_dest] = (uint16_t)slot;
-            sh.state[14][slot] = n_ray | ((ray_before + ray_rank) << 2);
-            sh.state[15][slot] = fan_class < 0 ? SP_SLOT_NONE : (((uint32_t)fan_class << 28) | (fan_before + fan_rank));
-        }
-        __syncthreads();                                                            // (B) state, perm, bases visible
-
-        // ---- 4. shade in material order (chunks of 32 handed out on demand), accumulate, write children ------
-        const uint32_t n_shade = sh.n_shade;
         while (true) {
             uint32_t chunk = 0;
-            if (lane == 0) chunk = atomicAdd(&sh.next_chunk, 1u);
+            if (lane == 0) chunk = atomicAdd(&cn.next_chunk, 1u);
             chunk = __shfl_sync(0xffffffffu, chunk, 0);
-            if (chunk * 32u >= n_shade) break;
-            const uint32_t k = chunk * 32u + lane;
-            if (k < n_shade) {
-                const uint32_t j = sh.perm[k];
+            if (chunk >= bin_chunks_end[SP_N_BINS - 2]) break;
+            int b = 0;
+#pragma unroll
+            for (int q = 0; q < SP_N_BINS - 2; ++q) b += (chunk >= bin_chunks_end[q]) ? 1 : 0;
+            uint32_t chunk_in_bin = chunk;
+#pragma unroll
+            for (int q = 0; q < SP_N_BINS - 2; ++q) if (b == q + 1) chunk_in_bin = chunk - bin_chunks_end[q];
+            const uint32_t k = chunk_in_bin * 32u + lane;
+            if (k < cn.bin_cnt[b]) {
+                const uint32_t j = sh.list[b][k];
+
                 Ray s;
                 s.o = v3(__uint_as_float(sh.state[0][j]), __uint_as_float(sh.state[1][j]), __uint_as_float(sh.state[2][j]));
                 s.d = v3(__uint_as_float(sh.state[3][j]), __uint_as_float(sh.state[4][j]), __uint_as_float(sh.state[5][j]));
@@ -345,12 +353,12 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 h.id = (int)(packed & 0x7FFFFFFFu); h.orient = (packed & 0x80000000u) ? 1 : -1;
                 const uint32_t rs = sh.state[14][j], fs = sh.state[15][j];
                 const uint32_t need_ray = rs & 3u;
-                const uint32_t rbase = sh.queue_base[0];
+                const uint32_t rbase = cn.queue_base[0];
                 ctx.ray_slot = (need_ray && rbase != SP_SLOT_NONE) ? rbase + (rs >> 2) : SP_SLOT_NONE;
                 ctx.ray_used = 0u;
                 ctx.fan_slot = SP_SLOT_NONE;
                 if (fs != SP_SLOT_NONE) {
-                    const uint32_t fbase = sh.queue_base[1 + (fs >> 28)];
+                    const uint32_t fbase = cn.queue_base[1 + (fs >> 28)];
                     if (fbase != SP_SLOT_NONE) ctx.fan_slot = fbase + (fs & 0x0FFFFFFFu);
                 }
                 const float3 add = sp_shade<FEAT>(ctx, s, h);
