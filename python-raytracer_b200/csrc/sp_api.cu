@@ -31,6 +31,35 @@ static int fail(const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail("%s: %s", #expr, cudaGetErrorString(e__));            \
     } while (0)
 
+// Device allocations are recycled through a process-wide free list keyed by size instead of going back
+// to the driver when a scene is destroyed: Scene.render after an edit builds a new sp_scene with the same
+// buffer sizes, and cudaMalloc / cudaFree of the multi-GB wavefront queues (plus the device-wide
+// synchronisation every cudaFree implies) would otherwise cost tens of milliseconds to seconds per frame.
+// sp_shutdown returns everything to the driver.
+#include <map>
+static std::multimap<size_t, void*> g_pool;
+
+static void pool_flush() {
+    for (auto& b : g_pool) cudaFree(b.second);
+    g_pool.clear();
+}
+
+static cudaError_t pool_get(void** out, size_t bytes) {
+    auto it = g_pool.find(bytes);
+    if (it != g_pool.end()) {
+        *out = it->second;
+        g_pool.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess && !g_pool.empty()) {          // make room and retry once
+        cudaGetLastError();
+        pool_flush();
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -38,29 +67,35 @@ template <typename T> struct DevBuf {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc(&p, count * sizeof(T));
+        return pool_get(reinterpret_cast<void**>(&p), count * sizeof(T));
     }
     cudaError_t upload(const std::vector<T>& h) {
         cudaError_t e = alloc(h.size());
         if (e != cudaSuccess || h.empty()) return e;
         return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) g_pool.emplace(n * sizeof(T), p); p = nullptr; n = 0; }
 };
 
 struct HostTexture { int H, W, decode; std::vector<uint32_t> texels; };
 
 struct QueueSet {
     DevBuf<float4> q0, q1, q2;
+    size_t n = 0;
     RayQueue view(uint32_t cap) { RayQueue q; q.q0 = q0.p; q.q1 = q1.p; q.q2 = q2.p; q.capacity = cap; return q; }
-    cudaError_t alloc(size_t n) {
+    cudaError_t alloc(size_t count) {
         cudaError_t e;
-        if ((e = q0.alloc(n)) != cudaSuccess) return e;
-        if ((e = q1.alloc(n)) != cudaSuccess) return e;
-        return q2.alloc(n);
+        n = count;
+        if ((e = q0.alloc(count)) != cudaSuccess) return e;
+        if ((e = q1.alloc(count)) != cudaSuccess) return e;
+        return q2.alloc(count);
     }
-    void release() { q0.release(); q1.release(); q2.release(); }
+    void release() { q0.release(); q1.release(); q2.release(); n = 0; }
 };
+
+// streams and events are recycled the same way
+static std::vector<cudaStream_t> g_stream_pool;
+static std::vector<cudaEvent_t> g_event_pool;
 
 struct sp_scene {
     // ---- host description ---------------------------------------------------------------------
@@ -114,9 +149,9 @@ struct sp_scene {
         slot_all.release(); slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
-        for (auto e : events) cudaEventDestroy(e);
+        for (auto e : events) g_event_pool.push_back(e);
         events.clear();
-        if (own_stream) cudaStreamDestroy(own_stream);
+        if (own_stream) { cudaStreamSynchronize(own_stream); g_stream_pool.push_back(own_stream); }
         own_stream = nullptr;
         stream = nullptr;
         d_lin.release(); d_u8.release();
@@ -323,6 +358,11 @@ int sp_init(int device) {
 
 void sp_shutdown(void) {
     if (g_device >= 0) cudaDeviceSynchronize();
+    pool_flush();
+    for (auto st : g_stream_pool) cudaStreamDestroy(st);
+    g_stream_pool.clear();
+    for (auto e : g_event_pool) cudaEventDestroy(e);
+    g_event_pool.clear();
     g_device = -1;
 }
 
@@ -461,7 +501,8 @@ int sp_scene_commit(sp_scene* s) {
 
     s->release_device();
     CUDA_TRY(cudaSetDevice(g_device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    if (!g_stream_pool.empty()) { s->own_stream = g_stream_pool.back(); g_stream_pool.pop_back(); }
+    else CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     s->stream = s->user_stream_set ? s->user_stream : s->own_stream;
     DScene& d = s->d;
     memset(&d, 0, sizeof d);
@@ -603,7 +644,10 @@ int sp_scene_commit(sp_scene* s) {
     CUDA_TRY(s->counts.alloc((size_t)(SP_MAX_LEVELS + 1) * SP_COUNTS_PER_LEVEL));
     CUDA_TRY(s->d_stats.alloc(1));
     s->events.resize((size_t)s->n_levels + 1);
-    for (auto& e : s->events) CUDA_TRY(cudaEventCreate(&e));
+    for (auto& e : s->events) {
+        if (!g_event_pool.empty()) { e = g_event_pool.back(); g_event_pool.pop_back(); }
+        else CUDA_TRY(cudaEventCreate(&e));
+    }
     uint32_t needed = 0;
     for (int i = 0; i < n_col; ++i) {
         const sp_material& m = s->mats[s->prims[s->cols[i].primitive].material];
@@ -638,7 +682,7 @@ static int ensure_queues(sp_scene* s) {
         for (int i = 0; i < 2; ++i) CUDA_TRY(s->ray_q[i].alloc(want_ray));
         s->ray_cap = want_ray;
     }
-    if (want_fan != s->fan_cap || s->fan_q[0].q0.n != (size_t)want_fan * s->d.n_fan_classes) {
+    if (want_fan != s->fan_cap || s->fan_q[0].n != (size_t)want_fan * s->d.n_fan_classes) {
         for (int i = 0; i < 2; ++i) CUDA_TRY(s->fan_q[i].alloc((size_t)want_fan * s->d.n_fan_classes));
         s->fan_cap = want_fan;
     }
