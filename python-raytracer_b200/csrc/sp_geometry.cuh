@@ -98,7 +98,7 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
             float3 oc = O - xyz(c);
             float3 Ol = v3(dot(xyz(r0), oc), dot(xyz(r1), oc), dot(xyz(r2), oc));
             float3 Dl = v3(dot(xyz(r0), D), dot(xyz(r1), D), dot(xyz(r2), D));
-            float ix = __frcp_rn(Dl.x), iy = __frcp_rn(Dl.y), iz = __frcp_rn(Dl.z);   // +-inf for axis-parallel rays, as 1/0
+            float ix = fast_rcp(Dl.x), iy = fast_rcp(Dl.y), iz = fast_rcp(Dl.z);   // +-inf for axis-parallel rays, as 1/0
             float t1 = (r0.w - Ol.x) * ix, t2 = (c.w - Ol.x) * ix;
             float t3 = (r1.w - Ol.y) * iy, t4 = (e.x - Ol.y) * iy;
             float t5 = (r2.w - Ol.z) * iz, t6 = (e.y - Ol.z) * iz;
@@ -143,9 +143,9 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
             const int id_base = n_sphere + n_plane + n_cuboid + n_tri;
             // 1/0 = inf sends the hit point of an axis-parallel ray out of bounds (the reference
             // substitutes N.D = 1e-4 there and misses all the same)
-            if (n_aax > 0) sp_intersect_aa<0>(aa, 0, n_aax, id_base, O, D, __frcp_rn(D.x), self.aa, best);
-            if (n_aay > 0) sp_intersect_aa<1>(aa, n_aax, n_aay, id_base, O, D, __frcp_rn(D.y), self.aa, best);
-            if (n_aaz > 0) sp_intersect_aa<2>(aa, n_aax + n_aay, n_aaz, id_base, O, D, __frcp_rn(D.z), self.aa, best);
+            if (n_aax > 0) sp_intersect_aa<0>(aa, 0, n_aax, id_base, O, D, fast_rcp(D.x), self.aa, best);
+            if (n_aay > 0) sp_intersect_aa<1>(aa, n_aax, n_aay, id_base, O, D, fast_rcp(D.y), self.aa, best);
+            if (n_aaz > 0) sp_intersect_aa<2>(aa, n_aax + n_aay, n_aaz, id_base, O, D, fast_rcp(D.z), self.aa, best);
         }
     }
 }

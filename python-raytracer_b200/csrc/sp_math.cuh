@@ -32,6 +32,7 @@ SP_DEV float3 normalize0(float3 a) {
 }
 // sqrt.approx / sin.approx / cos.approx (MUFU, ~1e-6 relative): used where the result feeds a random
 // direction or a hit distance, never a texel index
+SP_DEV float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // 1/0 = inf
 SP_DEV float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // sin and cos of 2*pi*u for u in [0, 1): evaluated at 2*pi*(u - 0.5), where the MUFU approximations are
 // accurate to ~5e-7 absolute, and negated (sin(x + pi) = -sin x)
