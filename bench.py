@@ -289,6 +289,9 @@ def run_native(args):
     level_s = totals["level_ms"] * 1e-3
     n_launch = max(totals["level_launches"], 1)
     flops = FLOP_PER_RAY_CORNELL * totals["rays"]
+    traffic_file = REPO / "profiles" / "r1_v8_dram_per_ray.json"       # from the committed ncu --set full capture
+    dram_per_ray = json.loads(traffic_file.read_text())["dram_bytes_per_ray"] if traffic_file.exists() else None
+    traffic = dram_per_ray * totals["rays"] / n_launch if dram_per_ray else None
     roofline = {
         "bound": "fp32", "kernel": "sp_level_kernel",
         "achieved": flops / level_s / 1e12, "peak": live["fp32_tflops"], "unit": "TFLOP/s",
@@ -296,12 +299,15 @@ def run_native(args):
         "peak_source": "FFMA chain micro-benchmark run by this process (sp_measure_peaks); MEASURED_PEAKS.json has no FP32 entry",
         "flop_per_ray": FLOP_PER_RAY_CORNELL, "rays_per_launch": totals["rays"] / n_launch,
         "avg_launch_ms": totals["level_ms"] / n_launch, "traffic": None,
+        "note": "fused generate+intersect+shade kernel: issue-bound on FP32/ALU/LSU work, neither HBM nor tensor; "
+                "ncu pipe utilisation in profiles/",
     }
     roofline_hbm = {
         "bound": "hbm", "kernel": "sp_level_kernel (queue records only)",
         "achieved": totals["queue_bytes"] / level_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": totals["queue_bytes"] / level_s / 1e9 / hbm_peak, "peak_source": hbm_src,
-        "bytes_per_record": 96, "traffic": None,
+        "bytes_per_record": 96, "traffic": traffic,
+        "algorithmic_bytes_per_launch": totals["queue_bytes"] / n_launch,
     }
 
     cpu = None
