@@ -257,6 +257,11 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
             const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
             bin = (int)SP_BIN_OF_KIND(ci.kind);
             sp_child_needs(ci, meta_depth(r.meta), meta_dr(r.meta), n_ray, fan_class);
+            // a Diffuse hit past its bounce budget and a Refractive / ThinFilm hit past max_ray_depth are
+            // black (diffuse.py:123-124, refractive.py:38): nothing to shade, nothing to emit
+            if (n_ray == 0 && fan_class < 0 &&
+                (ci.kind == SP_MAT_DIFFUSE || ci.kind == SP_MAT_REFRACTIVE || ci.kind == SP_MAT_THINFILM))
+                bin = SP_N_BINS - 1;
         }
         // position inside the bin, and inside this iteration's appends to the output queues: one
         // shared-memory atomic per warp and distinct bin / queue

@@ -45,24 +45,28 @@ SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float 
     fast_sincos_2pi(u[1], sn, cs);
     const int l = sc.n_importance;
     bool use_cos = (l == 0) || (u[0] < w_cos);
+    // both generators build the direction the same way (random.py:60-71 / 128-148): polar angle about an
+    // axis w, azimuth phi in the frame (u, v) of that axis; only the axis and the polar law differ, so the
+    // frame and the direction are computed once for the whole warp
+    float3 w = N;
+    float z, s;
     if (use_cos) {                                           // cosine_pdf.generate
-        float3 au, av;
-        sp_onb(N, au, av);
-        float s = fast_sqrt(u[2]);
-        dir = au * (cs * s) + av * (sn * s) + N * fast_sqrt(1.f - u[2]);
+        s = fast_sqrt(u[2]);
+        z = fast_sqrt(1.f - u[2]);
     } else {                                                 // spherical_caps_pdf.generate
         int pick = min((int)(u[3] * (float)l), l - 1);
         float3 to_c = sc.importance[pick].center - origin;
         float d2 = dot(to_c, to_c);
-        float3 w = to_c * rsqrtf(d2);
-        float ratio = clamp01(sc.importance[pick].radius * rsqrtf(d2));
+        float inv = rsqrtf(d2);
+        w = to_c * inv;
+        float ratio = clamp01(sc.importance[pick].radius * inv);
         float cmax = fast_sqrt(1.f - ratio * ratio);
-        float3 au, av;
-        sp_onb(w, au, av);
-        float z = 1.f + u[2] * (cmax - 1.f);
-        float s = fast_sqrt(fmaxf(1.f - z * z, 0.f));
-        dir = au * (cs * s) + av * (sn * s) + w * z;
+        z = 1.f + u[2] * (cmax - 1.f);
+        s = fast_sqrt(fmaxf(1.f - z * z, 0.f));
     }
+    float3 au, av;
+    sp_onb(w, au, av);
+    dir = au * (cs * s) + av * (sn * s) + w * z;
     float ndl = clamp01(dot(dir, N));
     if (ndl <= 0.f) return 0.f;
     float pdf = ndl * (1.f / SP_PI);
