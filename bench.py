@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--chunk", type=int, default=0, help="primaries per wavefront chunk (0 = library default)")
+    ap.add_argument("--queue-cap", type=int, default=0, help="records per wavefront queue (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -189,6 +190,9 @@ def run_native(args):
     native = NativeScene(flat)
     if args.chunk:
         native.set_option("chunk_primaries", args.chunk)
+    if args.queue_cap:
+        native.set_option("ray_queue_capacity", args.queue_cap)
+        native.set_option("fan_queue_capacity", args.queue_cap)
     stream = torch.cuda.current_stream()
     native.set_stream(stream.cuda_stream)
     begin, end = parallel.sample_range(args.spp, rank, world)

@@ -672,12 +672,22 @@ int sp_scene_commit(sp_scene* s) {
 // =================================================================================================
 // wavefront driver
 // =================================================================================================
-static int ensure_queues(sp_scene* s) {
-    // Defaults: 1 Mi primaries per chunk; queues sized for 24 records per primary (a diffuse first
-    // bounce turns 1 primary into diffuse_rays secondary hits).  The driver below measures the
-    // real occupancy on a small first chunk and then sizes later chunks to fit.
-    const uint32_t want_ray = (uint32_t)std::min<int64_t>(s->opt_ray_cap > 0 ? s->opt_ray_cap : (int64_t)24 << 20, 0x7FFFFFF0ll);
-    const uint32_t want_fan = (uint32_t)std::min<int64_t>(s->opt_fan_cap > 0 ? s->opt_fan_cap : (int64_t)24 << 20, 0x7FFFFFF0ll);
+#define SP_DEFAULT_CHUNK ((int64_t)4 << 20)      /* primaries per chunk: measured 262 Ki -> 16.6, 1 Mi -> 18.4, 4 Mi -> 18.9 Grays/s */
+
+static int ensure_queues(sp_scene* s, uint64_t primaries) {
+    // Queues are sized for 24 records per primary of a chunk (a diffuse first bounce turns 1 primary into
+    // diffuse_rays secondary hits): 96 Mi records (27 GB with two fan classes) for a full 4 Mi-primary
+    // chunk, proportionally less for small jobs.  The driver below measures the real occupancy on a small
+    // first chunk and then sizes later chunks to fit.
+    const int64_t chunk = s->opt_chunk > 0 ? s->opt_chunk : SP_DEFAULT_CHUNK;
+    int64_t auto_cap = 24 * (int64_t)std::min<uint64_t>(std::max<uint64_t>(primaries, 1), (uint64_t)chunk);
+    auto_cap = std::max<int64_t>((auto_cap + 0xFFFFF) & ~(int64_t)0xFFFFF, (int64_t)1 << 20);
+    uint32_t want_ray = (uint32_t)std::min<int64_t>(s->opt_ray_cap > 0 ? s->opt_ray_cap : auto_cap, 0x7FFFFFF0ll);
+    uint32_t want_fan = (uint32_t)std::min<int64_t>(s->opt_fan_cap > 0 ? s->opt_fan_cap : auto_cap, 0x7FFFFFF0ll);
+    for (int c = 0; c < s->d.n_fan_classes; ++c)       // the kernel counts work items in 32 bits
+        want_fan = (uint32_t)std::min<uint64_t>(want_fan, 0x7FFFFFFFull / (uint64_t)std::max(s->d.fan_mult[c], 1));
+    if (s->opt_ray_cap == 0 && s->ray_cap >= want_ray) want_ray = s->ray_cap;       // never shrink on our own
+    if (s->opt_fan_cap == 0 && s->fan_cap >= want_fan) want_fan = s->fan_cap;
     if (want_ray != s->ray_cap) {
         for (int i = 0; i < 2; ++i) CUDA_TRY(s->ray_q[i].alloc(want_ray));
         s->ray_cap = want_ray;
@@ -686,9 +696,6 @@ static int ensure_queues(sp_scene* s) {
         for (int i = 0; i < 2; ++i) CUDA_TRY(s->fan_q[i].alloc((size_t)want_fan * s->d.n_fan_classes));
         s->fan_cap = want_fan;
     }
-    for (int c = 0; c < s->d.n_fan_classes; ++c)
-        if ((uint64_t)s->fan_cap * (uint64_t)s->d.fan_mult[c] > 0x7FFFFFFFull)
-            return fail("fan_queue_capacity x diffuse_rays exceeds 2^31 work items; lower fan_queue_capacity");
     return 0;
 }
 
@@ -766,7 +773,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
     return 0;
 }
 
-static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what) {
+static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what, uint64_t primaries) {
     if (!s) return fail("%s: null scene", what);
     if (!s->committed) return fail("%s: scene not committed (sp_scene_commit)", what);
     CUDA_TRY(cudaSetDevice(g_device));
@@ -774,7 +781,7 @@ static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what
     s->d.seed_hi = (uint32_t)(seed >> 32);
     if (st) memset(st, 0, sizeof *st);
     CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
-    return ensure_queues(s);
+    return ensure_queues(s, primaries);
 }
 
 static int end_call(sp_scene* s, sp_stats* st, cudaEvent_t t0, cudaEvent_t t1) {
@@ -798,7 +805,7 @@ static int end_call(sp_scene* s, sp_stats* st, cudaEvent_t t0, cudaEvent_t t1) {
 
 // primaries per chunk given the occupancy seen so far
 static uint32_t pick_chunk(sp_scene* s, bool first) {
-    int64_t p = s->opt_chunk > 0 ? s->opt_chunk : (int64_t)1 << 20;
+    int64_t p = s->opt_chunk > 0 ? s->opt_chunk : SP_DEFAULT_CHUNK;
     if (first && s->use_ray == 0.0 && s->use_fan == 0.0) p = std::min<int64_t>(p, 1 << 16);   // probe
     const double slack = 1.3;
     if (s->use_ray > 0.0) p = std::min<int64_t>(p, (int64_t)(s->ray_cap / (s->use_ray * slack)));
@@ -807,7 +814,9 @@ static uint32_t pick_chunk(sp_scene* s, bool first) {
 }
 
 int sp_render_samples(sp_scene* s, int sample_begin, int sample_end, uint64_t seed, int clear, sp_stats* st) {
-    int rc = begin_call(s, seed, st, "sp_render_samples");
+    if (s && s->committed && !s->has_camera) return fail("sp_render_samples: the scene has no camera");
+    int rc = begin_call(s, seed, st, "sp_render_samples",
+                        s && s->committed ? (uint64_t)std::max(sample_end - sample_begin, 0) * s->accum.n : 0);
     if (rc) return rc;
     if (!s->has_camera) return fail("sp_render_samples: the scene has no camera");
     if (sample_begin < 0 || sample_end < sample_begin) return fail("sp_render_samples: invalid sample range");
@@ -880,7 +889,7 @@ int sp_render(sp_scene* s, int spp, uint64_t seed, float* out_linear, uint8_t* o
 
 int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64_t seed, float* out_rgb,
              int32_t* out_hit_id, float* out_t, sp_stats* st) {
-    int rc = begin_call(s, seed, st, "sp_trace");
+    int rc = begin_call(s, seed, st, "sp_trace", (uint64_t)std::max(n, 0));
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!origins || !dirs))) return fail("sp_trace: invalid arguments");
     if (n == 0) return 0;
@@ -928,7 +937,7 @@ int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64
 }
 
 static int primary_pass(sp_scene* s, int run, int sample, uint64_t seed, float* out_o, float* out_d, float* out_t, const char* what) {
-    int rc = begin_call(s, seed, nullptr, what);
+    int rc = begin_call(s, seed, nullptr, what, s && s->committed ? s->accum.n : 0);
     if (rc) return rc;
     if (!s->has_camera) return fail("%s: the scene has no camera", what);
     const size_t n = s->accum.n;
