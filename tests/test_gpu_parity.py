@@ -301,3 +301,39 @@ def test_cornell_full_resolution_energy_and_determinism():
     assert 50.0 < sa["rays_total"] / sa["rays_per_depth"][0] < 60.0      # reference: 57-59 rays per primary, we skip zero-weight ones
     np.testing.assert_allclose(a.mean(), b.mean(), rtol=1e-5)
     assert np.mean(np.abs(a - b) > 1e-3 * (1 + np.abs(a))) < 1e-4     # float atomics reorder sums, nothing else
+
+
+def test_cornell_matches_reference_converged_image():
+    """Monte-Carlo acceptance gate (BASELINE.json north_star / SURVEY §8d): the GPU frame against a converged
+    image rendered by the REAL reference (tests/golden/make_converged.py: 64x64, two independent halves of
+    128 spp, numpy RNG).  Bounds, with s = the reference's own split-half RMSE (noise of a 128-spp pair):
+      * equal sample count (256 spp):  RMSE(gpu, reference) <= 1.0 s      (expected 0.71 s: two 256-spp means)
+      * converged GPU frame (4096 spp): RMSE <= 0.75 s                      (expected 0.5 s: the reference's noise)
+      * tonemapped PSNR of the converged GPU frame vs the reference no worse than reference-half vs
+        reference-half, mean radiance within 1.5 %."""
+    import scenes
+    import sightpy
+    from sightpy.backend import NativeScene
+    g = load_golden("cornell_converged_64x64")
+    a, b = g["half_a"].astype(np.float64), g["half_b"].astype(np.float64)
+    ref = 0.5 * (a + b)
+    s = float(np.sqrt(np.mean((a - b) ** 2)))
+    nat = NativeScene(flatten_scene(scenes.cornell(sightpy, width=64, height=64)))
+    _, equal, _ = nat.render(256, seed=5)
+    _, conv, _ = nat.render(4096, seed=6)
+    nat.close()
+    equal, conv = equal.reshape(3, -1).astype(np.float64), conv.reshape(3, -1).astype(np.float64)
+    rmse_equal = float(np.sqrt(np.mean((equal - ref) ** 2)))
+    rmse_conv = float(np.sqrt(np.mean((conv - ref) ** 2)))
+
+    def psnr(x, y):
+        tx, ty = tonemap_u8(x, 64, 64).astype(np.float64), tonemap_u8(y, 64, 64).astype(np.float64)
+        return float(10 * np.log10(255.0 ** 2 / np.mean((tx - ty) ** 2)))
+
+    print(f"split-half RMSE {s:.4f}; gpu256 {rmse_equal:.4f} ({rmse_equal / s:.2f} s); gpu4096 {rmse_conv:.4f} "
+          f"({rmse_conv / s:.2f} s); PSNR gpu4096-vs-ref {psnr(conv, ref):.2f} dB, ref half-vs-half {psnr(a, b):.2f} dB; "
+          f"mean gpu {conv.mean():.5f} ref {ref.mean():.5f}")
+    assert rmse_equal <= 1.0 * s
+    assert rmse_conv <= 0.75 * s
+    assert psnr(conv, ref) >= psnr(a, b)
+    assert abs(conv.mean() - ref.mean()) <= 0.015 * ref.mean()
