@@ -337,3 +337,75 @@ def test_cornell_matches_reference_converged_image():
     assert rmse_conv <= 0.75 * s
     assert psnr(conv, ref) >= psnr(a, b)
     assert abs(conv.mean() - ref.mean()) <= 0.015 * ref.mean()
+
+
+# ---- less-travelled paths: mixed fan classes, no importance list, point light, empty scenes -----------------
+def _mixed_scene(importance):
+    import sightpy as sp
+    v, rgb = sp.vec3, sp.rgb
+    sc = sp.Scene(ambient_color=rgb(0.02, 0.02, 0.03))
+    sc.add_Camera(look_from=v(0.0, 1.2, 4.0), look_at=v(0.0, 0.6, 0.0), screen_width=40, screen_height=30, field_of_view=55)
+    sc.add_PointLight(pos=v(2.0, 3.0, 2.0), color=rgb(0.9, 0.8, 0.7))
+    sc.add_DirectionalLight(Ldir=v(-0.3, 0.9, 0.4), color=rgb(0.2, 0.2, 0.3))
+    lamp = sp.Sphere(material=sp.Emissive(color=rgb(6.0, 5.0, 4.0)), center=v(-1.5, 2.2, 0.5), radius=0.4)
+    lamp2 = sp.Cuboid(material=sp.Emissive(color=rgb(1.0, 2.0, 6.0)), center=v(1.8, 1.9, -0.5), width=0.5, height=0.3, length=0.5)
+    tile = sp.Plane(material=sp.Emissive(color=sp.image("wood.jpg", repeat=2.0)), center=v(0.0, 2.8, -1.0), width=1.0, height=1.0,
+                    u_axis=v(1.0, 0, 0), v_axis=v(0, 0, 1.0))
+    for prim in (lamp, lamp2, tile):
+        sc.add(prim, importance_sampled=importance)
+    sc.add(sp.Sphere(material=sp.Diffuse(diff_color=rgb(0.7, 0.3, 0.2), diffuse_rays=5), center=v(-0.8, 0.5, 0.0), radius=0.5))
+    sc.add(sp.Sphere(material=sp.Diffuse(diff_color=rgb(0.2, 0.6, 0.3), diffuse_rays=1, ambient_weight=0.3), center=v(0.5, 0.4, 0.6), radius=0.4))
+    box = sp.Cuboid(material=sp.Diffuse(diff_color=sp.image("checkered_floor.png", repeat=3.0), diffuse_rays=20),
+                    center=v(1.3, 0.35, -0.6), width=0.7, height=0.7, length=0.7)
+    sc.add(box)
+    sc.add(sp.Sphere(material=sp.Glossy(diff_color=rgb(0.3, 0.3, 0.8), n=v(1.4 + 0.5j, 1.4 + 0.5j, 1.6 + 0.7j), roughness=0.25,
+                                        spec_coeff=0.5, diff_coeff=0.6), center=v(0.0, 0.3, -1.2), radius=0.3, max_ray_depth=2))
+    sc.add(sp.Plane(material=sp.Diffuse(diff_color=rgb(0.6, 0.6, 0.6), diffuse_rays=5), center=v(0, 0.0, 0), width=8.0, height=8.0,
+                    u_axis=v(1.0, 0, 0), v_axis=v(0, 0, -1.0)))
+    return sc
+
+
+@pytest.mark.parametrize("importance", [True, False])
+def test_mixed_fan_classes_point_light_textured_diffuse_match_oracle(importance):
+    """Three Diffuse fan classes (diffuse_rays 1, 5, 20), a textured Diffuse box, textured / solid Emissive
+    shapes of every collider type on the importance list (or no list at all: pure cosine sampling), a
+    point light next to a directional one, a Glossy sphere: per-ray agreement with the oracle."""
+    from sightpy.backend import NativeScene
+    flat = flatten_scene(_mixed_scene(importance))
+    assert len(flat.importance) == (3 if importance else 0)
+    nat = NativeScene(flat)
+    o, d = nat.camera_rays(sample=1, seed=8)
+    out = nat.trace(o, d, seed=8)
+    nat.close()
+    want = Oracle(flat, rng="philox", seed=8).trace(o, d)
+    assert np.mean(out["hit_id"] != want["hit_id"]) < 0.002
+    same = out["hit_id"] == want["hit_id"]
+    err = np.abs(out["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[same]
+    scale = 1.0 + np.abs(want["rgb"]).max(axis=1)[same]
+    assert float(np.mean(err > RGB_TOL * scale)) < 0.03, float(np.mean(err > RGB_TOL * scale))
+    assert abs(out["rgb"].mean() - want["rgb"].mean()) < 0.02 * want["rgb"].mean()
+
+
+def test_empty_and_background_only_scenes():
+    import sightpy as sp
+    sc = sp.Scene()
+    sc.add_Camera(look_from=sp.vec3(0, 0, 1), look_at=sp.vec3(0, 0, 0), screen_width=16, screen_height=12)
+    img = np.asarray(sc.render(2))
+    assert img.shape == (12, 16, 3) and not img.any()                 # nothing to hit: black frame
+    sc.add_Background("stormydays.png")
+    img = np.asarray(sc.render(2))
+    assert img.any() and sc.last_stats["rays_total"] == 2 * 16 * 12
+
+
+def test_animation_frames_are_written(tmp_path, monkeypatch):
+    import sightpy as sp
+    sc = build_scene("example3", (48, 36))
+    monkeypatch.chdir(tmp_path)
+
+    def update(scene, t):
+        scene.camera.look_from = sp.vec3(0.3 * t, 0.25, 1.0)
+
+    for rel in ("sightpy/textures", "sightpy/backgrounds"):       # asset lookups fall back to the packaged copies
+        assert not (tmp_path / rel).exists()
+    sp.create_animation(sc, samples_per_pixel=1, fps=2, start_time=0.0, final_time=1.0, update_scene=update, name="t")
+    assert sorted(p.name for p in (tmp_path / "frames").iterdir()) == ["t_0.png", "t_1.png"]
