@@ -561,10 +561,19 @@ int sp_scene_commit(sp_scene* s) {
     s->n_levels = std::min(max_depth + max_dr + 1, SP_MAX_LEVELS - 1);
 
     std::vector<DCollider> dc((size_t)n_col);
-    std::vector<double> dcd((size_t)n_col * 40);
+    const int PL = 44;                                   // SP_DEV_PAYLOAD: 40 ABI slots + derived reciprocals
+    std::vector<double> dcd((size_t)n_col * PL, 0.0);
     for (int i = 0; i < n_col; ++i) {
         dc[i].type = s->cols[i].type; dc[i].prim = s->cols[i].primitive;
-        for (int k = 0; k < 40; ++k) { dc[i].p[k] = (float)s->cols[i].p[k]; dcd[(size_t)i * 40 + k] = s->cols[i].p[k]; }
+        double* pd = &dcd[(size_t)i * PL];
+        for (int k = 0; k < 40; ++k) pd[k] = s->cols[i].p[k];
+        switch (s->cols[i].type) {
+        case SP_COLLIDER_SPHERE: pd[4] = 1.0 / pd[3]; break;                                   // 1 / radius
+        case SP_COLLIDER_PLANE: pd[25] = 1.0 / pd[12]; pd[26] = 1.0 / pd[13]; break;           // 1 / w, 1 / h
+        case SP_COLLIDER_CUBOID: for (int k = 0; k < 3; ++k) pd[40 + k] = 1.0 / pd[18 + k]; break;   // 1 / (width, height, length)
+        default: break;
+        }
+        for (int k = 0; k < PL; ++k) dc[i].p[k] = (float)pd[k];
     }
     CUDA_TRY(s->d_cols.upload(dc));
     std::vector<DColInfo> dinfo((size_t)n_col);

@@ -194,7 +194,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
     const uint32_t depth = meta_depth(r.meta), dr = meta_dr(r.meta), medium = meta_medium(r.meta);
 
     HitGeom g = ((FEAT & SP_F_TEX) && m.precise)
-                    ? sp_eval_hit<double, FEAT>(sc, m, prim, sc.colliders_d + (size_t)h.id * 40, ctype, r, h)
+                    ? sp_eval_hit<double, FEAT>(sc, m, prim, sc.colliders_d + (size_t)h.id * SP_DEV_PAYLOAD, ctype, r, h)
                     : sp_eval_hit<float, FEAT>(sc, m, prim, col.p, ctype, r, h);
     const float orient = (float)h.orient;
 

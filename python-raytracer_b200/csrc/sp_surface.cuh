@@ -49,6 +49,13 @@ template <typename T> SP_DEV float3 to_f3(tv3<T> a) { return v3((float)a.x, (flo
 #define SP_CB_INVB 30
 #define SP_TR_N 9
 #define SP_TR_CEN 12
+// derived reciprocals appended to the device copies of the payload by sp_scene_commit (divisions are
+// the dearest instructions of the double-precision texel path)
+#define SP_DEV_PAYLOAD 44
+#define SP_SPH_INVR 4
+#define SP_PL_INVW 25
+#define SP_PL_INVH 26
+#define SP_CB_INVSIZE 40
 
 // Distance along the ray to collider `type`/`p`, choosing the root the float32 pass selected
 // (orient: +1 near/outer, -1 far/inner).  Same formulas as the float32 tests, in T.
@@ -83,12 +90,12 @@ SP_DEV T sp_refine_t(int type, const T* p, tv3<T> O, tv3<T> D, int orient, T t_f
 // Outward geometric normal of the collider at P (un-oriented).
 template <typename T>
 SP_DEV tv3<T> sp_collider_normal(int type, const T* p, tv3<T> P) {
-    if (type == 0) return (P - ld3(p + SP_SPH_C)) * ((T)1 / p[SP_SPH_R]);
+    if (type == 0) return (P - ld3(p + SP_SPH_C)) * p[SP_SPH_INVR];
     if (type == 1) return ld3(p + SP_PL_N);
     if (type == 3) return ld3(p + SP_TR_N);
     tv3<T> Pl = tmat(p + SP_CB_B, P - ld3(p + SP_CB_C));
-    T ax = fabs(Pl.x) * ((T)1 / p[SP_CB_SIZE]), ay = fabs(Pl.y) * ((T)1 / p[SP_CB_SIZE + 1]);
-    T az = fabs(Pl.z) * ((T)1 / p[SP_CB_SIZE + 2]);
+    T ax = fabs(Pl.x) * p[SP_CB_INVSIZE], ay = fabs(Pl.y) * p[SP_CB_INVSIZE + 1];
+    T az = fabs(Pl.z) * p[SP_CB_INVSIZE + 2];
     T am = fmax(fmax(ax, ay), az);
     auto sgn = [](T v) { return v > (T)0 ? (T)1 : (v < (T)0 ? (T)-1 : (T)0); };
     tv3<T> face = mk<T>(am == ax ? sgn(Pl.x) : (T)0, am == ay ? sgn(Pl.y) : (T)0, am == az ? sgn(Pl.z) : (T)0);
@@ -100,18 +107,18 @@ template <typename T>
 SP_DEV void sp_collider_uv(int type, const T* p, tv3<T> P, tv3<T> Nc, bool cross_layout, T& u, T& v) {
     const T pi = (T)3.14159265358979323846;
     if (type == 0) {
-        tv3<T> m = mk<T>((P.x - p[0]) / p[SP_SPH_R], (P.y - p[1]) / p[SP_SPH_R], (P.z - p[2]) / p[SP_SPH_R]);
-        u = (atan2(m.z, m.x) + pi) / ((T)2 * pi);
-        v = (asin(m.y) + pi / (T)2) / pi;
+        tv3<T> m = (P - ld3(p + SP_SPH_C)) * p[SP_SPH_INVR];
+        u = (atan2(m.z, m.x) + pi) * (T)0.15915494309189533577;          // 1 / (2 pi)
+        v = (asin(m.y) + pi / (T)2) * (T)0.31830988618379067154;           // 1 / pi
     } else if (type == 1) {
         tv3<T> mc = P - ld3(p + SP_PL_C);
-        u = (tdot(ld3(p + SP_PL_U), mc) / p[SP_PL_W] + (T)1) / (T)2 + p[SP_PL_SHIFT];
-        v = (tdot(ld3(p + SP_PL_V), mc) / p[SP_PL_H] + (T)1) / (T)2 + p[SP_PL_SHIFT + 1];
+        u = (tdot(ld3(p + SP_PL_U), mc) * p[SP_PL_INVW] + (T)1) * (T)0.5 + p[SP_PL_SHIFT];
+        v = (tdot(ld3(p + SP_PL_V), mc) * p[SP_PL_INVH] + (T)1) * (T)0.5 + p[SP_PL_SHIFT + 1];
     } else if (type == 2) {
         tv3<T> mc = P - ld3(p + SP_CB_C);
-        T w = p[SP_CB_SIZE];
+        const T k = p[SP_CB_INVSIZE] * (T)(2 * 0.985);       // every face is scaled by the box width (cuboid.py:165-186)
         T dw = tdot(ld3(p + SP_CB_AW), mc), dh = tdot(ld3(p + SP_CB_AH), mc), dl = tdot(ld3(p + SP_CB_AL), mc);
-        auto g = [w](T d, T off) { return (d / w * (T)2 * (T)0.985 + (T)1) / (T)2 + off; };
+        auto g = [k](T d, T off) { return (d * k + (T)1) * (T)0.5 + off; };
         auto is = [Nc](T x, T y, T z) { return Nc.x == x && Nc.y == y && Nc.z == z; };
         u = (T)0; v = (T)0;                              // rotated boxes match no face (cuboid.py:157-162)
         if (is(0, -1, 0))      { u = g(dw, 1);  v = g(-dl, 0); }   // BOTTOM
@@ -123,16 +130,24 @@ SP_DEV void sp_collider_uv(int type, const T* p, tv3<T> P, tv3<T> Nc, bool cross
     } else {
         u = (T)0; v = (T)0;                              // triangles have no uv mapping upstream
     }
-    if (cross_layout) { u = u / (T)4; v = v / (T)3; }
+    if (cross_layout) { u = u * (T)0.25; v = v * (T)(1.0 / 3.0); }
 }
 
 // img[-(int(v*H*repeat) % H), int(u*W*repeat) % W] with Python's floor-mod and negative indexing.
 template <typename T>
 SP_DEV int sp_texel_offset(T u, T v, int H, int W, T repeat, int Hreal, int Wreal) {
-    long long iv = (long long)(v * (T)H * repeat);      // astype(int): truncation towards zero
-    long long iu = (long long)(u * (T)W * repeat);
-    long long r = iv % H; if (r < 0) r += H;            // Python % with positive modulus
-    long long c = iu % W; if (c < 0) c += W;
+    const T fv = v * (T)H * repeat, fu = u * (T)W * repeat;
+    long long r, c;
+    if (fabs(fv) < (T)2.0e9 && fabs(fu) < (T)2.0e9) {   // the usual case: 32-bit remainders (64-bit ones cost ~100 instructions)
+        const int iv = (int)fv, iu = (int)fu;           // astype(int): truncation towards zero
+        int r32 = iv % H; if (r32 < 0) r32 += H;        // Python % with positive modulus
+        int c32 = iu % W; if (c32 < 0) c32 += W;
+        r = r32; c = c32;
+    } else {
+        const long long iv = (long long)fv, iu = (long long)fu;
+        r = iv % H; if (r < 0) r += H;
+        c = iu % W; if (c < 0) c += W;
+    }
     long long row = (r == 0) ? 0 : (long long)Hreal - r;   // negative index -r of the indexed array
     row = row < 0 ? 0 : (row >= Hreal ? Hreal - 1 : row);  // (the reference would raise IndexError)
     c = c >= Wreal ? Wreal - 1 : c;

@@ -46,7 +46,7 @@ struct GeomStream {
 // ---- full records used at shading time (one per collider / primitive / material) -------------
 struct DCollider {
     int type, prim;
-    float p[40];               // same slots as sp_collider.p (include/sightpy_b200.h)
+    float p[44];               // slots 0-39 as sp_collider.p (include/sightpy_b200.h) + derived reciprocals (sp_surface.cuh)
 };
 
 struct DPrimitive {
@@ -97,7 +97,7 @@ struct DScene {
     GeomStream all, shadow;
     const DCollider* colliders;
     const DColInfo* col_info;
-    const double* colliders_d;     // [n][40] double payloads for the precise hit path
+    const double* colliders_d;     // [n][44] double payloads for the precise hit path
     const DPrimitive* prims;
     const DMaterial* mats;
     const DTexture* textures;
