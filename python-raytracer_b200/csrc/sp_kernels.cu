@@ -110,6 +110,10 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     ctx.shadow_rays = 0;
     unsigned long long traced = 0;
 
+    __shared__ float s_lin_lut[(FEAT & SP_F_TEX) ? 256 : 1];
+    if (FEAT & SP_F_TEX)
+        for (uint32_t i = tid; i < 256u; i += SP_BLOCK) s_lin_lut[i] = c_decode[SP_DECODE_LINEAR][i];
+    ctx.lin_lut = s_lin_lut;
     if (tid < sizeof(sh.cnt) / sizeof(uint32_t)) reinterpret_cast<uint32_t*>(sh.cnt)[tid] = 0u;
     __syncthreads();
     uint32_t parity = 0;

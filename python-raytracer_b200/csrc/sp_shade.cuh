@@ -55,10 +55,14 @@ SP_DEV void sp_child_needs(const DColInfo& ci, uint32_t depth, uint32_t dr, int&
     }
 }
 
-SP_DEV float3 sp_fetch_texel(const DTexture& t, int offset) {
-    uint32_t w = __ldg(t.texels + offset);
-    const float* lut = c_decode[t.decode];
-    return v3(lut[w & 255u], lut[(w >> 8) & 255u], lut[(w >> 16) & 255u]);
+// Texel bytes -> values.  SP_DECODE_PLAIN is byte / 256 (exact in float); SP_DECODE_LINEAR goes through the
+// 256-entry sRGB table, read from a shared-memory copy: the lanes of a warp index it with unrelated bytes,
+// which constant memory would serialise.
+SP_DEV float3 sp_fetch_texel(const DTexture& t, int offset, const float* __restrict__ lin_lut) {
+    const uint32_t w = __ldg(t.texels + offset);
+    const uint32_t r = w & 255u, g = (w >> 8) & 255u, b = (w >> 16) & 255u;
+    if (t.decode == SP_DECODE_PLAIN) return v3((float)r, (float)g, (float)b) * (1.f / 256.f);
+    return v3(lin_lut[r], lin_lut[g], lin_lut[b]);
 }
 
 // ---- hit geometry in float or double ----------------------------------------------------------------
@@ -104,7 +108,7 @@ SP_DEV HitGeom sp_eval_hit(const DScene& sc, const DMaterial& m, const DPrimitiv
             if (m.noise_factor != 0.f) {
                 const DTexture& nz = sc.textures[m.aux_tex1];
                 int off = sp_texel_offset<T>(u, v, nz.H, nz.W, (T)0.5, nz.H, nz.W);
-                T nval = (T)c_decode[0][__ldg(nz.texels + off) & 255u];
+                T nval = (T)(__ldg(nz.texels + off) & 255u) * (T)(1.0 / 256.0);
                 thick = thick + (T)m.noise_factor * (nval - (T)0.5);
             }
             const DTexture& lut = sc.textures[m.aux_tex0];
@@ -168,6 +172,7 @@ struct ShadeCtx {
     const DScene* sc;
     const LevelOut* out;       // kernel parameter (constant bank), not copied into registers
     const int2* shadow_slot;    // collider id -> (chunk, type << 28 | local index) in the shadow-caster stream
+    const float* lin_lut;       // shared-memory copy of the sRGB -> linear table
     unsigned long long shadow_rays;
     // slots reserved for the hit being shaded
     uint32_t ray_slot, ray_used, fan_slot;
@@ -200,20 +205,20 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
 
     // ---- terminal materials ---------------------------------------------------------------------
     if (m.kind == SP_MAT_EMISSIVE) {                                     // emissive.py:21-23
-        float3 c = ((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color;
+        float3 c = ((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color, cx_.lin_lut) : m.color;
         return r.thr * c;
     }
     if ((FEAT & SP_F_SKY) && m.kind == SP_MAT_SKYBOX) {                                   // skybox.py:51-94
-        float3 c = sp_fetch_texel(sc.textures[m.color_tex], g.off_color);
+        float3 c = sp_fetch_texel(sc.textures[m.color_tex], g.off_color, cx_.lin_lut);
         if (depth != 0u && m.light_intensity != 0.f)
-            c += sp_fetch_texel(sc.textures[m.aux_tex0], g.off_aux0) * m.light_intensity;
+            c += sp_fetch_texel(sc.textures[m.aux_tex0], g.off_aux0, cx_.lin_lut) * m.light_intensity;
         return r.thr * c;
     }
 
     // ---- shading normal (material.py:18-36) ----------------------------------------------------------
     float3 N;
     if ((FEAT & SP_F_TEX) && m.normalmap_tex >= 0) {
-        float3 tx = sp_fetch_texel(sc.textures[m.normalmap_tex], g.off_normal);
+        float3 tx = sp_fetch_texel(sc.textures[m.normalmap_tex], g.off_normal, cx_.lin_lut);
         float3 nm = (tx - v3(0.5f)) * 2.f;
         const float* ib = col.p + (ctype == SP_COLLIDER_PLANE ? SP_PL_INVB : SP_CB_INVB);
         N = normalize0(mat3_mul(ib, nm)) * orient;
@@ -227,7 +232,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
     int zo;
 
     if ((FEAT & SP_F_DIFFUSE) && m.kind == SP_MAT_DIFFUSE) {                                // diffuse.py:25-124
-        float3 diff = ((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color;
+        float3 diff = ((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color, cx_.lin_lut) : m.color;
         int cls = -1; float inv_m = 1.f;
         if (dr < 1u) { cls = m.fan_class; inv_m = 1.f / (float)m.diffuse_rays; }
         else if ((int)dr < m.max_dr) { cls = 0; }
@@ -249,7 +254,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
     }
 
     if ((FEAT & SP_F_GLOSSY) && m.kind == SP_MAT_GLOSSY) {                                // glossy.py:25-110
-        float3 diff = (((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color) : m.color)
+        float3 diff = (((FEAT & SP_F_TEX) && m.color_tex >= 0) ? sp_fetch_texel(sc.textures[m.color_tex], g.off_color, cx_.lin_lut) : m.color)
                       * m.diff_coeff;
         float3 color = sc.ambient * diff;
         const DMedium med = sc.media[medium];
@@ -306,7 +311,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
     const uint32_t mode_refl = sp_self_mode(ctype, side_plus, dot(R, g.Nc), zo);
 
     if ((FEAT & SP_F_THIN) && m.kind == SP_MAT_THINFILM) {                               // thin_film_interference.py:24-115
-        float3 F = sp_fetch_texel(sc.textures[m.aux_tex0], g.off_aux0);
+        float3 F = sp_fetch_texel(sc.textures[m.aux_tex0], g.off_aux0, cx_.lin_lut);
         add = r.thr * sc.ambient * F;
         sp_emit_ray(cx_, r, nudged, R, r.thr * F, 0u, medium, dr, h.id, mode_refl);
         uint32_t mode_t = sp_self_mode(ctype, -side_plus, dot(r.d, g.Nc), zo);
