@@ -219,12 +219,25 @@ static void pack_collider(const sp_collider& c, int st, float* out) {
         out[16] = (float)hi[1]; out[17] = (float)hi[2]; out[18] = 0.f; out[19] = 0.f;
         break;
     }
-    case SP_ST_TRI:   // N, centroid, n31, p1, n12, p2, n23, p3
-        put3(0, p[9], p[10], p[11]);  put3(3, p[12], p[13], p[14]);
-        put3(6, p[15], p[16], p[17]); put3(9, p[0], p[1], p[2]);
-        put3(12, p[18], p[19], p[20]); put3(15, p[3], p[4], p[5]);
-        put3(18, p[21], p[22], p[23]); put3(21, p[6], p[7], p[8]);
+    case SP_ST_TRI: {   // rows of M = [e1 e2 N]^-1 and t = -M p1 (sp_types.cuh)
+        const double e1[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]}, e2[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+        const double* N = p + 9;
+        auto cross3 = [](const double* a, const double* b, double* o) {
+            o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+        };
+        double c0[3], c1[3], c2[3];                     // rows of the inverse: (e2 x N, N x e1, e1 x e2) / det
+        cross3(e2, N, c0); cross3(N, e1, c1); cross3(e1, e2, c2);
+        const double det = e1[0] * c0[0] + e1[1] * c0[1] + e1[2] * c0[2];
+        const double inv = det != 0.0 ? 1.0 / det : 0.0;  // degenerate triangles can never be hit (u, v = 0 + t*0 ... t0 = 0)
+        const double* rows[3] = {c0, c1, c2};
+        for (int r = 0; r < 3; ++r) {
+            double row[3] = {rows[r][0] * inv, rows[r][1] * inv, rows[r][2] * inv};
+            if (r == 2) { row[0] = N[0]; row[1] = N[1]; row[2] = N[2]; }      // exactly the reference normal
+            put3(4 * r, row[0], row[1], row[2]);
+            out[4 * r + 3] = (float)(-(row[0] * p[0] + row[1] * p[1] + row[2] * p[2]));
+        }
         break;
+    }
     default: {        // axis-aligned rectangle: (C, sign of N) (half extents along the in-plane axes, ascending)
         const int an = st - SP_ST_AAX, au = unit_axis(p + 3);
         const int b = an == 0 ? 1 : 0;                   // lower in-plane axis

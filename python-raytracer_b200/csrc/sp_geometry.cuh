@@ -113,23 +113,21 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
         }
     }
     // ---- triangles -----------------------------------------------------------------------------
+    // triangle.py:37-66 through the affine map to the unit triangle: the three edge tests
+    // n31.(M-p1) >= 0, n12.(M-p2) >= 0, n23.(M-p3) >= 0 are u >= 0, v >= 0, 1-u-v >= 0 of the hit point's
+    // barycentric coordinates, and the third row of the map is the plane normal (N.D, N.(O-p1)).
     {
         const float4* tr = ch + h->off_tri;
+#pragma unroll 2
         for (int i = 0; i < n_tri; ++i) {
-            float4 f0 = tr[6 * i], f1 = tr[6 * i + 1], f2 = tr[6 * i + 2];
-            float4 f3 = tr[6 * i + 3], f4 = tr[6 * i + 4], f5 = tr[6 * i + 5];
-            float3 N = v3(f0.x, f0.y, f0.z), cen = v3(f0.w, f1.x, f1.y);
-            float3 n31 = v3(f1.z, f1.w, f2.x), p1 = v3(f2.y, f2.z, f2.w);
-            float3 n12 = v3(f3.x, f3.y, f3.z), p2 = v3(f3.w, f4.x, f4.y);
-            float3 n23 = v3(f4.z, f4.w, f5.x), p3 = v3(f5.y, f5.z, f5.w);
-            float nd = dot(N, D);
+            const float4 m0 = tr[3 * i], m1 = tr[3 * i + 1], m2 = tr[3 * i + 2];
+            float nd = dot(xyz(m2), D);
             nd = (nd == 0.f) ? 1e-4f : nd;
-            float k = -dot(N, O - cen);
-            float t = __fdividef(k, nd);
-            float e1 = fmaf(t, dot(n31, D), dot(n31, O - p1));
-            float e2 = fmaf(t, dot(n12, D), dot(n12, O - p2));
-            float e3 = fmaf(t, dot(n23, D), dot(n23, O - p3));
-            bool ok = (e1 >= 0.f) && (e2 >= 0.f) && (e3 >= 0.f) && (k * nd > 0.f) && (i != self.tri);
+            const float w0 = dot(xyz(m2), O) + m2.w;                 // N.(O - p1) = -k
+            const float t = -w0 * fast_rcp(nd);
+            const float u = fmaf(t, dot(xyz(m0), D), dot(xyz(m0), O) + m0.w);
+            const float v = fmaf(t, dot(xyz(m1), D), dot(xyz(m1), O) + m1.w);
+            const bool ok = (u >= 0.f) && (v >= 0.f) && (u + v <= 1.f) && (t > 0.f) && (i != self.tri);
             if (ok && t < best.t) {
                 best.t = t; best.idx = n_sphere + n_plane + n_cuboid + i; best.orient = nd < 0.f ? 1 : -1;
             }

@@ -12,7 +12,8 @@
 // plane    : (N.xyz, w) (C.xyz, h) (U.xyz, -) (V.xyz, -)
 // cuboid   : (B0.xyz, lo.x) (B1.xyz, lo.y) (B2.xyz, lo.z) (C.xyz, hi.x) (hi.y, hi.z, -, -)
 //            B = basis rows, lo/hi = box corners relative to B*C (so tests run on O - C)
-// triangle : 24 floats N, centroid, n31, p1, n12, p2, n23, p3
+// triangle : rows of the affine map to the unit triangle (Woop): (M0.xyz, t0) (M1.xyz, t1) (N.xyz, t2) with
+//            M = [p2-p1, p3-p1, N]^-1, t = -M p1, so that M O + t = (u, v, signed distance to the plane)
 // aa rect  : a bounded plane whose normal and both edge axes are coordinate axes (every wall of the
 //            Cornell box, the examples' floors): (C.xyz, sign of the normal) (half extents along the
 //            two in-plane axes in x<y<z order, -, -); one section per normal axis, ~10 instructions
@@ -21,7 +22,7 @@
 #define SP_V4_SPHERE 1
 #define SP_V4_PLANE 4
 #define SP_V4_CUBOID 5
-#define SP_V4_TRIANGLE 6
+#define SP_V4_TRIANGLE 3
 #define SP_V4_AARECT 2
 // stream type codes (order of the sections and of the id array inside a chunk)
 enum { SP_ST_SPHERE = 0, SP_ST_PLANE = 1, SP_ST_CUBOID = 2, SP_ST_TRI = 3, SP_ST_AAX = 4, SP_ST_AAY = 5, SP_ST_AAZ = 6 };
