@@ -123,7 +123,7 @@ struct sp_scene {
     std::vector<cudaEvent_t> events;
     DevBuf<float4> geom_all, geom_shadow, accum;
     DevBuf<int> off_all, off_shadow;
-    DevBuf<int2> slot_all, slot_shadow;
+    DevBuf<int2> slot_shadow;
     DevBuf<DCollider> d_cols;
     DevBuf<DColInfo> d_colinfo;
     DevBuf<double> d_cols_d;
@@ -146,7 +146,7 @@ struct sp_scene {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
         geom_all.release(); geom_shadow.release(); accum.release(); off_all.release(); off_shadow.release();
-        slot_all.release(); slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_cols_d.release(); d_prims.release();
+        slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
         for (auto e : events) g_event_pool.push_back(e);
@@ -597,9 +597,8 @@ int sp_scene_commit(sp_scene* s) {
         ci.type = (uint8_t)s->cols[i].type; ci.kind = (uint8_t)m.kind; ci.mc = pr.mc ? 1 : 0;
         ci.fan_class = (uint8_t)dm[pr.material].fan_class;
         ci.max_ray_depth = (int16_t)pr.max_ray_depth; ci.max_dr = (int16_t)m.max_diffuse_reflections;
-        ci.mat = pr.material; ci.w_cos = (float)m.ambient_weight;
+        ci.slot = 0xFFFFFFFFu; ci.w_cos = (float)m.ambient_weight;
     }
-    CUDA_TRY(s->d_colinfo.upload(dinfo));
     CUDA_TRY(s->d_cols_d.upload(dcd));
 
     // ---- textures ---------------------------------------------------------------------------------------
@@ -628,9 +627,14 @@ int sp_scene_commit(sp_scene* s) {
     std::vector<int32_t> all_ids((size_t)n_col);
     for (int i = 0; i < n_col; ++i) all_ids[i] = i;
     BuiltStream all = build_stream(s->cols, all_ids), shadow = build_stream(s->cols, s->shadow_ids);
+    for (int i = 0; i < n_col; ++i) {                    // (chunk, type << 28 | local) -> chunk << 24 | type << 20 | local
+        const int2 w = all.slot[i];
+        dinfo[i].slot = ((uint32_t)w.x << 24) | (((uint32_t)w.y >> 28) << 20) | ((uint32_t)w.y & 0xFFFFFu);
+    }
+    if (all.chunk_off.size() - 1 > 255) return fail("too many geometry chunks");
+    CUDA_TRY(s->d_colinfo.upload(dinfo));
     CUDA_TRY(s->geom_all.upload(all.data));
     CUDA_TRY(s->off_all.upload(all.chunk_off));
-    CUDA_TRY(s->slot_all.upload(all.slot));
     CUDA_TRY(s->geom_shadow.upload(shadow.data));
     CUDA_TRY(s->off_shadow.upload(shadow.chunk_off));
     CUDA_TRY(s->slot_shadow.upload(shadow.slot));
@@ -754,7 +758,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
         a.out.stats = s->d_stats.p;
         a.accum = job.accum;
         a.out_hit = job.out_hit; a.out_t = job.out_t; a.out_o = job.out_o; a.out_d = job.out_d;
-        a.all_slot = s->slot_all.p; a.shadow_slot = s->slot_shadow.p;
+        a.shadow_slot = s->slot_shadow.p;
         CUDA_TRY(cudaEventRecord(s->events[L], s->stream));
         CUDA_TRY(sp_launch_level(s->d, a, s->material_set, L == 0 ? s->grid0 : s->grid_q, s->stream));
     }

@@ -205,7 +205,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         HitRec hit; hit.t = SP_INF; hit.id = -1; hit.orient = 0;
         {
             const uint32_t src = meta_src(r.meta), mode = meta_mode(r.meta);
-            int2 where = make_int2(-1, -1);
+            uint32_t where = 0xFFFFFFFFu;                  // chunk | stream type | local index of the source collider
             bool need_test = active;
             if (active && src != SP_SRC_NONE) {
                 if (mode == SP_SELF_ZERO) {
@@ -216,7 +216,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                     hit.t = 0.f; hit.id = (int)src; hit.orient = dot(r.d, Nc) < 0.f ? 1 : -1;
                     need_test = false;
                 } else {
-                    where = __ldg(a.all_slot + src);
+                    where = __ldg(&sc.col_info[src].slot);
                 }
             }
             for (int c = 0; c < n_chunks; ++c) {
@@ -227,8 +227,8 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 }
                 if (need_test) {
                     SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = self.aa = -1; self.mode = mode;
-                    if (where.x == c) {
-                        const int ty = where.y >> 28, li = where.y & 0x0FFFFFFF;
+                    if ((where >> 24) == (uint32_t)c) {
+                        const int ty = (int)((where >> 20) & 15u), li = (int)(where & 0xFFFFFu);
                         if (ty == 0) self.sphere = li; else if (ty == 1) self.plane = li;
                         else if (ty == 2) self.cuboid = li; else if (ty == 3) self.tri = li; else self.aa = li;
                     }

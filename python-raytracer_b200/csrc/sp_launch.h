@@ -25,7 +25,6 @@ struct LevelArgs {
     float4* accum;                 // per pixel (or per user ray): xyz = sum of radiance
     // optional per-item outputs of level 0
     int32_t* out_hit; float* out_t; float* out_o; float* out_d;
-    const int2* all_slot;
     const int2* shadow_slot;
 };
 

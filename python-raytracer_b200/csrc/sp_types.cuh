@@ -70,7 +70,7 @@ struct DMaterial {
 struct DColInfo {
     uint8_t type, kind, mc, fan_class;
     int16_t max_ray_depth, max_dr;
-    int32_t mat;
+    uint32_t slot;             // where the collider sits in the full stream: chunk[24:32) stream type[20:24) local index[0:20)
     float w_cos;
 };
 static_assert(sizeof(DColInfo) == 16, "one float4");
