@@ -138,6 +138,11 @@ int  sp_scene_set_globals(sp_scene*, const double ambient[3],
                           const double* media_re, const double* media_im, int n_media);
 int  sp_scene_set_camera(sp_scene*, const sp_camera*);
 int  sp_scene_add_texture(sp_scene*, const uint8_t* rgb_hw3, int H, int W, int decode, int* tex_id);
+/* Same, for an image the caller names with a stable non-zero key (same key == same bytes): its texels
+ * stay resident on the device and are shared by every later scene of the process that uses the key, so
+ * re-describing a scene per animation frame (animation.py:27-31) uploads each image once. */
+int  sp_scene_add_texture_keyed(sp_scene*, uint64_t key, const uint8_t* rgb_hw3, int H, int W, int decode,
+                                int* tex_id);
 int  sp_scene_set_materials(sp_scene*, const sp_material*, int n);
 int  sp_scene_set_primitives(sp_scene*, const sp_primitive*, int n);
 int  sp_scene_set_colliders(sp_scene*, const sp_collider*, int n);

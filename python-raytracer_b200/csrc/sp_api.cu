@@ -77,7 +77,37 @@ template <typename T> struct DevBuf {
     void release() { if (p) g_pool.emplace(n * sizeof(T), p); p = nullptr; n = 0; }
 };
 
-struct HostTexture { int H, W, decode; std::vector<uint32_t> texels; };
+struct HostTexture { int H, W, decode; uint64_t key; std::vector<uint32_t> texels; };
+
+// Device-resident textures shared between scenes.  A caller that re-describes a scene every frame
+// (animation.py: update_scene + render) names each image with a stable non-zero key; the packed texels
+// of a key are uploaded once and reused by every later scene of the process (SURVEY §8f "GPU-resident
+// scene reuse": example1's 4096x3072 sky box costs 28 ms to pack and upload, the frame itself 0.6 ms).
+struct CachedTexture { uint64_t key; int H, W, decode; uint32_t* d; size_t bytes; int refs; uint64_t last_use; };
+static std::vector<CachedTexture> g_tex_cache;
+static uint64_t g_tex_clock = 0;
+static const size_t kTexCacheLimit = (size_t)8 << 30;          // bytes kept alive for idle (unreferenced) textures
+
+static int tex_cache_find(uint64_t key, int H, int W, int decode) {
+    for (size_t i = 0; i < g_tex_cache.size(); ++i)
+        if (g_tex_cache[i].key == key && g_tex_cache[i].H == H && g_tex_cache[i].W == W && g_tex_cache[i].decode == decode)
+            return (int)i;
+    return -1;
+}
+
+static void tex_cache_trim() {
+    size_t idle = 0;
+    for (auto& t : g_tex_cache) if (t.refs == 0) idle += t.bytes;
+    while (idle > kTexCacheLimit) {
+        int victim = -1;
+        for (size_t i = 0; i < g_tex_cache.size(); ++i)
+            if (g_tex_cache[i].refs == 0 && (victim < 0 || g_tex_cache[i].last_use < g_tex_cache[(size_t)victim].last_use)) victim = (int)i;
+        if (victim < 0) break;
+        idle -= g_tex_cache[(size_t)victim].bytes;
+        cudaFree(g_tex_cache[(size_t)victim].d);
+        g_tex_cache.erase(g_tex_cache.begin() + victim);
+    }
+}
 
 struct QueueSet {
     DevBuf<float4> q0, q1, q2;
@@ -131,6 +161,7 @@ struct sp_scene {
     DevBuf<DMaterial> d_mats;
     DevBuf<DTexture> d_texdesc;
     std::vector<DevBuf<uint32_t>> d_texels;
+    std::vector<uint64_t> cached_tex_keys;       // keys of the shared textures this scene holds a reference to
     DevBuf<DMedium> d_media;
     DevBuf<uint32_t> counts;
     DevBuf<DeviceStats> d_stats;
@@ -141,10 +172,20 @@ struct sp_scene {
     int grid0 = 0, grid_q = 0;                   // CTAs of level-0 / queue-fed launches
     uint32_t material_set = 0;                   // compiled kernel variant (sp_pick_material_set)
 
-    ~sp_scene() { release_device(); }
+    ~sp_scene() { release_device(); release_textures(); }
+    void release_textures() {                    // a scene holds one reference per shared texture for its whole life
+        for (uint64_t k : cached_tex_keys)
+            for (auto& t : g_tex_cache) if (t.key == k && t.refs > 0) { t.refs--; break; }
+        cached_tex_keys.clear();
+        tex_cache_trim();
+    }
+    bool holds_texture(uint64_t key) const {
+        return std::find(cached_tex_keys.begin(), cached_tex_keys.end(), key) != cached_tex_keys.end();
+    }
     void release_device() {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
+
         geom_all.release(); geom_shadow.release(); accum.release(); off_all.release(); off_shadow.release();
         slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
@@ -371,6 +412,8 @@ int sp_init(int device) {
 
 void sp_shutdown(void) {
     if (g_device >= 0) cudaDeviceSynchronize();
+    for (auto& t : g_tex_cache) cudaFree(t.d);
+    g_tex_cache.clear();
     pool_flush();
     for (auto st : g_stream_pool) cudaStreamDestroy(st);
     g_stream_pool.clear();
@@ -412,18 +455,29 @@ int sp_scene_set_camera(sp_scene* s, const sp_camera* cam) {
     return 0;
 }
 
-int sp_scene_add_texture(sp_scene* s, const uint8_t* rgb, int H, int W, int decode, int* tex_id) {
+int sp_scene_add_texture_keyed(sp_scene* s, uint64_t key, const uint8_t* rgb, int H, int W, int decode, int* tex_id) {
     NEED_SCENE(s);
     if (!rgb || H < 1 || W < 1) return fail("sp_scene_add_texture: invalid image");
     if (decode != SP_DECODE_PLAIN && decode != SP_DECODE_LINEAR) return fail("sp_scene_add_texture: unknown decode %d", decode);
     HostTexture t;
-    t.H = H; t.W = W; t.decode = decode;
-    t.texels.resize((size_t)H * W);
-    for (size_t i = 0; i < t.texels.size(); ++i)
-        t.texels[i] = (uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16);
+    t.H = H; t.W = W; t.decode = decode; t.key = key;
+    const int cached = key != 0 ? tex_cache_find(key, H, W, decode) : -1;
+    if (cached >= 0 && !s->holds_texture(key)) {                       // resident: pin it for the life of this scene
+        g_tex_cache[(size_t)cached].refs++;
+        s->cached_tex_keys.push_back(key);
+    }
+    if (cached < 0) {                                                  // not resident yet: pack RGB8 -> one word per texel
+        t.texels.resize((size_t)H * W);
+        for (size_t i = 0; i < t.texels.size(); ++i)
+            t.texels[i] = (uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16);
+    }
     s->textures.push_back(std::move(t));
     if (tex_id) *tex_id = (int)s->textures.size() - 1;
     return 0;
+}
+
+int sp_scene_add_texture(sp_scene* s, const uint8_t* rgb, int H, int W, int decode, int* tex_id) {
+    return sp_scene_add_texture_keyed(s, 0, rgb, H, W, decode, tex_id);
 }
 
 int sp_scene_set_materials(sp_scene* s, const sp_material* m, int n) {
@@ -605,8 +659,25 @@ int sp_scene_commit(sp_scene* s) {
     std::vector<DTexture> td((size_t)n_tex);
     s->d_texels.resize((size_t)n_tex);
     for (int i = 0; i < n_tex; ++i) {
-        CUDA_TRY(s->d_texels[i].upload(s->textures[i].texels));
-        td[i].texels = s->d_texels[i].p; td[i].H = s->textures[i].H; td[i].W = s->textures[i].W;
+        HostTexture& ht = s->textures[i];
+        if (ht.key != 0) {
+            int ci = tex_cache_find(ht.key, ht.H, ht.W, ht.decode);
+            if (ci < 0) {
+                if (ht.texels.empty()) return fail("texture %d: key %llu left the cache between description and commit", i, (unsigned long long)ht.key);
+                CachedTexture ct{ht.key, ht.H, ht.W, ht.decode, nullptr, ht.texels.size() * sizeof(uint32_t), 0, 0};
+                CUDA_TRY(cudaMalloc(&ct.d, ct.bytes));
+                CUDA_TRY(cudaMemcpy(ct.d, ht.texels.data(), ct.bytes, cudaMemcpyHostToDevice));
+                g_tex_cache.push_back(ct);
+                ci = (int)g_tex_cache.size() - 1;
+            }
+            if (!s->holds_texture(ht.key)) { g_tex_cache[(size_t)ci].refs++; s->cached_tex_keys.push_back(ht.key); }
+            g_tex_cache[(size_t)ci].last_use = ++g_tex_clock;
+            td[i].texels = g_tex_cache[(size_t)ci].d;
+        } else {
+            CUDA_TRY(s->d_texels[i].upload(ht.texels));
+            td[i].texels = s->d_texels[i].p;
+        }
+        td[i].H = ht.H; td[i].W = ht.W;
         td[i].decode = s->textures[i].decode; td[i].pad = 0;
     }
     CUDA_TRY(s->d_texdesc.upload(td));

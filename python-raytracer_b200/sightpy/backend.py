@@ -75,6 +75,7 @@ def load_library():
         "sp_scene_set_globals": (i32, [vp, vp, vp, vp, i32]),
         "sp_scene_set_camera": (i32, [vp, vp]),
         "sp_scene_add_texture": (i32, [vp, vp, i32, i32, i32, C.POINTER(i32)]),
+        "sp_scene_add_texture_keyed": (i32, [vp, u64, vp, i32, i32, i32, C.POINTER(i32)]),
         "sp_scene_set_materials": (i32, [vp, vp, i32]),
         "sp_scene_set_primitives": (i32, [vp, vp, i32]),
         "sp_scene_set_colliders": (i32, [vp, vp, i32]),
@@ -168,8 +169,8 @@ class NativeScene:
         for t in flat.textures:
             tid = C.c_int(-1)
             u8 = np.ascontiguousarray(t.u8)
-            _check(lib, lib.sp_scene_add_texture(h, _ptr(u8), u8.shape[0], u8.shape[1], t.decode, C.byref(tid)),
-                   "add_texture")
+            _check(lib, lib.sp_scene_add_texture_keyed(h, int(getattr(t, "key", 0)), _ptr(u8), u8.shape[0], u8.shape[1],
+                                                       t.decode, C.byref(tid)), "add_texture")
         for name, fn in (("materials", lib.sp_scene_set_materials), ("primitives", lib.sp_scene_set_primitives),
                          ("colliders", lib.sp_scene_set_colliders), ("lights", lib.sp_scene_set_lights),
                          ("importance", lib.sp_scene_set_importance),

@@ -47,10 +47,16 @@ def decode_table(kind):
     return sRGB_to_sRGB_linear(b) if kind == DECODE_LINEAR else b
 
 
+_NEXT_TEXTURE_KEY = [1]
+
+
 class TextureImage:
-    """uint8 RGB image + decode-table kind. ``shape``/``as_float`` mimic the reference arrays."""
+    """uint8 RGB image + decode-table kind. ``shape``/``as_float`` mimic the reference arrays.
+    Immutable by convention: ``key`` names its bytes for the backend's device-resident texture cache."""
 
     def __init__(self, u8, decode):
+        self.key = _NEXT_TEXTURE_KEY[0]          # unique per object for the life of the process
+        _NEXT_TEXTURE_KEY[0] += 1
         u8 = np.ascontiguousarray(u8, dtype=np.uint8)
         if u8.ndim != 3 or u8.shape[2] != 3:
             raise ValueError("TextureImage expects an H x W x 3 uint8 array")

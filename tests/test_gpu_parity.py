@@ -409,3 +409,19 @@ def test_animation_frames_are_written(tmp_path, monkeypatch):
         assert not (tmp_path / rel).exists()
     sp.create_animation(sc, samples_per_pixel=1, fps=2, start_time=0.0, final_time=1.0, update_scene=update, name="t")
     assert sorted(p.name for p in (tmp_path / "frames").iterdir()) == ["t_0.png", "t_1.png"]
+
+
+def test_textures_stay_resident_across_scene_rebuilds():
+    """SURVEY §8f row 1 (animation reuse): after Scene.invalidate() the scene is re-described and re-committed,
+    but its images are found in the device-resident texture cache by key: same frame, far cheaper upload."""
+    import time
+    scene = build_scene("example1", (64, 48))
+    first = np.asarray(scene.render(2))
+    t = []
+    for _ in range(3):
+        scene.invalidate()
+        t0 = time.perf_counter()
+        again = np.asarray(scene.render(2))
+        t.append(time.perf_counter() - t0)
+        assert np.array_equal(first, again)
+    assert min(t) < 0.02, t          # packing + uploading the 4096x3072 sky box alone takes ~30 ms
