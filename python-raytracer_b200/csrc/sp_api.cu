@@ -37,6 +37,12 @@ static int fail(const char* fmt, ...) {
 // synchronisation every cudaFree implies) would otherwise cost tens of milliseconds to seconds per frame.
 // sp_shutdown returns everything to the driver.
 #include <map>
+#include <mutex>
+// One lock for everything the scenes of a process share (buffer / stream / event pools, texture cache):
+// every exported entry point that can touch them takes it, so scenes may be driven from different threads
+// (ctypes releases the GIL during a call); rendering calls of different scenes therefore serialise.
+static std::recursive_mutex g_lock;
+#define SP_LOCK std::lock_guard<std::recursive_mutex> lock__(g_lock)
 static std::multimap<size_t, void*> g_pool;
 
 static void pool_flush() {
@@ -126,6 +132,15 @@ struct QueueSet {
 // streams and events are recycled the same way
 static std::vector<cudaStream_t> g_stream_pool;
 static std::vector<cudaEvent_t> g_event_pool;
+
+struct ScopedEvent {                     // a pooled event for the duration of one call
+    cudaEvent_t e = nullptr;
+    ScopedEvent() {
+        if (!g_event_pool.empty()) { e = g_event_pool.back(); g_event_pool.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+    }
+    ~ScopedEvent() { if (e) g_event_pool.push_back(e); }
+};
 
 struct sp_scene {
     // ---- host description ---------------------------------------------------------------------
@@ -387,6 +402,7 @@ int sp_device_count(void) {
 }
 
 int sp_init(int device) {
+    SP_LOCK;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
@@ -411,6 +427,7 @@ int sp_init(int device) {
 }
 
 void sp_shutdown(void) {
+    SP_LOCK;
     if (g_device >= 0) cudaDeviceSynchronize();
     for (auto& t : g_tex_cache) cudaFree(t.d);
     g_tex_cache.clear();
@@ -429,7 +446,10 @@ int sp_scene_create(sp_scene** out) {
     return 0;
 }
 
-void sp_scene_destroy(sp_scene* s) { delete s; }
+void sp_scene_destroy(sp_scene* s) {
+    SP_LOCK;
+    delete s;
+}
 
 // =================================================================================================
 // scene description
@@ -456,6 +476,7 @@ int sp_scene_set_camera(sp_scene* s, const sp_camera* cam) {
 }
 
 int sp_scene_add_texture_keyed(sp_scene* s, uint64_t key, const uint8_t* rgb, int H, int W, int decode, int* tex_id) {
+    SP_LOCK;
     NEED_SCENE(s);
     if (!rgb || H < 1 || W < 1) return fail("sp_scene_add_texture: invalid image");
     if (decode != SP_DECODE_PLAIN && decode != SP_DECODE_LINEAR) return fail("sp_scene_add_texture: unknown decode %d", decode);
@@ -526,6 +547,7 @@ int sp_scene_set_shadow_colliders(sp_scene* s, const int32_t* ids, int n) {
 }
 
 int sp_scene_commit(sp_scene* s) {
+    SP_LOCK;
     if (!s) return fail("sp_scene_commit: null scene");
     if (g_device < 0) return fail("sp_scene_commit: call sp_init first");
     if (s->media_re.empty()) return fail("sp_scene_commit: sp_scene_set_globals was not called");
@@ -911,14 +933,16 @@ static uint32_t pick_chunk(sp_scene* s, bool first) {
 }
 
 int sp_render_samples(sp_scene* s, int sample_begin, int sample_end, uint64_t seed, int clear, sp_stats* st) {
+    SP_LOCK;
     if (s && s->committed && !s->has_camera) return fail("sp_render_samples: the scene has no camera");
     int rc = begin_call(s, seed, st, "sp_render_samples",
                         s && s->committed ? (uint64_t)std::max(sample_end - sample_begin, 0) * s->accum.n : 0);
     if (rc) return rc;
     if (!s->has_camera) return fail("sp_render_samples: the scene has no camera");
     if (sample_begin < 0 || sample_end < sample_begin) return fail("sp_render_samples: invalid sample range");
-    cudaEvent_t t0, t1;
-    CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+    ScopedEvent ev0, ev1;
+    if (!ev0.e || !ev1.e) return fail("sp_render_samples: cudaEventCreate failed");
+    cudaEvent_t t0 = ev0.e, t1 = ev1.e;
     CUDA_TRY(cudaEventRecord(t0, s->stream));
     if (clear) CUDA_TRY(cudaMemsetAsync(s->accum.p, 0, s->accum.n * sizeof(float4), s->stream));
     const uint32_t n_pix_total = (uint32_t)s->d.cam.W * (uint32_t)s->d.cam.H;
@@ -942,7 +966,6 @@ int sp_render_samples(sp_scene* s, int sample_begin, int sample_end, uint64_t se
         rc = run_chunk(s, job, st);
     }
     int rc2 = end_call(s, st, t0, t1);
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
     return rc ? rc : rc2;
 }
 
@@ -950,6 +973,7 @@ void* sp_accum_device_ptr(sp_scene* s) { return s ? (void*)s->accum.p : nullptr;
 uint64_t sp_accum_bytes(sp_scene* s) { return s ? (uint64_t)(s->accum.n * sizeof(float4)) : 0; }
 
 int sp_resolve(sp_scene* s, int spp_total, float* out_linear, uint8_t* out_srgb8) {
+    SP_LOCK;
     if (!s || !s->committed || !s->has_camera) return fail("sp_resolve: scene not committed or has no camera");
     if (spp_total < 1) return fail("sp_resolve: spp_total must be >= 1");
     CUDA_TRY(cudaSetDevice(g_device));
@@ -966,6 +990,7 @@ int sp_resolve(sp_scene* s, int spp_total, float* out_linear, uint8_t* out_srgb8
 }
 
 int sp_scene_set_stream(sp_scene* s, void* cuda_stream, int use_it) {
+    SP_LOCK;
     if (!s) return fail("sp_scene_set_stream: null scene");
     s->user_stream_set = use_it != 0;
     s->user_stream = (cudaStream_t)cuda_stream;
@@ -986,6 +1011,7 @@ int sp_render(sp_scene* s, int spp, uint64_t seed, float* out_linear, uint8_t* o
 
 int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64_t seed, float* out_rgb,
              int32_t* out_hit_id, float* out_t, sp_stats* st) {
+    SP_LOCK;
     int rc = begin_call(s, seed, st, "sp_trace", (uint64_t)std::max(n, 0));
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!origins || !dirs))) return fail("sp_trace: invalid arguments");
@@ -1034,6 +1060,7 @@ int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64
 }
 
 static int primary_pass(sp_scene* s, int run, int sample, uint64_t seed, float* out_o, float* out_d, float* out_t, const char* what) {
+    SP_LOCK;
     int rc = begin_call(s, seed, nullptr, what, s && s->committed ? s->accum.n : 0);
     if (rc) return rc;
     if (!s->has_camera) return fail("%s: the scene has no camera", what);
@@ -1080,6 +1107,7 @@ int sp_set_option(sp_scene* s, const char* name, int64_t value) {
 }
 
 int sp_measure_peaks(double* fp32_tflops, double* copy_gbs) {
+    SP_LOCK;
     if (g_device < 0) return fail("sp_measure_peaks: call sp_init first");
     CUDA_TRY(cudaSetDevice(g_device));
     double a = 0.0, b = 0.0;
