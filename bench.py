@@ -135,7 +135,7 @@ def cpu_sample(width, height, n_samples, processes):
     return sum(r for r, _ in res), time.perf_counter() - t0
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -149,7 +149,7 @@ def run_reference(args):
         rays += r; secs += s
     value = rays / secs / 1e6
     sample = f"Cornell box {w}x{h}, {cores} spp per step (one sample per worker process), float64 numpy oracle"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -162,7 +162,7 @@ def run_reference(args):
 
 
 # ---- native arm --------------------------------------------------------------------------------------
-def run_native(args):
+def run_native(args, emit=print):
     import torch
     import torch.distributed as dist
 
@@ -335,17 +335,32 @@ def run_native(args):
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
         "shadow_rays": totals["shadow"],
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_native(args)
+    # The contract is ONE JSON line on stdout.  Libraries underneath print there too (NCCL announces its
+    # version on stdout when the first communicator is created), so file descriptor 1 points at stderr for
+    # the duration of the run and is restored for the result line only.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    emit = lines.append
+    try:
+        if args.impl == "reference":
+            run_reference(args, emit)
+        else:
+            run_native(args, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in lines:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
