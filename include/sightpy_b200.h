@@ -165,6 +165,10 @@ int  sp_render(sp_scene*, int spp, uint64_t seed, float* out_linear_rgb, uint8_t
  * the call returns after it completed. */
 int  sp_render_samples(sp_scene*, int sample_begin, int sample_end, uint64_t seed, int clear,
                        sp_stats* stats);
+/* Same for the pixels [pix_begin, pix_end) only (row-major pixel index): pixel-band sharding, used when a
+ * frame has fewer samples than there are GPUs. */
+int  sp_render_region(sp_scene*, int64_t pix_begin, int64_t pix_end, int sample_begin, int sample_end,
+                      uint64_t seed, int clear, sp_stats* stats);
 void*    sp_accum_device_ptr(sp_scene*);      /* float4[H*W] on the scene's device                 */
 uint64_t sp_accum_bytes(sp_scene*);
 /* Resolve the accumulation buffer: divide by spp_total, tonemap (on the device), then copy to

@@ -932,41 +932,49 @@ static uint32_t pick_chunk(sp_scene* s, bool first) {
     return (uint32_t)std::max<int64_t>(p, 1024);
 }
 
-int sp_render_samples(sp_scene* s, int sample_begin, int sample_end, uint64_t seed, int clear, sp_stats* st) {
+int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample_begin, int sample_end, uint64_t seed,
+                     int clear, sp_stats* st) {
     SP_LOCK;
-    if (s && s->committed && !s->has_camera) return fail("sp_render_samples: the scene has no camera");
-    int rc = begin_call(s, seed, st, "sp_render_samples",
-                        s && s->committed ? (uint64_t)std::max(sample_end - sample_begin, 0) * s->accum.n : 0);
+    if (s && s->committed && !s->has_camera) return fail("sp_render_region: the scene has no camera");
+    const uint64_t region = (s && s->committed && pix_end > pix_begin) ? (uint64_t)(pix_end - pix_begin) : 0;
+    int rc = begin_call(s, seed, st, "sp_render_region", (uint64_t)std::max(sample_end - sample_begin, 0) * region);
     if (rc) return rc;
-    if (!s->has_camera) return fail("sp_render_samples: the scene has no camera");
-    if (sample_begin < 0 || sample_end < sample_begin) return fail("sp_render_samples: invalid sample range");
+    const uint32_t n_pix_total = (uint32_t)s->d.cam.W * (uint32_t)s->d.cam.H;
+    if (sample_begin < 0 || sample_end < sample_begin) return fail("sp_render_region: invalid sample range");
+    if (pix_begin < 0 || pix_end < pix_begin || pix_end > (int64_t)n_pix_total) return fail("sp_render_region: invalid pixel range");
     ScopedEvent ev0, ev1;
-    if (!ev0.e || !ev1.e) return fail("sp_render_samples: cudaEventCreate failed");
+    if (!ev0.e || !ev1.e) return fail("sp_render_region: cudaEventCreate failed");
     cudaEvent_t t0 = ev0.e, t1 = ev1.e;
     CUDA_TRY(cudaEventRecord(t0, s->stream));
     if (clear) CUDA_TRY(cudaMemsetAsync(s->accum.p, 0, s->accum.n * sizeof(float4), s->stream));
-    const uint32_t n_pix_total = (uint32_t)s->d.cam.W * (uint32_t)s->d.cam.H;
-    uint32_t sample = (uint32_t)sample_begin, pix = 0;
+    const uint32_t first_pix = (uint32_t)pix_begin, n_region = (uint32_t)(pix_end - pix_begin);
+    uint32_t sample = (uint32_t)sample_begin, pix = 0;          // pix: offset inside the region
     bool first = true;
-    while (sample < (uint32_t)sample_end && rc == 0) {
+    while (n_region > 0 && sample < (uint32_t)sample_end && rc == 0) {
         const uint32_t P = pick_chunk(s, first);
         first = false;
         ChunkJob job{};
         job.source = SP_SRC_CAMERA; job.run = SP_RUN_FULL; job.accum = s->accum.p;
-        if (pix == 0 && P >= n_pix_total) {
-            const uint32_t ns = std::min<uint32_t>(P / n_pix_total, (uint32_t)sample_end - sample);
-            job.pix_begin = 0; job.n_pix = n_pix_total; job.sample_begin = sample; job.n_items = ns * n_pix_total;
+        if (pix == 0 && P >= n_region) {                         // whole region x several samples
+            const uint32_t ns = std::min<uint32_t>(P / n_region, (uint32_t)sample_end - sample);
+            job.pix_begin = first_pix; job.n_pix = n_region; job.sample_begin = sample; job.n_items = ns * n_region;
             sample += ns;
-        } else {
-            const uint32_t n = std::min<uint32_t>(P, n_pix_total - pix);
-            job.pix_begin = pix; job.n_pix = n; job.sample_begin = sample; job.n_items = n;
+        } else {                                                 // a slice of the region, one sample
+            const uint32_t n = std::min<uint32_t>(P, n_region - pix);
+            job.pix_begin = first_pix + pix; job.n_pix = n; job.sample_begin = sample; job.n_items = n;
             pix += n;
-            if (pix == n_pix_total) { pix = 0; ++sample; }
+            if (pix == n_region) { pix = 0; ++sample; }
         }
         rc = run_chunk(s, job, st);
     }
     int rc2 = end_call(s, st, t0, t1);
     return rc ? rc : rc2;
+}
+
+int sp_render_samples(sp_scene* s, int sample_begin, int sample_end, uint64_t seed, int clear, sp_stats* st) {
+    if (!s || !s->committed) return fail("sp_render_samples: scene not committed (sp_scene_commit)");
+    if (!s->has_camera) return fail("sp_render_samples: the scene has no camera");
+    return sp_render_region(s, 0, (int64_t)s->accum.n, sample_begin, sample_end, seed, clear, st);
 }
 
 void* sp_accum_device_ptr(sp_scene* s) { return s ? (void*)s->accum.p : nullptr; }

@@ -85,6 +85,7 @@ def load_library():
         "sp_scene_commit": (i32, [vp]),
         "sp_render": (i32, [vp, i32, u64, vp, vp, C.POINTER(Stats)]),
         "sp_render_samples": (i32, [vp, i32, i32, u64, i32, C.POINTER(Stats)]),
+        "sp_render_region": (i32, [vp, C.c_int64, C.c_int64, i32, i32, u64, i32, C.POINTER(Stats)]),
         "sp_accum_device_ptr": (vp, [vp]),
         "sp_accum_bytes": (u64, [vp]),
         "sp_resolve": (i32, [vp, i32, vp, vp]),
@@ -203,6 +204,14 @@ class NativeScene:
         st = Stats()
         _check(self.lib, self.lib.sp_render_samples(self.handle, int(sample_begin), int(sample_end), int(seed),
                                                     int(bool(clear)), C.byref(st)), "sp_render_samples")
+        return st.as_dict()
+
+    def render_region(self, pix_begin, pix_end, sample_begin, sample_end, seed=0, clear=True):
+        """Accumulate samples [sample_begin, sample_end) of the pixels [pix_begin, pix_end) (row-major index)."""
+        st = Stats()
+        _check(self.lib, self.lib.sp_render_region(self.handle, int(pix_begin), int(pix_end), int(sample_begin),
+                                                   int(sample_end), int(seed), int(bool(clear)), C.byref(st)),
+               "sp_render_region")
         return st.as_dict()
 
     def accum_pointer(self):

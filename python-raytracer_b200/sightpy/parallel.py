@@ -1,6 +1,7 @@
 """Frame-level sharding across the GPUs of one node.
 
 Pixels and samples are independent, so the only exchange is the final image: rank r of R renders
+(when there are fewer samples than ranks: a contiguous band of pixels for all samples, otherwise)
 the contiguous sample range [r*spp/R, (r+1)*spp/R) of the whole frame into its own float4
 accumulation buffer; the buffers are summed onto rank 0 with one NCCL ``reduce`` over NVLink
 (33 MB at 1080p) and rank 0 tonemaps.  The counter-based RNG is keyed by the *global* sample
@@ -59,8 +60,14 @@ def render_frame(native, spp, seed=0, want_linear=False):
         return (srgb, stats) if not want_linear else (srgb, lin, stats)
     import torch.distributed as dist
     native.use_current_stream()      # same stream as the collective: the reduce is ordered after the last level kernel
-    begin, end = sample_range(spp, rank, size)
-    stats = native.render_samples(begin, end, seed, clear=True)
+    if spp >= size:
+        begin, end = sample_range(spp, rank, size)
+        stats = native.render_samples(begin, end, seed, clear=True)
+    else:
+        # fewer samples than ranks: contiguous pixel bands instead (the reduce then just concatenates,
+        # every other rank's pixels being zero)
+        begin, end = sample_range(native.width * native.height, rank, size)
+        stats = native.render_region(begin, end, 0, spp, seed, clear=True)
     acc = native.accum_tensor()
     dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
     srgb, lin = native.resolve(spp, want_linear=want_linear)     # synchronises the stream first

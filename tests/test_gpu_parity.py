@@ -425,3 +425,18 @@ def test_textures_stay_resident_across_scene_rebuilds():
         t.append(time.perf_counter() - t0)
         assert np.array_equal(first, again)
     assert min(t) < 0.02, t          # packing + uploading the 4096x3072 sky box alone takes ~30 ms
+
+
+def test_pixel_band_shards_add_up_to_the_full_frame():
+    """Pixel-band sharding (parallel.py, used when spp < number of GPUs): disjoint pixel ranges rendered into
+    the same accumulator reproduce the full frame."""
+    nat, _ = native_for("cornell")
+    n = nat.width * nat.height
+    _, full, sf = nat.render(2, seed=9)
+    rays = 0
+    for k, (a, b) in enumerate([(0, n // 3), (n // 3, n // 3 + 7), (n // 3 + 7, n)]):
+        rays += nat.render_region(a, b, 0, 2, seed=9, clear=(k == 0))["rays_total"]
+    _, parts = nat.resolve(2)
+    nat.close()
+    assert rays == sf["rays_total"]
+    np.testing.assert_allclose(parts, full, rtol=1e-4, atol=1e-6)

@@ -58,12 +58,20 @@ def _worker(rank, world, port, spp, out_dir):
             pass
 
         def render_samples(self, begin, end, seed=0, clear=True):
+            return self.render_region(0, self.width * self.height, begin, end, seed, clear)
+
+        def render_region(self, pix_begin, pix_end, begin, end, seed=0, clear=True):
             if clear:
                 self.acc.zero_()
             orc = Oracle(self.flat, rng="philox", seed=seed)
             view = self.acc.view(-1, 4)
+            pixels = np.arange(pix_begin, pix_end, dtype=np.uint32)
             for s in range(begin, end):
-                view[:, :3] += torch.from_numpy(orc.render_linear(1, sample_begin=s).T.astype(np.float32))
+                if len(pixels) == 0:
+                    break
+                O, D, pix = orc.camera_rays(s, pixels=pixels)
+                rgb = orc.trace_columns(O, D, pix, sample=s)["rgb"]
+                view[pix_begin:pix_end, :3] += torch.from_numpy(rgb.astype(np.float32))
             return dict(rays_total=orc.rays_total)
 
         def accum_tensor(self):
@@ -81,9 +89,10 @@ def _worker(rank, world, port, spp, out_dir):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_gloo_frame_equals_single_process(tmp_path):
+@pytest.mark.parametrize("spp", [3, 1])          # 3: sample-range shards; 1 (< world size): pixel-band shards
+def test_two_rank_gloo_frame_equals_single_process(tmp_path, spp):
     import torch.multiprocessing as mp
-    spp, world = 3, 2
+    world = 2
     mp.start_processes(_worker, args=(world, _free_port(), spp, str(tmp_path)), nprocs=world, join=True,
                        start_method="spawn")
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
