@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -917,6 +918,15 @@ static int end_call(sp_scene* s, sp_stats* st, cudaEvent_t t0, cudaEvent_t t1) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, t0, t1);
         st->device_ms = ms;
+    }
+    if (getenv("SIGHTPY_PHASE_TIMING")) {             // only meaningful for -DSP_PHASE_TIMING builds of sp_kernels.cu
+        double tot = 0;
+        for (int k = 0; k < 6; ++k) tot += (double)ds.phase_cycles[k];
+        if (tot > 0)
+            fprintf(stderr, "[sightpy-b200] warp-cycles: generate %.1f %%, intersect %.1f %%, park+count %.1f %%, wait A %.1f %%, "
+                            "shade %.1f %%, wait C %.1f %%\n", 100.0 * ds.phase_cycles[0] / tot, 100.0 * ds.phase_cycles[1] / tot,
+                    100.0 * ds.phase_cycles[2] / tot, 100.0 * ds.phase_cycles[3] / tot, 100.0 * ds.phase_cycles[4] / tot,
+                    100.0 * ds.phase_cycles[5] / tot);
     }
     if (ds.overflow) return fail("wavefront queue overflow: raise ray_queue_capacity / fan_queue_capacity or lower chunk_primaries");
     return 0;

@@ -71,6 +71,14 @@ struct IterShared {
                                                    // while the other is in use, which saves a barrier
 };
 
+// Development aid: build with -DSP_PHASE_TIMING and run with SIGHTPY_PHASE_TIMING=1 to get the share of
+// warp-cycles each phase of the kernel takes (clock64() at the phase boundaries, printed by sp_api.cu).
+#ifdef SP_PHASE_TIMING
+#define SP_TICK(k) do { const long long now__ = clock64(); phase_acc[k] += (unsigned long long)(now__ - tick__); tick__ = now__; } while (0)
+#else
+#define SP_TICK(k) do { } while (0)
+#endif
+
 template <uint32_t FEAT>
 __global__ void __launch_bounds__(SP_BLOCK, SP_CTAS_PER_SM(FEAT))
 sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
@@ -116,6 +124,10 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     ctx.lin_lut = s_lin_lut;
     if (tid < sizeof(sh.cnt) / sizeof(uint32_t)) reinterpret_cast<uint32_t*>(sh.cnt)[tid] = 0u;
     __syncthreads();
+#ifdef SP_PHASE_TIMING
+    unsigned long long phase_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long tick__ = clock64();
+#endif
     uint32_t parity = 0;
     for (unsigned long long base64 = (unsigned long long)blockIdx.x * SP_BATCH; base64 < total;
          base64 += (unsigned long long)gridDim.x * SP_BATCH, parity ^= 1u) {
@@ -201,6 +213,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
             continue;
         }
 
+        SP_TICK(0);
         // ---- 2. nearest hit over all colliders ------------------------------------------------------
         HitRec hit; hit.t = SP_INF; hit.id = -1; hit.orient = 0;
         {
@@ -248,6 +261,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         }
         if ((FEAT & SP_F_LEVEL0) && a.run == SP_RUN_DISTANCES) continue;
 
+        SP_TICK(1);
         // ---- 3. park the ray; what the hit will emit; per-warp counts of bins and queue records ---------
         sh.state[0][slot] = __float_as_uint(r.o.x); sh.state[1][slot] = __float_as_uint(r.o.y); sh.state[2][slot] = __float_as_uint(r.o.z);
         sh.state[3][slot] = __float_as_uint(r.d.x); sh.state[4][slot] = __float_as_uint(r.d.y); sh.state[5][slot] = __float_as_uint(r.d.z);
@@ -324,7 +338,9 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         }
         }   // pass
         if ((FEAT & SP_F_LEVEL0) && a.run != SP_RUN_FULL) continue;
+        SP_TICK(2);
         __syncthreads();                                                            // (A) everything parked
+        SP_TICK(3);
         // clear the other counter set: last touched before barrier (C) of the previous iteration,
         // next touched after barrier (C) of this one
         if (tid < sizeof(IterCounters) / sizeof(uint32_t)) reinterpret_cast<uint32_t*>(&sh.cnt[parity ^ 1u])[tid] = 0u;
@@ -381,7 +397,9 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 if (ctx.fan_slot != SP_SLOT_NONE) sp_write_dead(a.out.fans, ctx.fan_slot);
             }
         }
+        SP_TICK(4);
         __syncthreads();                                                            // (C) the exchange area is free again
+        SP_TICK(5);
     }
 
     // ---- counters: one atomic per warp -------------------------------------------------------------
@@ -391,6 +409,10 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         traced += __shfl_down_sync(0xffffffffu, traced, o);
         shr += __shfl_down_sync(0xffffffffu, shr, o);
     }
+#ifdef SP_PHASE_TIMING
+    if (lane == 0)
+        for (int k = 0; k < 6; ++k) atomicAdd(&a.out.stats->phase_cycles[k], phase_acc[k]);
+#endif
     if (lane == 0) {
         if (traced) atomicAdd(&a.out.stats->rays[a.level], traced);
         if (shr) atomicAdd(&a.out.stats->shadow_rays, shr);

@@ -174,6 +174,9 @@ struct LevelOut {
 struct DeviceStats {
     unsigned long long rays[SP_MAX_LEVELS];
     unsigned long long shadow_rays;
+    // -DSP_PHASE_TIMING builds: warp-cycles spent in [0] ray generation, [1] intersection, [2] park + count,
+    // [3] waiting at barrier A, [4] shading, [5] waiting at barrier C (summed over warps and launches)
+    unsigned long long phase_cycles[6];
     unsigned int overflow;
     unsigned int pad;
 };
