@@ -440,3 +440,15 @@ def test_pixel_band_shards_add_up_to_the_full_frame():
     nat.close()
     assert rays == sf["rays_total"]
     np.testing.assert_allclose(parts, full, rtol=1e-4, atol=1e-6)
+
+
+def test_example_scripts_run(tmp_path):
+    """The scripts under examples/ use nothing but `from sightpy import *`, like the reference's own examples."""
+    import subprocess
+    import sys
+    from conftest import REPO
+    for script, args in (("cornell_box.py", ["96", "54", "4"]), ("spheres.py", [])):
+        out = subprocess.run([sys.executable, str(REPO / "examples" / script), *args], cwd=tmp_path, capture_output=True,
+                             text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert (tmp_path / script.replace(".py", ".png")).stat().st_size > 1000
