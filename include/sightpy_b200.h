@@ -194,7 +194,9 @@ int  sp_distances(sp_scene*, uint64_t seed, float* out_t);
 
 /* ---- tuning / measurement ---------------------------------------------------------------------- */
 /* options: "ray_queue_capacity", "fan_queue_capacity" (records), "chunk_primaries" (0 = auto),
- * "max_levels" (debugging: trace only the first k recursion depths, 0 = all) */
+ * "max_levels" (debugging: trace only the first k recursion depths, 0 = all),
+ * "bvh" (1 = scenes with >= 64 colliders put their small colliders into a bounding-volume hierarchy, the
+ *        default; 0 = every ray tests every collider) */
 int  sp_set_option(sp_scene*, const char* name, int64_t value);
 /* Roofline denominators measured on the bound device: dependent-free FFMA chains (TFLOP/s, 2 flop
  * per FFMA) and a float4 copy (GB/s, read + write bytes). */

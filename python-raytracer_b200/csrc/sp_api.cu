@@ -158,7 +158,7 @@ struct sp_scene {
     std::vector<sp_light> lights;
     std::vector<int32_t> importance, shadow_ids;
     // ---- options ------------------------------------------------------------------------------------
-    int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0;
+    int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0, opt_bvh = 1;
     // ---- device residency -----------------------------------------------------------------------------
     DScene d{};
     int n_levels = 1;
@@ -171,6 +171,8 @@ struct sp_scene {
     DevBuf<int> off_all, off_shadow;
     DevBuf<int2> slot_shadow;
     DevBuf<DCollider> d_cols;
+    DevBuf<float4> bvh_nodes, bvh_data;
+    DevBuf<int4> bvh_items;
     DevBuf<DColInfo> d_colinfo;
     DevBuf<double> d_cols_d;
     DevBuf<DPrimitive> d_prims;
@@ -203,7 +205,7 @@ struct sp_scene {
         d_texels.clear();
 
         geom_all.release(); geom_shadow.release(); accum.release(); off_all.release(); off_shadow.release();
-        slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_cols_d.release(); d_prims.release();
+        slot_shadow.release(); d_cols.release(); d_colinfo.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
         for (auto e : events) g_event_pool.push_back(e);
@@ -378,6 +380,153 @@ static BuiltStream build_stream(const std::vector<sp_collider>& cols, std::vecto
         bs.chunk_off.push_back(4);
     }
     return bs;
+}
+
+// ---- BVH over the small colliders of a large scene (layout and rationale: sp_geometry.cuh) ----------------
+struct Aabb { double lo[3], hi[3]; };
+
+static Aabb collider_aabb(const sp_collider& c) {
+    const double* p = c.p;
+    Aabb b;
+    auto from_center = [&](const double* ctr, const double ext[3]) {
+        for (int k = 0; k < 3; ++k) { b.lo[k] = ctr[k] - ext[k]; b.hi[k] = ctr[k] + ext[k]; }
+    };
+    switch (c.type) {
+    case SP_COLLIDER_SPHERE: { const double e[3] = {std::fabs(p[3]), std::fabs(p[3]), std::fabs(p[3])}; from_center(p, e); break; }
+    case SP_COLLIDER_PLANE: {            // |u_axis . (M - C)| <= w, |v_axis . (M - C)| <= h  (axes as given, plane.py:57-90)
+        double e[3];
+        const double uu = p[3] * p[3] + p[4] * p[4] + p[5] * p[5], vv = p[6] * p[6] + p[7] * p[7] + p[8] * p[8];
+        for (int k = 0; k < 3; ++k)
+            e[k] = (uu > 0 ? std::fabs(p[3 + k]) / uu * std::fabs(p[12]) : 0.0) + (vv > 0 ? std::fabs(p[6 + k]) / vv * std::fabs(p[13]) : 0.0);
+        from_center(p, e);
+        break;
+    }
+    case SP_COLLIDER_CUBOID: {           // centre +- sum of |axis| * half size
+        double e[3];
+        for (int k = 0; k < 3; ++k)
+            e[k] = 0.5 * (std::fabs(p[3 + k] * p[18]) + std::fabs(p[6 + k] * p[19]) + std::fabs(p[9 + k] * p[20]));
+        from_center(p, e);
+        break;
+    }
+    default:                             // triangle
+        for (int k = 0; k < 3; ++k) {
+            b.lo[k] = std::min(p[k], std::min(p[3 + k], p[6 + k]));
+            b.hi[k] = std::max(p[k], std::max(p[3 + k], p[6 + k]));
+        }
+    }
+    for (int k = 0; k < 3; ++k) {        // conservative: beyond anything float rounding of the slab test can cost
+        const double pad = 1e-5 * (std::fabs(b.lo[k]) + std::fabs(b.hi[k])) + 1e-5;
+        b.lo[k] -= pad; b.hi[k] += pad;
+    }
+    return b;
+}
+
+struct BuiltBvh {
+    std::vector<float4> nodes, data;
+    std::vector<int4> items;
+};
+
+static int bvh_build_rec(BuiltBvh& out, std::vector<int>& order, int first, int count, const std::vector<Aabb>& boxes,
+                         const std::vector<int>& item_of, Aabb& bounds) {
+    // returns the child code of this subtree (>= 0 node index, < 0 leaf) and its bounds
+    for (int k = 0; k < 3; ++k) { bounds.lo[k] = 1e300; bounds.hi[k] = -1e300; }
+    for (int i = first; i < first + count; ++i)
+        for (int k = 0; k < 3; ++k) {
+            bounds.lo[k] = std::min(bounds.lo[k], boxes[order[i]].lo[k]);
+            bounds.hi[k] = std::max(bounds.hi[k], boxes[order[i]].hi[k]);
+        }
+    if (count <= 4) {                    // leaf: its items become consecutive in the item array
+        const int at = (int)out.items.size();
+        for (int i = first; i < first + count; ++i) out.items.push_back(make_int4(item_of[order[i]], 0, order[i], 0));
+        return ~((at << 3) | (count - 1));
+    }
+    double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+    for (int i = first; i < first + count; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const double c = 0.5 * (boxes[order[i]].lo[k] + boxes[order[i]].hi[k]);
+            clo[k] = std::min(clo[k], c); chi[k] = std::max(chi[k], c);
+        }
+    int axis = 0;
+    for (int k = 1; k < 3; ++k) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+    const int half = count / 2;
+    std::nth_element(order.begin() + first, order.begin() + first + half, order.begin() + first + count, [&](int a, int b) {
+        return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis];
+    });
+    const int me = (int)out.nodes.size() / 4;
+    out.nodes.resize(out.nodes.size() + 4);
+    Aabb ba, bb;
+    const int ca = bvh_build_rec(out, order, first, half, boxes, item_of, ba);
+    const int cb = bvh_build_rec(out, order, first + half, count - half, boxes, item_of, bb);
+    out.nodes[4 * me] = make_float4((float)ba.lo[0], (float)ba.lo[1], (float)ba.lo[2], (float)ba.hi[0]);
+    out.nodes[4 * me + 1] = make_float4((float)ba.hi[1], (float)ba.hi[2], (float)bb.lo[0], (float)bb.lo[1]);
+    out.nodes[4 * me + 2] = make_float4((float)bb.lo[2], (float)bb.hi[0], (float)bb.hi[1], (float)bb.hi[2]);
+    float4 kids; memset(&kids, 0, sizeof kids);
+    memcpy(&kids.x, &ca, 4); memcpy(&kids.y, &cb, 4);
+    out.nodes[4 * me + 3] = kids;
+    return me;
+}
+
+// Which colliders go into the BVH: finite ones whose box is small against the extent of all collider centres
+// (a ground plane or a sky box would sit at the root and be tested by every ray anyway).
+static std::vector<char> bvh_membership(const std::vector<sp_collider>& cols, const std::vector<Aabb>& boxes) {
+    std::vector<char> in((size_t)cols.size(), 0);
+    if ((int)cols.size() < SP_BVH_MIN_COLLIDERS) return in;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    std::vector<double> diag(cols.size());
+    for (size_t i = 0; i < cols.size(); ++i) {
+        double d2 = 0;
+        for (int k = 0; k < 3; ++k) { const double e = boxes[i].hi[k] - boxes[i].lo[k]; d2 += e * e; }
+        diag[i] = std::sqrt(d2);
+    }
+    std::vector<double> sorted(diag);
+    std::nth_element(sorted.begin(), sorted.begin() + sorted.size() / 2, sorted.end());
+    const double typical = sorted[sorted.size() / 2];            // median collider size
+    for (size_t i = 0; i < cols.size(); ++i)
+        for (int k = 0; k < 3; ++k) {
+            const double c = 0.5 * (boxes[i].lo[k] + boxes[i].hi[k]);
+            if (diag[i] <= 64.0 * typical) { lo[k] = std::min(lo[k], c); hi[k] = std::max(hi[k], c); }
+        }
+    double extent = 0;
+    for (int k = 0; k < 3; ++k) extent = std::max(extent, hi[k] - lo[k]);
+    int n_in = 0;
+    for (size_t i = 0; i < cols.size(); ++i) {
+        in[i] = (diag[i] <= 0.25 * extent && std::isfinite(diag[i])) ? 1 : 0;
+        n_in += in[i];
+    }
+    if (n_in < SP_BVH_MIN_COLLIDERS / 2) std::fill(in.begin(), in.end(), 0);
+    return in;
+}
+
+static BuiltBvh build_bvh(const std::vector<sp_collider>& cols, const std::vector<char>& member, const std::vector<Aabb>& boxes,
+                          const std::vector<char>& casts_shadow) {
+    BuiltBvh out;
+    std::vector<int> order, item_of(cols.size(), 0);
+    for (size_t i = 0; i < cols.size(); ++i) {
+        if (!member[i]) continue;
+        order.push_back((int)i);
+        item_of[i] = stream_type(cols[i]) | (casts_shadow[i] ? 256 : 0);
+    }
+    if (order.empty()) return out;
+    Aabb root;
+    const int code = bvh_build_rec(out, order, 0, (int)order.size(), boxes, item_of, root);
+    if (code < 0) {                     // a single leaf: wrap it in a root whose second child is an empty box
+        out.nodes.assign(4, make_float4(0, 0, 0, 0));
+        out.nodes[0] = make_float4((float)root.lo[0], (float)root.lo[1], (float)root.lo[2], (float)root.hi[0]);
+        out.nodes[1] = make_float4((float)root.hi[1], (float)root.hi[2], 1.f, 1.f);
+        out.nodes[2] = make_float4(1.f, -1.f, -1.f, -1.f);
+        float4 kids; memset(&kids, 0, sizeof kids);
+        const int none = code;          // never visited: its box is inverted
+        memcpy(&kids.x, &code, 4); memcpy(&kids.y, &none, 4);
+        out.nodes[3] = kids;
+    }
+    for (auto& it : out.items) {        // packed collider data, in item order
+        const int st = it.x & 255;
+        it.y = (int)out.data.size();
+        std::vector<float> tmp((size_t)4 * type_vec4(st), 0.f);
+        pack_collider(cols[(size_t)it.z], st, tmp.data());
+        for (int v = 0; v < type_vec4(st); ++v) out.data.push_back(make_float4(tmp[4 * v], tmp[4 * v + 1], tmp[4 * v + 2], tmp[4 * v + 3]));
+    }
+    return out;
 }
 
 // =================================================================================================
@@ -718,12 +867,28 @@ int sp_scene_commit(sp_scene* s) {
     CUDA_TRY(s->d_media.upload(med));
 
     // ---- geometry streams -------------------------------------------------------------------------------
-    std::vector<int32_t> all_ids((size_t)n_col);
-    for (int i = 0; i < n_col; ++i) all_ids[i] = i;
-    BuiltStream all = build_stream(s->cols, all_ids), shadow = build_stream(s->cols, s->shadow_ids);
+    // large scenes: the small colliders go into a BVH, the streams keep the scene-sized ones
+    std::vector<Aabb> boxes((size_t)n_col);
+    for (int i = 0; i < n_col; ++i) boxes[i] = collider_aabb(s->cols[i]);
+    std::vector<char> in_bvh = bvh_membership(s->cols, boxes);
+    if (!s->opt_bvh) std::fill(in_bvh.begin(), in_bvh.end(), 0);     // option "bvh" = 0: exhaustive loop over staged chunks
+    std::vector<char> casts_shadow((size_t)n_col, 0);
+    for (int id : s->shadow_ids) casts_shadow[id] = 1;
+    const BuiltBvh bvh = build_bvh(s->cols, in_bvh, boxes, casts_shadow);
+    CUDA_TRY(s->bvh_nodes.upload(bvh.nodes));
+    CUDA_TRY(s->bvh_items.upload(bvh.items));
+    CUDA_TRY(s->bvh_data.upload(bvh.data));
+    d.bvh.nodes = s->bvh_nodes.p; d.bvh.items = s->bvh_items.p; d.bvh.data = s->bvh_data.p;
+    d.bvh.n_nodes = (int)bvh.nodes.size() / 4; d.bvh.n_items = (int)bvh.items.size();
+    d.n_shadow_casters = (int)s->shadow_ids.size();
+    std::vector<int32_t> all_ids, shadow_stream_ids;
+    for (int i = 0; i < n_col; ++i) if (!in_bvh[i]) all_ids.push_back(i);
+    for (int id : s->shadow_ids) if (!in_bvh[id]) shadow_stream_ids.push_back(id);
+    BuiltStream all = build_stream(s->cols, all_ids), shadow = build_stream(s->cols, shadow_stream_ids);
     for (int i = 0; i < n_col; ++i) {                    // (chunk, type << 28 | local) -> chunk << 24 | type << 20 | local
         const int2 w = all.slot[i];
-        dinfo[i].slot = ((uint32_t)w.x << 24) | (((uint32_t)w.y >> 28) << 20) | ((uint32_t)w.y & 0xFFFFFu);
+        dinfo[i].slot = w.x < 0 ? 0xFFFFFFFFu        // inside the BVH: recognised there by its collider id
+                                : ((uint32_t)w.x << 24) | (((uint32_t)w.y >> 28) << 20) | ((uint32_t)w.y & 0xFFFFFu);
     }
     if (all.chunk_off.size() - 1 > 255) return fail("too many geometry chunks");
     CUDA_TRY(s->d_colinfo.upload(dinfo));
@@ -781,6 +946,7 @@ int sp_scene_commit(sp_scene* s) {
         default: break;
         }
     }
+    if (d.bvh.n_nodes > 0) needed |= SP_F_BVH;
     s->material_set = sp_pick_material_set(needed);
     s->grid0 = sp_level_grid(g_device, s->d, s->material_set, true);
     s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false);
@@ -1119,6 +1285,10 @@ int sp_set_option(sp_scene* s, const char* name, int64_t value) {
     else if (!strcmp(name, "fan_queue_capacity")) s->opt_fan_cap = value;
     else if (!strcmp(name, "chunk_primaries")) s->opt_chunk = value;
     else if (!strcmp(name, "max_levels")) s->opt_max_levels = value;
+    else if (!strcmp(name, "bvh")) {
+        s->opt_bvh = value;
+        if (s->committed) return sp_scene_commit(s);             // the geometry tables depend on it
+    }
     else return fail("sp_set_option: unknown option '%s'", name);
     s->use_ray = s->use_fan = 0.0;
     return 0;

@@ -28,123 +28,198 @@ struct SelfSlot { int sphere, plane, cuboid, tri, aa; uint32_t mode; };
 
 struct ChunkBest { float t; int idx; int orient; };   // idx = position in the chunk's id array
 
-// One axis-aligned rectangle section: normal along axis A (0, 1, 2), in-plane axes B < C.
+// ---- one collider against one ray --------------------------------------------------------------------
+// `tag` is what a winning test leaves in best.idx (position in the chunk's id array, or the collider id for
+// BVH leaves); `is_self` marks the collider the ray starts on (see the header comment).
+SP_DEV void sp_item_sphere(float4 s, float3 O, float3 D, bool is_self, uint32_t mode, int tag, ChunkBest& best) {
+    float3 oc = O - xyz(s);
+    float b = dot(D, oc);
+    float3 q = fma3(D, -b, oc);
+    float disc = s.w - dot(q, q);
+    if (disc > 0.f) {
+        float sq = fast_sqrt(disc);
+        float h0 = -b - sq, h1 = -b + sq;
+        bool near_ok = (h0 > 0.f) && !is_self;             // SP_SELF_FAR: only the far root
+        float t = near_ok ? h0 : h1;
+        bool ok = (t > 0.f) && !(is_self && mode != SP_SELF_FAR);
+        if (ok && t < best.t) { best.t = t; best.idx = tag; best.orient = near_ok ? 1 : -1; }
+    }
+}
+
+SP_DEV void sp_item_plane(float4 a, float4 c, float4 u4, float4 v4, float3 O, float3 D, bool is_self, int tag,
+                          ChunkBest& best) {
+    float3 N = xyz(a), oc = O - xyz(c);
+    float nd = dot(N, D);
+    nd = (nd == 0.f) ? 1e-4f : nd;
+    float k = -dot(N, oc);
+    float t = __fdividef(k, nd);
+    float u = fmaf(t, dot(xyz(u4), D), dot(xyz(u4), oc));
+    float v = fmaf(t, dot(xyz(v4), D), dot(xyz(v4), oc));
+    bool ok = (fabsf(u) <= a.w) && (fabsf(v) <= c.w) && (k * nd > 0.f) && !is_self;
+    if (ok && t < best.t) { best.t = t; best.idx = tag; best.orient = nd < 0.f ? 1 : -1; }
+}
+
+SP_DEV void sp_item_cuboid(float4 r0, float4 r1, float4 r2, float4 c, float4 e, float3 O, float3 D, bool is_self,
+                           uint32_t mode, int tag, ChunkBest& best) {
+    float3 oc = O - xyz(c);
+    float3 Ol = v3(dot(xyz(r0), oc), dot(xyz(r1), oc), dot(xyz(r2), oc));
+    float3 Dl = v3(dot(xyz(r0), D), dot(xyz(r1), D), dot(xyz(r2), D));
+    float ix = fast_rcp(Dl.x), iy = fast_rcp(Dl.y), iz = fast_rcp(Dl.z);   // +-inf for axis-parallel rays, as 1/0
+    float t1 = (r0.w - Ol.x) * ix, t2 = (c.w - Ol.x) * ix;
+    float t3 = (r1.w - Ol.y) * iy, t4 = (e.x - Ol.y) * iy;
+    float t5 = (r2.w - Ol.z) * iz, t6 = (e.y - Ol.z) * iz;
+    float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+    float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+    bool miss = (tmax < 0.f) || (tmin > tmax);
+    bool inside = (tmin < 0.f) || is_self;                 // SP_SELF_FAR: exit point only
+    float t = inside ? tmax : tmin;
+    bool ok = !miss && !(is_self && mode != SP_SELF_FAR);
+    if (ok && t < best.t) { best.t = t; best.idx = tag; best.orient = inside ? -1 : 1; }
+}
+
+// triangle.py:37-66 through the affine map to the unit triangle: the three edge tests
+// n31.(M-p1) >= 0, n12.(M-p2) >= 0, n23.(M-p3) >= 0 are u >= 0, v >= 0, 1-u-v >= 0 of the hit point's
+// barycentric coordinates, and the third row of the map is the plane normal (N.D, N.(O-p1)).
+SP_DEV void sp_item_triangle(float4 m0, float4 m1, float4 m2, float3 O, float3 D, bool is_self, int tag, ChunkBest& best) {
+    float nd = dot(xyz(m2), D);
+    nd = (nd == 0.f) ? 1e-4f : nd;
+    const float w0 = dot(xyz(m2), O) + m2.w;                 // N.(O - p1) = -k
+    const float t = -w0 * fast_rcp(nd);
+    const float u = fmaf(t, dot(xyz(m0), D), dot(xyz(m0), O) + m0.w);
+    const float v = fmaf(t, dot(xyz(m1), D), dot(xyz(m1), O) + m1.w);
+    const bool ok = (u >= 0.f) && (v >= 0.f) && (u + v <= 1.f) && (t > 0.f) && !is_self;
+    if (ok && t < best.t) { best.t = t; best.idx = tag; best.orient = nd < 0.f ? 1 : -1; }
+}
+
+// Axis-aligned rectangle, normal along axis A (0, 1, 2), in-plane axes B < C.  1/0 = inf sends the hit point of
+// an axis-parallel ray out of bounds (the reference substitutes N.D = 1e-4 there and misses all the same).
 template <int A>
-SP_DEV void sp_intersect_aa(const float4* __restrict__ aa, int first, int count, int id_base, float3 O, float3 D,
-                            float inv_da, int self_aa, ChunkBest& best) {
+SP_DEV void sp_item_aa(float4 r0, float4 r1, float3 O, float3 D, float inv_da, bool is_self, int tag, ChunkBest& best) {
     const float oa = A == 0 ? O.x : (A == 1 ? O.y : O.z), da = A == 0 ? D.x : (A == 1 ? D.y : D.z);
     const float ob = A == 0 ? O.y : O.x, db = A == 0 ? D.y : D.x;
     const float oc = A == 2 ? O.y : O.z, dc = A == 2 ? D.y : D.z;
+    const float ca = A == 0 ? r0.x : (A == 1 ? r0.y : r0.z);
+    const float cb = A == 0 ? r0.y : r0.x, cc = A == 2 ? r0.y : r0.z;
+    const float t = (ca - oa) * inv_da;                        // k / N.D with the normal's sign cancelled
+    const float pb = fmaf(t, db, ob) - cb, pc = fmaf(t, dc, oc) - cc;
+    const bool ok = (fabsf(pb) <= r1.x) && (fabsf(pc) <= r1.y) && (t > 0.f) && !is_self;
+    if (ok && t < best.t) { best.t = t; best.idx = tag; best.orient = (r0.w * da < 0.f) ? 1 : -1; }
+}
+
+template <int A>
+SP_DEV void sp_intersect_aa(const float4* __restrict__ aa, int first, int count, int id_base, float3 O, float3 D,
+                            float inv_da, int self_aa, ChunkBest& best) {
 #pragma unroll 2
-    for (int i = first; i < first + count; ++i) {
-        const float4 r0 = aa[2 * i], r1 = aa[2 * i + 1];
-        const float ca = A == 0 ? r0.x : (A == 1 ? r0.y : r0.z);
-        const float cb = A == 0 ? r0.y : r0.x, cc = A == 2 ? r0.y : r0.z;
-        const float t = (ca - oa) * inv_da;                        // k / N.D with the normal's sign cancelled
-        const float pb = fmaf(t, db, ob) - cb, pc = fmaf(t, dc, oc) - cc;
-        const bool ok = (fabsf(pb) <= r1.x) && (fabsf(pc) <= r1.y) && (t > 0.f) && (i != self_aa);
-        if (ok && t < best.t) { best.t = t; best.idx = id_base + i; best.orient = (r0.w * da < 0.f) ? 1 : -1; }
-    }
+    for (int i = first; i < first + count; ++i)
+        sp_item_aa<A>(aa[2 * i], aa[2 * i + 1], O, D, inv_da, i == self_aa, id_base + i, best);
 }
 
 SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D, SelfSlot self,
                                ChunkBest& best) {
     const GeomChunkHeader* h = reinterpret_cast<const GeomChunkHeader*>(ch);
     const int n_sphere = h->n_sphere, n_plane = h->n_plane, n_cuboid = h->n_cuboid, n_tri = h->n_tri;
-
-    // ---- spheres ---------------------------------------------------------------------------
     {
         const float4* sp = ch + h->off_sphere;
 #pragma unroll 4
-        for (int i = 0; i < n_sphere; ++i) {
-            float4 s = sp[i];
-            float3 oc = O - xyz(s);
-            float b = dot(D, oc);
-            float3 q = fma3(D, -b, oc);
-            float disc = s.w - dot(q, q);
-            if (disc > 0.f) {
-                float sq = fast_sqrt(disc);
-                float h0 = -b - sq, h1 = -b + sq;
-                bool is_self = (i == self.sphere);
-                bool near_ok = (h0 > 0.f) && !is_self;             // SP_SELF_FAR: only the far root
-                float t = near_ok ? h0 : h1;
-                bool ok = (t > 0.f) && !(is_self && self.mode != SP_SELF_FAR);
-                if (ok && t < best.t) { best.t = t; best.idx = i; best.orient = near_ok ? 1 : -1; }
-            }
-        }
+        for (int i = 0; i < n_sphere; ++i) sp_item_sphere(sp[i], O, D, i == self.sphere, self.mode, i, best);
     }
-    // ---- bounded planes ------------------------------------------------------------------------
     {
         const float4* pl = ch + h->off_plane;
 #pragma unroll 2
-        for (int i = 0; i < n_plane; ++i) {
-            float4 a = pl[4 * i], c = pl[4 * i + 1], u4 = pl[4 * i + 2], v4 = pl[4 * i + 3];
-            float3 N = xyz(a), oc = O - xyz(c);
-            float nd = dot(N, D);
-            nd = (nd == 0.f) ? 1e-4f : nd;
-            float k = -dot(N, oc);
-            float t = __fdividef(k, nd);
-            float u = fmaf(t, dot(xyz(u4), D), dot(xyz(u4), oc));
-            float v = fmaf(t, dot(xyz(v4), D), dot(xyz(v4), oc));
-            bool ok = (fabsf(u) <= a.w) && (fabsf(v) <= c.w) && (k * nd > 0.f) && (i != self.plane);
-            if (ok && t < best.t) { best.t = t; best.idx = n_sphere + i; best.orient = nd < 0.f ? 1 : -1; }
-        }
+        for (int i = 0; i < n_plane; ++i)
+            sp_item_plane(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3], O, D, i == self.plane, n_sphere + i, best);
     }
-    // ---- oriented cuboids ------------------------------------------------------------------------
     {
         const float4* cb = ch + h->off_cuboid;
-        for (int i = 0; i < n_cuboid; ++i) {
-            float4 r0 = cb[5 * i], r1 = cb[5 * i + 1], r2 = cb[5 * i + 2], c = cb[5 * i + 3], e = cb[5 * i + 4];
-            float3 oc = O - xyz(c);
-            float3 Ol = v3(dot(xyz(r0), oc), dot(xyz(r1), oc), dot(xyz(r2), oc));
-            float3 Dl = v3(dot(xyz(r0), D), dot(xyz(r1), D), dot(xyz(r2), D));
-            float ix = fast_rcp(Dl.x), iy = fast_rcp(Dl.y), iz = fast_rcp(Dl.z);   // +-inf for axis-parallel rays, as 1/0
-            float t1 = (r0.w - Ol.x) * ix, t2 = (c.w - Ol.x) * ix;
-            float t3 = (r1.w - Ol.y) * iy, t4 = (e.x - Ol.y) * iy;
-            float t5 = (r2.w - Ol.z) * iz, t6 = (e.y - Ol.z) * iz;
-            float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
-            float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
-            bool is_self = (i == self.cuboid);
-            bool miss = (tmax < 0.f) || (tmin > tmax);
-            bool inside = (tmin < 0.f) || is_self;                 // SP_SELF_FAR: exit point only
-            float t = inside ? tmax : tmin;
-            bool ok = !miss && !(is_self && self.mode != SP_SELF_FAR);
-            if (ok && t < best.t) { best.t = t; best.idx = n_sphere + n_plane + i; best.orient = inside ? -1 : 1; }
-        }
+        for (int i = 0; i < n_cuboid; ++i)
+            sp_item_cuboid(cb[5 * i], cb[5 * i + 1], cb[5 * i + 2], cb[5 * i + 3], cb[5 * i + 4], O, D, i == self.cuboid,
+                           self.mode, n_sphere + n_plane + i, best);
     }
-    // ---- triangles -----------------------------------------------------------------------------
-    // triangle.py:37-66 through the affine map to the unit triangle: the three edge tests
-    // n31.(M-p1) >= 0, n12.(M-p2) >= 0, n23.(M-p3) >= 0 are u >= 0, v >= 0, 1-u-v >= 0 of the hit point's
-    // barycentric coordinates, and the third row of the map is the plane normal (N.D, N.(O-p1)).
     {
         const float4* tr = ch + h->off_tri;
 #pragma unroll 2
-        for (int i = 0; i < n_tri; ++i) {
-            const float4 m0 = tr[3 * i], m1 = tr[3 * i + 1], m2 = tr[3 * i + 2];
-            float nd = dot(xyz(m2), D);
-            nd = (nd == 0.f) ? 1e-4f : nd;
-            const float w0 = dot(xyz(m2), O) + m2.w;                 // N.(O - p1) = -k
-            const float t = -w0 * fast_rcp(nd);
-            const float u = fmaf(t, dot(xyz(m0), D), dot(xyz(m0), O) + m0.w);
-            const float v = fmaf(t, dot(xyz(m1), D), dot(xyz(m1), O) + m1.w);
-            const bool ok = (u >= 0.f) && (v >= 0.f) && (u + v <= 1.f) && (t > 0.f) && (i != self.tri);
-            if (ok && t < best.t) {
-                best.t = t; best.idx = n_sphere + n_plane + n_cuboid + i; best.orient = nd < 0.f ? 1 : -1;
-            }
-        }
+        for (int i = 0; i < n_tri; ++i)
+            sp_item_triangle(tr[3 * i], tr[3 * i + 1], tr[3 * i + 2], O, D, i == self.tri, n_sphere + n_plane + n_cuboid + i, best);
     }
-    // ---- axis-aligned rectangles -----------------------------------------------------------------
     {
         const int n_aax = h->n_aax, n_aay = h->n_aay, n_aaz = h->n_aaz;
         if (n_aax + n_aay + n_aaz > 0) {
             const float4* aa = ch + h->off_aa;
             const int id_base = n_sphere + n_plane + n_cuboid + n_tri;
-            // 1/0 = inf sends the hit point of an axis-parallel ray out of bounds (the reference
-            // substitutes N.D = 1e-4 there and misses all the same)
             if (n_aax > 0) sp_intersect_aa<0>(aa, 0, n_aax, id_base, O, D, fast_rcp(D.x), self.aa, best);
             if (n_aay > 0) sp_intersect_aa<1>(aa, n_aax, n_aay, id_base, O, D, fast_rcp(D.y), self.aa, best);
             if (n_aaz > 0) sp_intersect_aa<2>(aa, n_aax + n_aay, n_aaz, id_base, O, D, fast_rcp(D.z), self.aa, best);
         }
+    }
+}
+
+// ---- bounding-volume hierarchy over the small colliders of a large scene ---------------------------------
+// An acceleration structure (the reference itself notes that meshes need one,
+// triangle_mesh.py:7-9), used when a scene has SP_BVH_MIN_COLLIDERS colliders or more: with it a ray no longer
+// tests every collider, so the bound of such scenes is memory latency / divergence, not FMA throughput.
+// The colliders a ray does reach go through the very same sp_item_* tests, and the boxes are conservative,
+// so hits are those of the exhaustive loop.  Colliders that span a large part of the scene (ground planes,
+// sky boxes) stay in the staged chunk and are tested by every ray.
+//   node  (4 float4): child 0 box (lo.xyz, hi.x | hi.yz) child 1 box (lo.xy | lo.z, hi.xyz), children (int, int)
+//                     child >= 0: node index; child < 0: leaf, ~child = first item << 3 | (count - 1)
+//   item  (int4)    : stream type | casts shadow << 8, float4 offset of its packed data, collider id, -
+
+SP_DEV bool sp_box_hit(float3 lo, float3 hi, float3 O, float3 inv, float t_max, float& t_near) {
+    const float tx1 = (lo.x - O.x) * inv.x, tx2 = (hi.x - O.x) * inv.x;
+    const float ty1 = (lo.y - O.y) * inv.y, ty2 = (hi.y - O.y) * inv.y;
+    const float tz1 = (lo.z - O.z) * inv.z, tz2 = (hi.z - O.z) * inv.z;
+    t_near = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fmaxf(fminf(tz1, tz2), 0.f));
+    const float t_far = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fminf(fmaxf(tz1, tz2), t_max));
+    return t_near <= t_far;                    // NaN (0 * inf on a slab boundary) compares false: handled by the box inflation
+}
+
+// Nearest hit among the BVH's colliders closer than best.t.  casters_only: shadow rays (glossy.py:53-57) look at
+// shadow-casting colliders only and may stop at the first hit closer than t_any.
+SP_DEV void sp_bvh_nearest(const DBvh& bvh, float3 O, float3 D, int src_id, uint32_t mode, bool casters_only, float t_any,
+                           ChunkBest& best) {
+    if (bvh.n_nodes == 0) return;
+    const float3 inv = v3(fast_rcp(D.x), fast_rcp(D.y), fast_rcp(D.z));
+    int stack[32];
+    int sp = 0, node = 0;
+    while (true) {
+        const float4 n0 = __ldg(bvh.nodes + 4 * node), n1 = __ldg(bvh.nodes + 4 * node + 1);
+        const float4 n2 = __ldg(bvh.nodes + 4 * node + 2), n3 = __ldg(bvh.nodes + 4 * node + 3);
+        float ta, tb;
+        const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), O, inv, best.t, ta);
+        const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), O, inv, best.t, tb);
+        int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
+        if (ha && hb && tb < ta) { const int c = ca; ca = cb; cb = c; }      // nearer child first
+        int next = -1;                                                      // inner node to descend into
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const bool h = k == 0 ? (ha || hb) : (ha && hb);
+            const int c = k == 0 ? (ha ? ca : cb) : cb;
+            if (!h) continue;
+            if (c >= 0) {
+                if (next < 0) next = c; else stack[sp++] = c;
+            } else {                                                        // leaf
+                const int code = ~c, first = code >> 3, count = (code & 7) + 1;
+                for (int i = first; i < first + count; ++i) {
+                    const int4 it = __ldg(bvh.items + i);
+                    if (casters_only && !(it.x & 256)) continue;
+                    const float4* d = bvh.data + it.y;
+                    const bool is_self = it.z == src_id;
+                    switch (it.x & 255) {
+                    case SP_ST_SPHERE: sp_item_sphere(__ldg(d), O, D, is_self, mode, it.z, best); break;
+                    case SP_ST_PLANE: sp_item_plane(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), O, D, is_self, it.z, best); break;
+                    case SP_ST_CUBOID: sp_item_cuboid(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), __ldg(d + 4), O, D, is_self, mode, it.z, best); break;
+                    case SP_ST_TRI: sp_item_triangle(__ldg(d), __ldg(d + 1), __ldg(d + 2), O, D, is_self, it.z, best); break;
+                    case SP_ST_AAX: sp_item_aa<0>(__ldg(d), __ldg(d + 1), O, D, inv.x, is_self, it.z, best); break;
+                    case SP_ST_AAY: sp_item_aa<1>(__ldg(d), __ldg(d + 1), O, D, inv.y, is_self, it.z, best); break;
+                    default: sp_item_aa<2>(__ldg(d), __ldg(d + 1), O, D, inv.z, is_self, it.z, best); break;
+                    }
+                }
+                if (best.t < t_any) return;
+            }
+        }
+        if (next >= 0) { node = next; continue; }
+        if (sp == 0) return;
+        node = stack[--sp];
     }
 }
 

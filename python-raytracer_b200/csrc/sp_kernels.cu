@@ -31,7 +31,7 @@
 #ifndef SP_CTAS_FULL
 #define SP_CTAS_FULL 3
 #endif
-#define SP_CTAS_PER_SM(FEAT) ((((FEAT) & (SP_F_TEX | SP_F_GLOSSY | SP_F_THIN | SP_F_SKY)) == 0u) ? SP_CTAS_MC : SP_CTAS_FULL)
+#define SP_CTAS_PER_SM(FEAT) ((((FEAT) & (SP_F_TEX | SP_F_GLOSSY | SP_F_THIN | SP_F_SKY | SP_F_BVH)) == 0u) ? SP_CTAS_MC : SP_CTAS_FULL)
 
 SP_DEV void sp_stage_chunk(float4* __restrict__ dst, const DScene& sc, const GeomStream& gs, int c) {
     const int lo = __ldg(gs.chunk_off + c), hi = __ldg(gs.chunk_off + c + 1);
@@ -249,6 +249,11 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                     sp_intersect_chunk(s_geom, r.o, r.d, self, best);
                     if (best.idx >= 0) { hit.t = best.t; hit.orient = best.orient; hit.id = sp_chunk_id(s_geom, best.idx); }
                 }
+            }
+            if ((FEAT & SP_F_BVH) && need_test) {
+                ChunkBest best; best.t = hit.t; best.idx = -1; best.orient = 0;
+                sp_bvh_nearest(sc.bvh, r.o, r.d, src == SP_SRC_NONE ? -1 : (int)src, mode, false, -SP_INF, best);
+                if (best.idx >= 0) { hit.t = best.t; hit.orient = best.orient; hit.id = best.idx; }
             }
         }
         if (active) {
@@ -482,12 +487,13 @@ static size_t geom_smem_bytes(const DScene& sc) { return (size_t)sc.all.max_chun
 #define SP_SET_MC      (SP_F_DIFFUSE | SP_F_REFR)                                        /* Cornell box */
 #define SP_SET_WHITTED (SP_F_TEX | SP_F_GLOSSY | SP_F_REFR | SP_F_THIN | SP_F_SKY)       /* examples 1-4 */
 #define SP_SET_ALL     (SP_F_MATERIALS)
-static const uint32_t kMaterialSets[] = {SP_SET_MC, SP_SET_WHITTED, SP_SET_ALL};
+#define SP_SET_ALL_BVH (SP_F_MATERIALS | SP_F_BVH)                                        /* many colliders */
+static const uint32_t kMaterialSets[] = {SP_SET_MC, SP_SET_WHITTED, SP_SET_ALL, SP_SET_ALL_BVH};
 
 uint32_t sp_pick_material_set(uint32_t needed) {
     for (uint32_t set : kMaterialSets)
         if ((needed & ~set) == 0u) return set;
-    return SP_SET_ALL;
+    return SP_SET_ALL_BVH;
 }
 
 typedef void (*LevelKernel)(const DScene, const LevelArgs);
@@ -495,6 +501,7 @@ static LevelKernel level_kernel(uint32_t material_set, bool level0) {
     switch (material_set) {
     case SP_SET_MC: return level0 ? sp_level_kernel<SP_SET_MC | SP_F_LEVEL0> : sp_level_kernel<SP_SET_MC | SP_F_QUEUES>;
     case SP_SET_WHITTED: return level0 ? sp_level_kernel<SP_SET_WHITTED | SP_F_LEVEL0> : sp_level_kernel<SP_SET_WHITTED | SP_F_QUEUES>;
+    case SP_SET_ALL_BVH: return level0 ? sp_level_kernel<SP_SET_ALL_BVH | SP_F_LEVEL0> : sp_level_kernel<SP_SET_ALL_BVH | SP_F_QUEUES>;
     default: return level0 ? sp_level_kernel<SP_SET_ALL | SP_F_LEVEL0> : sp_level_kernel<SP_SET_ALL | SP_F_QUEUES>;
     }
 }

@@ -151,7 +151,8 @@ SP_DEV float3 sp_f0(float3 re1, float3 im1, float3 re2, float3 im2) {
 
 // Nearest shadow-caster distance from `o` along `d` (glossy.py:53-57); walks the shadow stream
 // straight from global memory / L1 (uniform addresses across the warp).
-SP_DEV float sp_shadow_nearest(const DScene& sc, float3 o, float3 d, int src_id, uint32_t mode,
+template <uint32_t FEAT>
+SP_DEV float sp_shadow_nearest(const DScene& sc, float3 o, float3 d, int src_id, uint32_t mode, float dist,
                                const int2* __restrict__ shadow_slot) {
     ChunkBest best; best.t = SP_INF; best.idx = -1; best.orient = 0;
     int2 where = (src_id >= 0 && shadow_slot) ? __ldg(shadow_slot + src_id) : make_int2(-1, -1);
@@ -165,6 +166,7 @@ SP_DEV float sp_shadow_nearest(const DScene& sc, float3 o, float3 d, int src_id,
         }
         sp_intersect_chunk(ch, o, d, self, best);
     }
+    if ((FEAT & SP_F_BVH) && best.t >= dist) sp_bvh_nearest(sc.bvh, o, d, src_id, mode, true, dist, best);
     return best.t;
 }
 
@@ -274,10 +276,10 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
             }
             if (NdotL <= 0.f) continue;                // lv == 0: both light terms vanish
             float see = 1.f;
-            if (sc.shadow.n_items > 0) {
+            if (sc.n_shadow_casters > 0) {
                 uint32_t mode = sp_self_mode(ctype, side_plus, dot(L, g.Nc), zo);
                 float nearest = (mode == SP_SELF_ZERO) ? 0.f
-                                : sp_shadow_nearest(sc, nudged, L, h.id, mode, cx_.shadow_slot);
+                                : sp_shadow_nearest<FEAT>(sc, nudged, L, h.id, mode, dist, cx_.shadow_slot);
                 see = nearest >= dist ? 1.f : 0.f;
                 cx_.shadow_rays++;
             }

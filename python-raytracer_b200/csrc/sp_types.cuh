@@ -24,6 +24,7 @@
 #define SP_V4_CUBOID 5
 #define SP_V4_TRIANGLE 3
 #define SP_V4_AARECT 2
+#define SP_BVH_MIN_COLLIDERS 64      // smaller scenes are looped exhaustively
 // stream type codes (order of the sections and of the id array inside a chunk)
 enum { SP_ST_SPHERE = 0, SP_ST_PLANE = 1, SP_ST_CUBOID = 2, SP_ST_TRI = 3, SP_ST_AAX = 4, SP_ST_AAY = 5, SP_ST_AAZ = 6 };
 
@@ -84,6 +85,14 @@ struct DLight { int kind; float3 vec; float3 color; };
 struct DImportance { float3 center; float radius; };
 struct DMedium { float3 re, im, absorb; };   // absorb = 2*Im(n)*2*pi/lambda*1e9  (refractive.py:113-121)
 
+// bounding-volume hierarchy over the small colliders of a large scene (layout: sp_geometry.cuh)
+struct DBvh {
+    const float4* nodes;
+    const int4* items;
+    const float4* data;
+    int n_nodes, n_items;
+};
+
 struct DCamera {
     float3 look_from, right, up, fwd;
     float cam_w, cam_h, lens_radius, focal_distance;
@@ -96,6 +105,7 @@ struct DCamera {
 
 struct DScene {
     GeomStream all, shadow;
+    DBvh bvh;                          // n_nodes == 0: every collider is in the streams
     const DCollider* colliders;
     const DColInfo* col_info;
     const double* colliders_d;     // [n][44] double payloads for the precise hit path
@@ -108,6 +118,7 @@ struct DScene {
     DCamera cam;
     float3 ambient;
     int n_lights, n_importance, n_colliders, n_fan_classes;
+    int n_shadow_casters;              // colliders of shadow-casting primitives (stream + BVH)
     float inv_n_importance;
     unsigned long long fan_magic[SP_MAX_FAN_CLASSES];   // ceil(2^64 / fan_mult): n / mult == __umul64hi(n, magic) for n < 2^32
     int fan_mult[SP_MAX_FAN_CLASSES];     // rays per fan record of each class (class 0: 1)
@@ -127,6 +138,7 @@ enum : uint32_t {
     SP_F_SKY = 32u,       // SkyBox / Panorama materials
     SP_F_LEVEL0 = 64u,    // sources of a level-0 launch (camera, caller rays) and its per-ray outputs
     SP_F_QUEUES = 128u,   // source of a level >= 1 launch
+    SP_F_BVH = 256u,      // scenes with many colliders: BVH traversal after the staged chunk
     SP_F_MATERIALS = 63u,
 };
 

@@ -469,3 +469,32 @@ def test_rendered_examples_match_the_reference_images(name, spp, ref_db):
     psnr = 10 * np.log10(255.0 ** 2 / np.mean((got - want) ** 2))
     print(f"{name}: PSNR vs the reference's shipped image {psnr:.2f} dB (reference vs itself: {ref_db} dB)")
     assert psnr >= 37.0 and psnr >= ref_db - 2.5
+
+
+def test_bvh_and_exhaustive_loop_agree():
+    """Scenes with >= 64 colliders put their small colliders into a BVH; with option "bvh" = 0 the
+    same scene is traced by the exhaustive multi-chunk loop.  Both must find the same hits (the boxes are
+    conservative and the per-collider tests are the same functions), and the exhaustive path must still agree
+    with the oracle (it is what the smaller scenes run)."""
+    import scenes
+    import sightpy
+    from sightpy.backend import NativeScene
+    scene = scenes.stress(sightpy, width=32, height=24, n_spheres=400, n_triangles=160, n_collections=2)
+    flat = flatten_scene(scene)
+    nat = NativeScene(flat)
+    o, d = nat.camera_rays(sample=0, seed=3)
+    with_bvh = nat.trace(o, d, seed=3)
+    nat.set_option("bvh", 0)
+    brute = nat.trace(o, d, seed=3)
+    nat.close()
+    assert np.mean(with_bvh["hit_id"] != brute["hit_id"]) < 0.002
+    same = with_bvh["hit_id"] == brute["hit_id"]
+    np.testing.assert_allclose(with_bvh["t"][same], brute["t"][same], rtol=1e-5, atol=1e-5)
+    err = np.abs(with_bvh["rgb"] - brute["rgb"]).max(axis=1)[same]
+    assert np.mean(err > 1e-3) < 0.01
+    assert abs(with_bvh["stats"]["rays_total"] - brute["stats"]["rays_total"]) <= 0.001 * brute["stats"]["rays_total"]
+    want = Oracle(flat, rng="philox", seed=3).trace(o, d)
+    ok = brute["hit_id"] == want["hit_id"]
+    assert np.mean(~ok) < 0.003
+    e2 = np.abs(brute["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[ok]
+    assert float(np.mean(e2 > RGB_TOL * (1.0 + np.abs(want["rgb"]).max(axis=1)[ok]))) < 0.03
