@@ -498,3 +498,53 @@ def test_bvh_and_exhaustive_loop_agree():
     assert np.mean(~ok) < 0.003
     e2 = np.abs(brute["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[ok]
     assert float(np.mean(e2 > RGB_TOL * (1.0 + np.abs(want["rgb"]).max(axis=1)[ok]))) < 0.03
+
+
+def test_triangle_mesh_from_obj_matches_oracle(tmp_path):
+    """TriangleMesh (broken upstream, triangle_mesh.py:40) loads a Wavefront OBJ; 320 triangles + floor + light
+    run through the BVH and must agree with the oracle, which loops over every triangle."""
+    import sightpy as sp
+    from sightpy.backend import NativeScene
+    # a UV sphere written as OBJ
+    n_lat, n_lon = 10, 16
+    verts = [(0.0, 1.0, 0.0)]
+    for i in range(1, n_lat):
+        th = np.pi * i / n_lat
+        for j in range(n_lon):
+            ph = 2 * np.pi * j / n_lon
+            verts.append((np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)))
+    verts.append((0.0, -1.0, 0.0))
+    faces = []
+    ring = lambda i, j: 1 + (i - 1) * n_lon + (j % n_lon)
+    for j in range(n_lon):
+        faces.append((0, ring(1, j + 1), ring(1, j)))
+        faces.append((len(verts) - 1, ring(n_lat - 1, j), ring(n_lat - 1, j + 1)))
+    for i in range(1, n_lat - 1):
+        for j in range(n_lon):
+            faces.append((ring(i, j), ring(i, j + 1), ring(i + 1, j)))
+            faces.append((ring(i, j + 1), ring(i + 1, j + 1), ring(i + 1, j)))
+    obj = tmp_path / "ball.obj"
+    obj.write_text("".join(f"v {x:.6f} {y:.6f} {z:.6f}\n" for x, y, z in verts)
+                   + "".join(f"f {a + 1} {b + 1} {c + 1}\n" for a, b, c in faces))
+    v, rgb = sp.vec3, sp.rgb
+    sc = sp.Scene(ambient_color=rgb(0.03, 0.03, 0.03))
+    sc.add_Camera(look_from=v(0.0, 1.0, 4.0), look_at=v(0.0, 0.3, 0.0), screen_width=48, screen_height=36, field_of_view=50)
+    sc.add_DirectionalLight(Ldir=v(0.4, 0.8, 0.5), color=rgb(0.7, 0.7, 0.7))
+    sc.add(sp.TriangleMesh(str(obj), center=v(0.0, 0.6, 0.0),
+                           material=sp.Glossy(diff_color=rgb(0.8, 0.5, 0.2), n=v(1.5 + 0.3j, 1.5 + 0.3j, 1.5 + 0.3j), roughness=0.3,
+                                              spec_coeff=0.4, diff_coeff=0.7), max_ray_depth=2))
+    sc.add(sp.Plane(material=sp.Diffuse(diff_color=rgb(0.6, 0.6, 0.6), diffuse_rays=4), center=v(0, -0.5, 0), width=10.0, height=10.0,
+                    u_axis=v(1.0, 0, 0), v_axis=v(0, 0, -1.0)))
+    sc.add(sp.Sphere(material=sp.Emissive(color=rgb(5.0, 5.0, 5.0)), center=v(-2.0, 2.5, 1.0), radius=0.5), importance_sampled=True)
+    flat = flatten_scene(sc)
+    assert len(flat.colliders) == len(faces) + 2 and len(faces) == 288
+    nat = NativeScene(flat)
+    o, d = nat.camera_rays(sample=0, seed=4)
+    out = nat.trace(o, d, seed=4)
+    nat.close()
+    want = Oracle(flat, rng="philox", seed=4).trace(o, d)
+    assert np.mean(out["hit_id"] != want["hit_id"]) < 0.01          # shared edges of a closed mesh are exact ties
+    same = out["hit_id"] == want["hit_id"]
+    err = np.abs(out["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[same]
+    assert float(np.mean(err > RGB_TOL * (1.0 + np.abs(want["rgb"]).max(axis=1)[same]))) < 0.03
+    assert abs(out["rgb"].mean() - want["rgb"].mean()) < 0.03 * want["rgb"].mean()
