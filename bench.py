@@ -303,8 +303,10 @@ def run_native(args, emit=print):
         "peak_source": "FFMA chain micro-benchmark run by this process (sp_measure_peaks); MEASURED_PEAKS.json has no FP32 entry",
         "flop_per_ray": FLOP_PER_RAY_CORNELL, "rays_per_launch": totals["rays"] / n_launch,
         "avg_launch_ms": totals["level_ms"] / n_launch, "traffic": None,
-        "note": "fused generate+intersect+shade kernel: issue-bound on FP32/ALU/LSU work, neither HBM nor tensor; "
-                "ncu pipe utilisation in profiles/",
+        "note": "fused generate+intersect+shade kernel: neither HBM- nor tensor-bound; the binding resource is "
+                "instruction issue (ncu, profiles/r1_v13_level_kernel.md: 0.62-0.66 of 1.0 instructions per scheduler "
+                "per cycle, pipes FMA 20 % / ALU 43 % / MUFU 18 % / LSU 24 %, ~1700 warp instructions per 32 rays of "
+                "which the 8 collider tests are ~350)",
     }
     roofline_hbm = {
         "bound": "hbm", "kernel": "sp_level_kernel (queue records only)",
