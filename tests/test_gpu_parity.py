@@ -548,3 +548,28 @@ def test_triangle_mesh_from_obj_matches_oracle(tmp_path):
     err = np.abs(out["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[same]
     assert float(np.mean(err > RGB_TOL * (1.0 + np.abs(want["rgb"]).max(axis=1)[same]))) < 0.03
     assert abs(out["rgb"].mean() - want["rgb"].mean()) < 0.03 * want["rgb"].mean()
+
+
+def test_tiny_and_ragged_sizes():
+    """Edge sizes: 1x1 and 3x2 frames, a single caller ray, zero caller rays, chunks smaller than a CTA batch."""
+    import scenes
+    import sightpy
+    from sightpy.backend import NativeScene
+    for w, h in ((1, 1), (3, 2), (33, 7)):
+        flat = flatten_scene(scenes.cornell(sightpy, width=w, height=h))
+        nat = NativeScene(flat)
+        nat.set_option("chunk_primaries", 1024)
+        srgb, lin, st = nat.render(5, seed=2)
+        assert srgb.shape == (h, w, 3) and st["rays_per_depth"][0] == 5 * w * h
+        o, d = nat.camera_rays(sample=0, seed=2)
+        one = nat.trace(o[:1], d[:1], seed=2)
+        want = Oracle(flat, rng="philox", seed=2).trace(o[:1], d[:1])
+        assert one["hit_id"][0] == want["hit_id"][0]
+        np.testing.assert_allclose(one["rgb"], want["rgb"], rtol=1e-3, atol=1e-4)
+        none = nat.trace(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+        assert none["rgb"].shape == (0, 3)
+        # frame == mean of the oracle over the same samples (5 spp, all pixels)
+        orc = Oracle(flat, rng="philox", seed=2)
+        ref = sum(orc.trace(*nat.camera_rays(sample=s, seed=2), sample=s)["rgb"] for s in range(5)) / 5
+        np.testing.assert_allclose(lin.reshape(3, -1).T, ref, rtol=2e-3, atol=2e-4)
+        nat.close()
