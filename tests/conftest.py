@@ -42,5 +42,7 @@ def build_scene(name, size):
             kwargs["normalmap"] = True
         if variant == "mc":
             kwargs["mc"] = True
+        if variant.isdigit():
+            kwargs["seed"] = int(variant)
         _SCENE_CACHE[key] = scenes.BUILDERS[base](sightpy, width=size[0], height=size[1], **kwargs)
     return _SCENE_CACHE[key]

@@ -42,6 +42,11 @@ GOLDEN_SIZES = {  # (width, height) of the fixture renders
     "example3_normalmap": (96, 72), "example2_mc": (96, 72), "triangles": (96, 72),
     "cornell": (40, 40), "cornell_mc": (32, 32),
 }
+# seeded random scenes (tests/scenes.py: fuzz): every collider type / deterministic material at random poses
+N_FUZZ = 12
+GOLDEN_SIZES.update({f"fuzz_{i}": (48, 36) for i in range(N_FUZZ)})
+N_FUZZ_MC = 8
+GOLDEN_SIZES.update({f"fuzzmc_{i}": (32, 24) for i in range(N_FUZZ_MC)})
 
 
 def load_reference():
@@ -76,6 +81,8 @@ def build(name, ns, size):
         kwargs["normalmap"] = True
     if variant == "mc":
         kwargs["mc"] = True
+    if variant.isdigit():
+        kwargs["seed"] = int(variant)
     return scenes.BUILDERS[base](ns, width=w, height=h, **kwargs)
 
 
@@ -108,7 +115,7 @@ def main(argv):
 
     ref = load_reference()
     names = argv or list(GOLDEN_SIZES)
-    report = {}
+    report = json.loads((HERE / "golden_report.json").read_text()) if argv else {}
     for name in names:
         size = GOLDEN_SIZES[name]
         cwd = os.getcwd()
@@ -187,7 +194,7 @@ def main(argv):
         # the reference's own rendered examples (end-to-end acceptance band)
         for i in range(1, 5):
             (HERE / f"EXAMPLE{i}.png").write_bytes((REF_ROOT / "images" / f"EXAMPLE{i}.png").read_bytes())
-        (HERE / "golden_report.json").write_text(json.dumps(report, indent=1))
+    (HERE / "golden_report.json").write_text(json.dumps(report, indent=1))
     print("done")
 
 

@@ -192,5 +192,166 @@ def stress(ns, width=3840, height=2160, n_spheres=4096, n_triangles=1024, n_coll
     return sc
 
 
+def fuzz(ns, width=48, height=36, seed=0):
+    """Seeded random Whitted scene: every collider type at random poses, every deterministic material with
+    random parameters, random lights / background / depth limits.  Parameters are drawn first as plain
+    floats so that the reference's classes and ours are handed identical numbers."""
+    v, rgb = ns.vec3, ns.rgb
+    rng = np.random.default_rng(1000 + seed)
+    U = lambda lo, hi, *shape: rng.uniform(lo, hi, size=shape or None)   # noqa: E731
+    f3 = lambda a: v(*map(float, a))                                    # noqa: E731
+
+    def unit(a):
+        a = np.asarray(a, dtype=np.float64)
+        return a / np.linalg.norm(a)
+
+    c3 = lambda a: v(*map(complex, a))                                  # noqa: E731
+
+    def material(allow_emissive=True, uv=True):
+        k = int(rng.integers(0, 5 if allow_emissive else 4))
+        if k == 3 and not uv:
+            k = 2       # thin films need a uv mapping, which triangles lack
+        if k == 0:      # dielectric-ish glossy, optionally textured
+            tex = uv and rng.random() < 0.4
+            colour = ns.image("checkered_floor.png", repeat=float(U(1.0, 6.0))) if tex else rgb(*map(float, U(0.05, 0.95, 3)))
+            return ns.Glossy(diff_color=colour, n=c3(U(1.1, 2.4, 3) + 1j * U(0.0, 0.6, 3)),
+                             roughness=float(U(0.0, 0.6)), spec_coeff=float(U(0.1, 0.6)), diff_coeff=float(U(0.3, 0.9)))
+        if k == 1:      # metal
+            return ns.Glossy(diff_color=rgb(*map(float, U(0.05, 0.95, 3))), n=c3(U(0.1, 1.6, 3) + 1j * U(1.5, 3.8, 3)),
+                             roughness=float(U(0.0, 0.3)), spec_coeff=float(U(0.2, 0.6)), diff_coeff=float(U(0.3, 0.9)))
+        if k == 2:      # absorbing glass
+            return ns.Refractive(n=c3(U(1.2, 1.8) + U(0.0, 0.05, 3) + 1j * U(0.0, 6e-8, 3)))
+        if k == 3:
+            return ns.ThinFilmInterference(thickness=float(U(150.0, 380.0)), noise=float(rng.choice([0.0, 20.0, 60.0])))
+        return ns.Emissive(color=rgb(*map(float, U(0.2, 3.0, 3))))
+
+    sc = ns.Scene(ambient_color=rgb(*map(float, U(0.0, 0.12, 3))))
+    ang, rad = float(U(0, 2 * np.pi)), float(U(4.0, 6.5))
+    sc.add_Camera(look_from=v(rad * np.sin(ang), float(U(0.4, 3.0)), rad * np.cos(ang)),
+                  look_at=f3(U(-0.5, 0.5, 3) + np.array([0, 0.6, 0])), screen_width=width, screen_height=height,
+                  field_of_view=float(U(45.0, 85.0)))
+    for _ in range(int(rng.integers(1, 3))):
+        sc.add_DirectionalLight(Ldir=f3(unit(U(-1, 1, 3) + np.array([0, 1.2, 0]))), color=rgb(*map(float, U(0.1, 0.6, 3))))
+    # ground: slightly tilted bounded plane
+    up = unit(np.array([0, 1.0, 0]) + U(-0.08, 0.08, 3))
+    ua = unit(np.cross(up, [0.0, 0.0, 1.0])); va = np.cross(ua, up)
+    sc.add(ns.Plane(material=material(False), center=v(0.0, -0.6, 0.0), width=float(U(8, 30)), height=float(U(8, 30)),
+                    u_axis=f3(ua), v_axis=f3(va), max_ray_depth=int(rng.integers(1, 5)), shadow=bool(rng.random() < 0.8)))
+    for _ in range(int(rng.integers(2, 5))):
+        sc.add(ns.Sphere(material=material(), center=f3(U(-2.2, 2.2, 3) * np.array([1, 0.5, 1]) + np.array([0, 0.5, 0])),
+                         radius=float(U(0.25, 0.9)), max_ray_depth=int(rng.integers(1, 6)), shadow=bool(rng.random() < 0.7)))
+    for _ in range(int(rng.integers(1, 3))):
+        cb = ns.Cuboid(material=material(), center=f3(U(-2.0, 2.0, 3) * np.array([1, 0.4, 1]) + np.array([0, 0.4, 0])),
+                       width=float(U(0.3, 1.2)), height=float(U(0.3, 1.4)), length=float(U(0.3, 1.2)),
+                       shadow=bool(rng.random() < 0.7), max_ray_depth=int(rng.integers(1, 6)))
+        for _ in range(int(rng.integers(1, 3))):
+            cb.rotate(θ=float(U(0, 360)), u=f3(unit(U(-1, 1, 3))))
+        sc.add(cb)
+    for _ in range(int(rng.integers(0, 4))):
+        c = U(-2.0, 2.0, 3) * np.array([1, 0.4, 1]) + np.array([0, 0.8, 0])
+        p = [f3(c + U(-1.0, 1.0, 3)) for _ in range(3)]
+        prim = ns.Primitive(center=f3(c), material=material(uv=False), max_ray_depth=int(rng.integers(1, 4)),
+                            shadow=bool(rng.random() < 0.7))
+        prim.collider_list += [ns.Triangle_Collider(assigned_surface=prim, p1=p[0], p2=p[1], p3=p[2])]
+        prim.bounded_sphere_radius = 2.0
+        sc.add(prim)
+    if rng.random() < 0.6:      # free-standing bounded plane at a random pose, then rotated as a primitive
+        nrm = unit(U(-1, 1, 3)); ua = unit(np.cross(nrm, unit(U(-1, 1, 3)))); va = np.cross(nrm, ua)
+        pl = ns.Plane(material=material(), center=f3(U(-2.5, 2.5, 3) * np.array([1, 0.3, 1]) + np.array([0, 1.0, 0])),
+                      width=float(U(0.8, 3.0)), height=float(U(0.8, 3.0)), u_axis=f3(ua), v_axis=f3(va),
+                      max_ray_depth=int(rng.integers(1, 5)), shadow=bool(rng.random() < 0.7))
+        if rng.random() < 0.5:
+            pl.rotate(θ=float(U(0, 360)), u=f3(unit(U(-1, 1, 3))))
+        sc.add(pl)
+    bg = int(rng.integers(0, 4))
+    if bg == 0:
+        sc.add_Background("stormydays.png")
+    elif bg == 1:
+        sc.add_Background("miramar.jpeg", spherical=True)
+    elif bg == 2:
+        sc.add_Background("lake.png", light_intensity=float(U(0.5, 3.0)), blur=0.0)
+    return sc
+
+
+def fuzzmc(ns, width=32, height=24, seed=0):
+    """Seeded random Monte-Carlo scene: a closed-ish room of Diffuse surfaces (solid and textured, several
+    fan sizes and ambient weights), emitters of every collider type, glass / glossy / thin-film bystanders,
+    0-3 importance-sampled primitives."""
+    v, rgb = ns.vec3, ns.rgb
+    rng = np.random.default_rng(5000 + seed)
+    U = lambda lo, hi, *shape: rng.uniform(lo, hi, size=shape or None)   # noqa: E731
+    f3 = lambda a: v(*map(float, a))                                    # noqa: E731
+    c3 = lambda a: v(*map(complex, a))                                  # noqa: E731
+
+    def unit(a):
+        a = np.asarray(a, dtype=np.float64)
+        return a / np.linalg.norm(a)
+
+    fans = [20] + [int(x) for x in rng.choice([4, 7, 12], size=int(rng.integers(0, 3)), replace=False)]
+
+    def diffuse(uv=True):
+        tex = uv and rng.random() < 0.3
+        colour = ns.image("checkered_floor.png", repeat=float(U(1.0, 5.0))) if tex else rgb(*map(float, U(0.1, 0.9, 3)))
+        return ns.Diffuse(diff_color=colour, diffuse_rays=int(rng.choice(fans)), ambient_weight=float(rng.choice([0.5, 0.3, 0.8])))
+
+    def bystander():
+        k = int(rng.integers(0, 4))
+        if k == 0:
+            return ns.Refractive(n=c3(U(1.3, 1.7) + np.zeros(3) + 1j * U(0.0, 3e-8, 3)))
+        if k == 1:
+            return ns.Glossy(diff_color=rgb(*map(float, U(0.1, 0.9, 3))), n=c3(U(1.1, 2.0, 3) + 1j * U(0.0, 2.0, 3)),
+                             roughness=float(U(0.0, 0.4)), spec_coeff=float(U(0.1, 0.5)), diff_coeff=float(U(0.3, 0.9)))
+        if k == 2:
+            return ns.ThinFilmInterference(thickness=float(U(150.0, 380.0)), noise=float(rng.choice([0.0, 40.0])))
+        return diffuse()
+
+    sc = ns.Scene(ambient_color=rgb(*map(float, U(0.0, 0.05, 3))))
+    sc.add_Camera(look_from=v(float(U(-0.5, 0.5)), float(U(1.5, 2.5)), 7.5), look_at=v(0.0, 2.0, 0.0), screen_width=width,
+                  screen_height=height, field_of_view=float(U(40.0, 60.0)))
+    if rng.random() < 0.5:
+        sc.add_DirectionalLight(Ldir=f3(unit(U(-1, 1, 3) + np.array([0, 1.5, 0]))), color=rgb(*map(float, U(0.1, 0.4, 3))))
+    n_importance = int(rng.integers(0, 4))
+    # room: floor, back wall, two side walls, ceiling (4 x 4 x 4, open towards the camera)
+    walls = [((0, 0, 0), (1, 0, 0), (0, 0, -1)), ((0, 2, -2), (1, 0, 0), (0, 1, 0)), ((-2, 2, 0), (0, 0, 1), (0, 1, 0)),
+             ((2, 2, 0), (0, 0, -1), (0, 1, 0)), ((0, 4, 0), (1, 0, 0), (0, 0, 1))]
+    for c, ua, va in walls:
+        sc.add(ns.Plane(material=diffuse(), center=f3(c), width=4.0, height=4.0, u_axis=f3(ua), v_axis=f3(va),
+                        max_ray_depth=int(rng.integers(2, 5))))
+    # emitters
+    kind = int(rng.integers(0, 3))
+    lamp = ns.Emissive(color=rgb(*map(float, U(4.0, 16.0, 3))))
+    if kind == 0:
+        em = ns.Plane(material=lamp, center=v(float(U(-0.8, 0.8)), 3.98, float(U(-0.8, 0.8))), width=float(U(0.6, 1.6)),
+                      height=float(U(0.6, 1.6)), u_axis=v(1.0, 0, 0), v_axis=v(0, 0, 1.0))
+    elif kind == 1:
+        em = ns.Sphere(material=lamp, center=f3(U(-1.2, 1.2, 3) + np.array([0, 2.8, 0])), radius=float(U(0.15, 0.45)))
+    else:
+        em = ns.Cuboid(material=lamp, center=f3(U(-1.0, 1.0, 3) + np.array([0, 3.0, 0])), width=float(U(0.3, 0.8)),
+                       height=float(U(0.2, 0.5)), length=float(U(0.3, 0.8)))
+        em.rotate(θ=float(U(0, 90)), u=f3(unit(U(-1, 1, 3))))
+    sc.add(em, importance_sampled=n_importance >= 1)
+    for j in range(int(rng.integers(2, 5))):
+        c = U(-1.4, 1.4, 3) + np.array([0, 1.2, 0])
+        m = bystander()
+        if rng.random() < 0.6:
+            ob = ns.Sphere(material=m, center=f3(c), radius=float(U(0.3, 0.7)), max_ray_depth=int(rng.integers(2, 5)),
+                           shadow=bool(rng.random() < 0.5), mc=bool(rng.random() < 0.5))
+        else:
+            ob = ns.Cuboid(material=m, center=f3(c), width=float(U(0.4, 1.0)), height=float(U(0.4, 1.6)),
+                           length=float(U(0.4, 1.0)), max_ray_depth=int(rng.integers(2, 5)), shadow=bool(rng.random() < 0.5))
+            ob.rotate(θ=float(U(0, 360)), u=f3(unit(U(-0.3, 0.3, 3) + np.array([0, 1.0, 0]))))
+        sc.add(ob, importance_sampled=(j + 2) <= n_importance)
+    if rng.random() < 0.5:
+        c = U(-1.0, 1.0, 3) + np.array([0, 2.0, 0])
+        prim = ns.Primitive(center=f3(c), material=diffuse(uv=False), max_ray_depth=3, shadow=True)
+        prim.collider_list += [ns.Triangle_Collider(assigned_surface=prim, p1=f3(c + U(-1, 1, 3)), p2=f3(c + U(-1, 1, 3)),
+                                                    p3=f3(c + U(-1, 1, 3)))]
+        prim.bounded_sphere_radius = 2.0
+        sc.add(prim)
+    if rng.random() < 0.5:
+        sc.add_Background("lake.png", light_intensity=float(U(0.5, 2.0)), blur=0.0)
+    return sc
+
+
 BUILDERS = {"example1": example1, "example2": example2, "example3": example3, "example4": example4,
-            "cornell": cornell, "triangles": triangles}
+            "cornell": cornell, "triangles": triangles, "fuzz": fuzz, "fuzzmc": fuzzmc}
