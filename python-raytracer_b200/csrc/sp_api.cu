@@ -174,6 +174,7 @@ struct sp_scene {
     DevBuf<float4> bvh_nodes, bvh_data;
     DevBuf<int4> bvh_items;
     DevBuf<DColInfo> d_colinfo;
+    DevBuf<float4> d_collite;
     DevBuf<double> d_cols_d;
     DevBuf<DPrimitive> d_prims;
     DevBuf<DMaterial> d_mats;
@@ -205,7 +206,7 @@ struct sp_scene {
         d_texels.clear();
 
         geom_all.release(); geom_shadow.release(); accum.release(); off_all.release(); off_shadow.release();
-        slot_shadow.release(); d_cols.release(); d_colinfo.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
+        slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
         for (auto e : events) g_event_pool.push_back(e);
@@ -825,6 +826,12 @@ int sp_scene_commit(sp_scene* s) {
         ci.max_ray_depth = (int16_t)pr.max_ray_depth; ci.max_dr = (int16_t)m.max_diffuse_reflections;
         ci.slot = 0xFFFFFFFFu; ci.w_cos = (float)m.ambient_weight;
     }
+    std::vector<float4> dlite((size_t)n_col);
+    for (int i = 0; i < n_col; ++i) {
+        const DMaterial& m = dm[s->prims[s->cols[i].primitive].material];
+        dlite[i] = make_float4(m.color.x, m.color.y, m.color.z, m.diffuse_rays > 0 ? 1.f / (float)m.diffuse_rays : 1.f);
+    }
+    CUDA_TRY(s->d_collite.upload(dlite));
     CUDA_TRY(s->d_cols_d.upload(dcd));
 
     // ---- textures ---------------------------------------------------------------------------------------
@@ -904,7 +911,7 @@ int sp_scene_commit(sp_scene* s) {
     d.shadow.data = s->geom_shadow.p; d.shadow.chunk_off = s->off_shadow.p;
     d.shadow.n_chunks = (int)shadow.chunk_off.size() - 1; d.shadow.n_items = shadow.n_items;
 
-    d.colliders = s->d_cols.p; d.col_info = s->d_colinfo.p; d.colliders_d = s->d_cols_d.p; d.prims = s->d_prims.p; d.mats = s->d_mats.p;
+    d.colliders = s->d_cols.p; d.col_info = s->d_colinfo.p; d.col_lite = s->d_collite.p; d.colliders_d = s->d_cols_d.p; d.prims = s->d_prims.p; d.mats = s->d_mats.p;
     d.textures = s->d_texdesc.p; d.media = s->d_media.p;
     d.n_lights = (int)s->lights.size();
     for (int i = 0; i < d.n_lights; ++i) {

@@ -153,6 +153,59 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
     }
 }
 
+// The same walk with the ray's source collider named by its position in the chunk's id array (the value a
+// winning test leaves in best.idx) instead of a per-section index: one compare per test, nothing to decode.
+template <int A>
+SP_DEV void sp_intersect_aa_tag(const float4* __restrict__ aa, int first, int count, int id_base, float3 O, float3 D,
+                                float inv_da, int self_tag, ChunkBest& best) {
+#pragma unroll 2
+    for (int i = first; i < first + count; ++i)
+        sp_item_aa<A>(aa[2 * i], aa[2 * i + 1], O, D, inv_da, id_base + i == self_tag, id_base + i, best);
+}
+
+SP_DEV void sp_intersect_chunk_tag(const float4* __restrict__ ch, float3 O, float3 D, int self_tag, uint32_t mode,
+                                   ChunkBest& best) {
+    const GeomChunkHeader* h = reinterpret_cast<const GeomChunkHeader*>(ch);
+    const int n_sphere = h->n_sphere, n_plane = h->n_plane, n_cuboid = h->n_cuboid, n_tri = h->n_tri;
+    int tag = 0;
+    {
+        const float4* sp = ch + h->off_sphere;
+#pragma unroll 4
+        for (int i = 0; i < n_sphere; ++i) sp_item_sphere(sp[i], O, D, i == self_tag, mode, i, best);
+        tag += n_sphere;
+    }
+    {
+        const float4* pl = ch + h->off_plane;
+#pragma unroll 2
+        for (int i = 0; i < n_plane; ++i)
+            sp_item_plane(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3], O, D, tag + i == self_tag, tag + i, best);
+        tag += n_plane;
+    }
+    {
+        const float4* cb = ch + h->off_cuboid;
+        for (int i = 0; i < n_cuboid; ++i)
+            sp_item_cuboid(cb[5 * i], cb[5 * i + 1], cb[5 * i + 2], cb[5 * i + 3], cb[5 * i + 4], O, D, tag + i == self_tag,
+                           mode, tag + i, best);
+        tag += n_cuboid;
+    }
+    {
+        const float4* tr = ch + h->off_tri;
+#pragma unroll 2
+        for (int i = 0; i < n_tri; ++i)
+            sp_item_triangle(tr[3 * i], tr[3 * i + 1], tr[3 * i + 2], O, D, tag + i == self_tag, tag + i, best);
+        tag += n_tri;
+    }
+    {
+        const int n_aax = h->n_aax, n_aay = h->n_aay, n_aaz = h->n_aaz;
+        if (n_aax + n_aay + n_aaz > 0) {
+            const float4* aa = ch + h->off_aa;
+            if (n_aax > 0) sp_intersect_aa_tag<0>(aa, 0, n_aax, tag, O, D, fast_rcp(D.x), self_tag, best);
+            if (n_aay > 0) sp_intersect_aa_tag<1>(aa, n_aax, n_aay, tag, O, D, fast_rcp(D.y), self_tag, best);
+            if (n_aaz > 0) sp_intersect_aa_tag<2>(aa, n_aax + n_aay, n_aaz, tag, O, D, fast_rcp(D.z), self_tag, best);
+        }
+    }
+}
+
 // ---- bounding-volume hierarchy over the small colliders of a large scene ---------------------------------
 // An acceleration structure (the reference itself notes that meshes need one,
 // triangle_mesh.py:7-9), used when a scene has SP_BVH_MIN_COLLIDERS colliders or more: with it a ray no longer

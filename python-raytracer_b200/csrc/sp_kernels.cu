@@ -15,6 +15,7 @@
 // round trip.  The colliders are staged into shared memory in 32 KB type-sorted chunks and every
 // lane of a warp reads the same address (broadcast).
 #include <cstdio>
+#include <cstdlib>
 
 #include "sp_launch.h"
 #include "sp_sampling.cuh"
@@ -386,6 +387,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 const uint32_t need_ray = rs & 3u;
                 const uint32_t rbase = cn.queue_base[0];
                 ctx.ray_slot = (need_ray && rbase != SP_SLOT_NONE) ? rbase + (rs >> 2) : SP_SLOT_NONE;
+                ctx.ray_slot1 = ctx.ray_slot == SP_SLOT_NONE ? SP_SLOT_NONE : ctx.ray_slot + 1u;
                 ctx.ray_used = 0u;
                 ctx.fan_slot = SP_SLOT_NONE;
                 if (fs != SP_SLOT_NONE) {
@@ -424,6 +426,8 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         if (shr) atomicAdd(&a.out.stats->shadow_rays, shr);
     }
 }
+
+#include "sp_warp_kernel.cuh"
 
 // ---- frame resolve: average, sRGB OETF, per-pixel max normalisation, truncation to uint8 ---------
 // scene.py:118-140 + colour_functions.py:4-18.  Double precision: the output is quantised by
@@ -507,9 +511,28 @@ static LevelKernel level_kernel(uint32_t material_set, bool level0) {
     }
 }
 
+// Queue-fed levels of small untextured Monte-Carlo scenes run the warp-autonomous kernel (sp_warp_kernel.cuh).
+// SIGHTPY_WARP_KERNEL=0 keeps them on sp_level_kernel (A/B measurements).
+bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set) {
+    static const bool enabled = [] { const char* e = getenv("SIGHTPY_WARP_KERNEL"); return !(e && e[0] == '0'); }();
+    if (!enabled || material_set != SP_SET_MC) return false;
+    if (sc.all.n_chunks != 1 || sc.bvh.n_nodes != 0 || sc.n_colliders > SPW_MAX_COLLIDERS) return false;
+    for (int c = 0; c < sc.n_fan_classes; ++c)
+        if (sc.fan_mult[c] > 1024) return false;
+    return true;
+}
+
 int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (!level0 && sp_use_warp_kernel(sc, material_set)) {
+        auto k = sp_warp_kernel<SP_SET_MC>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SPW_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        return sms * per_sm;
+    }
     LevelKernel k = level_kernel(material_set, level0);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
     int per_sm = 1;
@@ -519,6 +542,10 @@ int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool leve
 }
 
 cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st) {
+    if (a.source == SP_SRC_QUEUES && a.run == SP_RUN_FULL && sp_use_warp_kernel(sc, material_set)) {
+        sp_warp_kernel<SP_SET_MC><<<grid, SPW_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
+        return cudaGetLastError();
+    }
     level_kernel(material_set, a.source != SP_SRC_QUEUES)<<<grid, SP_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
     return cudaGetLastError();
 }

@@ -177,16 +177,16 @@ struct ShadeCtx {
     const float* lin_lut;       // shared-memory copy of the sRGB -> linear table
     unsigned long long shadow_rays;
     // slots reserved for the hit being shaded
-    uint32_t ray_slot, ray_used, fan_slot;
+    uint32_t ray_slot, ray_slot1, ray_used, fan_slot;   // ray_slot1: where a second child ray goes
 };
 
 SP_DEV void sp_emit_ray(ShadeCtx& cx_, const Ray& r, float3 o, float3 d, float3 thr, uint32_t k,
                         uint32_t medium, uint32_t dr, int src, uint32_t mode) {
     if (!any_nonzero(thr)) return;          // zero-weight children cannot contribute
-    const uint32_t slot = cx_.ray_slot;
+    const uint32_t slot = cx_.ray_used == 0u ? cx_.ray_slot : cx_.ray_slot1;
     if (slot == SP_SLOT_NONE) return;       // the CTA's reservation overflowed the queue (reported to the host)
     uint32_t meta = sp_pack_meta(meta_depth(r.meta) + 1u, dr, medium, (uint32_t)src, mode);
-    sp_write_record(cx_.out->rays, slot + cx_.ray_used, o, d, thr, r.pix, sp_child_path(r.path, k), meta);
+    sp_write_record(cx_.out->rays, slot, o, d, thr, r.pix, sp_child_path(r.path, k), meta);
     cx_.ray_used += 1u;
 }
 

@@ -108,6 +108,7 @@ struct DScene {
     DBvh bvh;                          // n_nodes == 0: every collider is in the streams
     const DCollider* colliders;
     const DColInfo* col_info;
+    const float4* col_lite;        // per collider: its material's plain colour, 1 / diffuse_rays (inline shading, sp_warp_kernel.cuh)
     const double* colliders_d;     // [n][44] double payloads for the precise hit path
     const DPrimitive* prims;
     const DMaterial* mats;

@@ -1,0 +1,349 @@
+// Warp-autonomous level kernel for small untextured Monte-Carlo scenes (the Cornell box family).
+//
+// Same contract as sp_level_kernel (sp_kernels.cu): one launch consumes every ray of one recursion depth
+// of get_raycolor (ray.py:122-148) from the previous level's queues and appends the next level's records.
+// What differs is how the work is organised inside an SM.  sp_level_kernel parks all 512 rays of a CTA
+// iteration in shared memory, regroups them by the material they hit and shades them behind a CTA barrier;
+// ncu put a third of its warp instructions into that bookkeeping (shared-memory atomics, ballots, list
+// handling, chunk hand-out) and 8 % of its issue cycles into the two barriers.  Here every warp is on its
+// own — there is no barrier and no atomic in the loop:
+//   * the cheap, common outcomes of a hit are handled on the spot: a Diffuse hit writes its fan record
+//     (diffuse.py:25-124: hit point, shading normal, throughput x albedo), an Emissive hit adds
+//     throughput x colour to its pixel (emissive.py:21-23), a hit that is black by construction does nothing;
+//   * the expensive outcome — Refractive (refractive.py:24-123: complex Fresnel, two children) — goes into a
+//     *warp-private stash* in shared memory and is shaded 32 hits at a time, so that code runs with full
+//     lanes no matter how the glass hits are scattered over the rays;
+//   * queue slots come from *warp-private slabs*: a warp reserves a run of slots with one global atomic
+//     (per 64-256 records instead of per CTA iteration) and hands them out with ballot + popc.  A slab that
+//     cannot take a whole request is finished by the first ranks and the rest go to a fresh one, so the
+//     only unused slots are each warp's last slab; they are filled with dead records at exit;
+//   * work items are walked segment by segment (ray records, then each fan class), which makes the record /
+//     child split of a fan item an incremental update instead of a 64-bit magic division per ray.
+// Eligibility (host, sp_use_warp_kernel): queue-fed level, material set Diffuse + Refractive + Emissive
+// without textures, one geometry chunk, no BVH, fewer than 64 colliders, fan multiplicities <= 1024.
+#pragma once
+#include "sp_launch.h"
+#include "sp_sampling.cuh"
+#include "sp_shade.cuh"
+
+#define SPW_BLOCK 256
+#define SPW_WARPS (SPW_BLOCK / 32)
+#define SPW_STASH_WORDS 14           // o d thr pix path meta t (id | orient)
+#define SPW_STASH_CAP 64             // < 32 left over + 32 pushed
+#define SPW_MAX_COLLIDERS 64           // = SP_BVH_MIN_COLLIDERS: larger scenes go through the BVH variant
+#define SPW_N_QUEUES (1 + SP_MAX_FAN_CLASSES)
+
+struct WarpShared {
+    uint32_t stash[SPW_WARPS][SPW_STASH_WORDS][SPW_STASH_CAP];
+    uint32_t slab[SPW_WARPS][SPW_N_QUEUES][2];     // per warp and output queue: next free slot, end of the slab
+    float2 src_info[SPW_MAX_COLLIDERS];            // per collider: position in the chunk's id array (as int bits), cosine-pdf weight
+    float4 lite[SPW_MAX_COLLIDERS];                // per collider: albedo / emitted colour, 1 / diffuse_rays
+};
+
+// Slots for `tot` records of output queue q, requested by the whole warp at once.  Rank x of the request
+// lives at  x < rem ? first + x : fresh + (x - rem).
+struct SlabGrant { uint32_t first, rem, fresh; };
+SP_DEV uint32_t sp_slab_pos(const SlabGrant& g, uint32_t x) {
+    if (x < g.rem) return g.first + x;
+    return g.fresh == SP_SLOT_NONE ? SP_SLOT_NONE : g.fresh + (x - g.rem);
+}
+
+SP_DEV SlabGrant sp_slab_alloc(uint32_t* slab, uint32_t tot, uint32_t q, uint32_t slab_size, const LevelOut& out, uint32_t lane) {
+    SlabGrant g;
+    const uint32_t next = slab[0], end = slab[1];
+    g.first = next; g.rem = end - next; g.fresh = SP_SLOT_NONE;
+    uint32_t new_next = next + tot, new_end = end;
+    if (tot > g.rem) {                                        // warp-uniform: finish this slab, open another
+        uint32_t b = 0;
+        if (lane == 0) {
+            const uint32_t cap = (q == 0) ? out.rays.capacity : out.fan_cap[q - 1];
+            b = atomicAdd(out.counts + q, slab_size);
+            if (b + slab_size > cap) { out.stats->overflow = 1u; b = SP_SLOT_NONE; }
+            else if (q > 0) b += out.fan_base[q - 1];
+        }
+        b = __shfl_sync(0xffffffffu, b, 0);
+        g.fresh = b;
+        if (b == SP_SLOT_NONE) { new_next = 0u; new_end = 0u; }
+        else { new_next = b + (tot - g.rem); new_end = b + slab_size; }
+    }
+    __syncwarp();
+    if (lane == 0) { slab[0] = new_next; slab[1] = new_end; }
+    __syncwarp();
+    return g;
+}
+
+// Shade the top n (<= 32) entries of the warp's stash: all Refractive hits that can still spawn children.
+template <uint32_t FEAT>
+__device__ __noinline__ void sp_shade_stash(const DScene* scp, const LevelArgs* ap, uint32_t* stash, uint32_t* slabs,
+                                            uint32_t first, uint32_t n, uint32_t slab_size, uint32_t lane) {
+    const DScene& sc = *scp;
+    const LevelArgs& a = *ap;
+    const bool mine = lane < n;
+    Ray s;
+    HitRec h;
+    s.o = s.d = s.thr = v3(0.f); s.pix = s.path = s.meta = 0u; h.t = 0.f; h.id = 0; h.orient = 1;
+    int n_ray = 0;
+    if (mine) {
+        const uint32_t j = first + lane;
+        const uint32_t* st = stash + j;
+        s.o = v3(__uint_as_float(st[0 * SPW_STASH_CAP]), __uint_as_float(st[1 * SPW_STASH_CAP]), __uint_as_float(st[2 * SPW_STASH_CAP]));
+        s.d = v3(__uint_as_float(st[3 * SPW_STASH_CAP]), __uint_as_float(st[4 * SPW_STASH_CAP]), __uint_as_float(st[5 * SPW_STASH_CAP]));
+        s.thr = v3(__uint_as_float(st[6 * SPW_STASH_CAP]), __uint_as_float(st[7 * SPW_STASH_CAP]), __uint_as_float(st[8 * SPW_STASH_CAP]));
+        s.pix = st[9 * SPW_STASH_CAP]; s.path = st[10 * SPW_STASH_CAP]; s.meta = st[11 * SPW_STASH_CAP];
+        h.t = __uint_as_float(st[12 * SPW_STASH_CAP]);
+        const uint32_t packed = st[13 * SPW_STASH_CAP];
+        h.id = (int)(packed & 0x7FFFFFFFu); h.orient = (packed & 0x80000000u) ? 1 : -1;
+        const float4 raw = __ldg(reinterpret_cast<const float4*>(sc.col_info + h.id));
+        const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
+        int fan_class;
+        sp_child_needs(ci, meta_depth(s.meta), meta_dr(s.meta), n_ray, fan_class);
+    }
+    __syncwarp();                                             // the entries are free again
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t b0 = __ballot_sync(0xffffffffu, n_ray & 1), b1 = __ballot_sync(0xffffffffu, n_ray & 2);
+    const uint32_t tot = __popc(b0) + 2u * __popc(b1);
+    ShadeCtx ctx;
+    ctx.sc = scp; ctx.out = &a.out; ctx.shadow_slot = a.shadow_slot; ctx.lin_lut = nullptr; ctx.shadow_rays = 0;
+    ctx.ray_slot = ctx.ray_slot1 = SP_SLOT_NONE; ctx.ray_used = 0u; ctx.fan_slot = SP_SLOT_NONE;
+    if (tot) {
+        const SlabGrant g = sp_slab_alloc(slabs, tot, 0u, slab_size < 64u ? 64u : slab_size, a.out, lane);
+        const uint32_t rank = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
+        if (n_ray >= 1) ctx.ray_slot = sp_slab_pos(g, rank);
+        if (n_ray >= 2) ctx.ray_slot1 = sp_slab_pos(g, rank + 1u);
+    }
+    if (mine) {
+        const float3 add = sp_shade<FEAT>(ctx, s, h);
+        float* px = reinterpret_cast<float*>(a.accum + s.pix);
+        if (add.x != 0.f) atomicAdd(px, add.x);
+        if (add.y != 0.f) atomicAdd(px + 1, add.y);
+        if (add.z != 0.f) atomicAdd(px + 2, add.z);
+        // reserved but unused slots become dead records
+        if (ctx.ray_used < 1u && n_ray >= 1 && ctx.ray_slot != SP_SLOT_NONE) sp_write_dead(a.out.rays, ctx.ray_slot);
+        if (ctx.ray_used < 2u && n_ray >= 2 && ctx.ray_slot1 != SP_SLOT_NONE) sp_write_dead(a.out.rays, ctx.ray_slot1);
+    }
+}
+
+template <uint32_t FEAT>
+__global__ void __launch_bounds__(SPW_BLOCK, 4)
+sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
+    static_assert((FEAT & ~(SP_F_DIFFUSE | SP_F_REFR)) == 0u, "inline shading covers untextured Diffuse / Emissive only");
+    extern __shared__ float4 s_geom[];
+    __shared__ WarpShared sh;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // ---- work items of this launch -------------------------------------------------------------------
+    const uint32_t n_rays = min(__ldg(a.in_counts), a.in_rays.capacity);
+    uint32_t total = n_rays;
+    for (int c = 0; c < sc.n_fan_classes; ++c) total += min(__ldg(a.in_counts + 1 + c), a.in_fan_cap[c]) * (uint32_t)sc.fan_mult[c];
+    if (total == 0u) return;
+    // slots per slab: about an eighth of what a warp can emit in this launch, so that the unused tails stay a
+    // few per cent of the queue even for small launches; a power of two in [32, 256]
+    uint32_t slab_size = 32u;
+    {
+        const uint32_t per_warp = total / (gridDim.x * SPW_WARPS * 8u);
+        while (slab_size < 256u && slab_size * 2u <= per_warp) slab_size *= 2u;
+    }
+
+    sp_stage_chunk(s_geom, sc, sc.all, 0);
+    for (uint32_t i = tid; i < (uint32_t)sc.n_colliders; i += SPW_BLOCK) {
+        const float4 raw = __ldg(reinterpret_cast<const float4*>(sc.col_info + i));
+        const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
+        sh.src_info[i].y = ci.w_cos;
+        sh.lite[i] = __ldg(sc.col_lite + i);
+    }
+    if (tid < SPW_WARPS * SPW_N_QUEUES * 2) reinterpret_cast<uint32_t*>(sh.slab)[tid] = 0u;
+    __syncthreads();
+    {
+        const GeomChunkHeader* gh = reinterpret_cast<const GeomChunkHeader*>(s_geom);
+        const int n_items = gh->n_sphere + gh->n_plane + gh->n_cuboid + gh->n_tri + gh->n_aax + gh->n_aay + gh->n_aaz;
+        const int* ids = reinterpret_cast<const int*>(s_geom + gh->off_ids);
+        for (int k = (int)tid; k < n_items; k += SPW_BLOCK) sh.src_info[ids[k]].x = __int_as_float(k);
+    }
+    __syncthreads();
+
+    uint32_t* const stash = &sh.stash[warp][0][0];
+    uint32_t* const slabs = &sh.slab[warp][0][0];
+    uint32_t n_st = 0;                                         // entries in the stash (warp-uniform)
+    unsigned long long traced = 0;
+    const uint32_t n_warps = gridDim.x * SPW_WARPS;
+    const uint32_t stride = n_warps * 32u;
+
+    for (int seg = 0; seg <= sc.n_fan_classes; ++seg) {
+        // segment 0: explicit ray records; segment 1 + c: the children of fan class c
+        uint32_t mult = 1u, n_items = n_rays, fan_base = 0u;
+        if (seg > 0) {
+            mult = (uint32_t)sc.fan_mult[seg - 1];
+            n_items = min(__ldg(a.in_counts + seg), a.in_fan_cap[seg - 1]) * mult;
+            fan_base = a.in_fan_base[seg - 1];
+        }
+        // item = rec * mult + child, kept up to date incrementally: (rec0, rem0) belong to the warp's first item
+        const uint32_t inv24 = (1u << 24) / mult + 1u;         // floor(x / mult) == (x * inv24) >> 24 for x * mult < 2^24
+        const uint32_t step_rec = stride / mult, step_rem = stride % mult;
+        uint32_t wb = (blockIdx.x * SPW_WARPS + warp) * 32u;
+        uint32_t rec0 = wb / mult, rem0 = wb % mult;
+#pragma unroll 1
+        for (; wb < n_items; wb += stride) {
+            const uint32_t item = wb + lane;
+            bool active = item < n_items;
+            Ray r;
+            r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
+            // ---- 1. the ray of this item -----------------------------------------------------------------
+            if (seg == 0) {
+                if (active) {
+                    const float4 q2 = a.in_rays.q2[item];
+                    r.meta = __float_as_uint(q2.w);
+                    if (r.meta == SP_META_DEAD) {
+                        active = false;
+                    } else {
+                        const float4 q0 = a.in_rays.q0[item], q1 = a.in_rays.q1[item];
+                        r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
+                        r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
+                    }
+                }
+            } else {
+                const uint32_t x = rem0 + lane;
+                const uint32_t qd = (x * inv24) >> 24;
+                const uint32_t rec = rec0 + qd, child = x - qd * mult;
+                rec0 += step_rec; rem0 += step_rem;
+                if (rem0 >= mult) { rem0 -= mult; rec0 += 1u; }
+                if (active) {
+                    const uint32_t s = fan_base + rec;
+                    const float4 q2 = a.in_fans.q2[s];
+                    r.meta = __float_as_uint(q2.w);
+                    if (r.meta == SP_META_DEAD) {
+                        active = false;
+                    } else {
+                        const float4 q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
+                        r.o = xyz(q0); r.thr = xyz(q2);
+                        r.pix = __float_as_uint(q0.w);
+                        r.path = sp_child_path(__float_as_uint(q1.w), child);
+                        const float w_cos = sh.src_info[meta_src(r.meta)].y;
+                        const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), w_cos, r.pix, r.path, r.d);
+                        r.thr = r.thr * weight;
+                        active = weight > 0.f;                 // zero-weight samples cannot contribute: not traced
+                    }
+                }
+            }
+
+            // ---- 2. nearest hit over the chunk --------------------------------------------------------------
+            HitRec hit; hit.t = SP_INF; hit.id = -1; hit.orient = 0;
+            if (active) {
+                const uint32_t src = meta_src(r.meta), mode = meta_mode(r.meta);
+                int self_tag = -1;
+                bool need_test = true;
+                if (src != SP_SRC_NONE) {
+                    if (mode == SP_SELF_ZERO) {
+                        // the ray dives back into the surface it starts on: immediate hit at t = 0 (sp_kernels.cu)
+                        const DCollider& c0 = sc.colliders[src];
+                        float3 Nc = to_f3(sp_collider_normal<float>(c0.type, c0.p, from_f3<float>(r.o)));
+                        hit.t = 0.f; hit.id = (int)src; hit.orient = dot(r.d, Nc) < 0.f ? 1 : -1;
+                        need_test = false;
+                    } else {
+                        self_tag = __float_as_int(sh.src_info[src].x);
+                    }
+                }
+                if (need_test) {
+                    ChunkBest best; best.t = SP_INF; best.idx = -1; best.orient = 0;
+                    sp_intersect_chunk_tag(s_geom, r.o, r.d, self_tag, mode, best);
+                    if (best.idx >= 0) { hit.t = best.t; hit.orient = best.orient; hit.id = sp_chunk_id(s_geom, best.idx); }
+                }
+                traced += 1;
+            }
+
+            // ---- 3. what the hit does -------------------------------------------------------------------------
+            int fan_class = -1;
+            bool glass = false;
+            float4 lite = make_float4(0.f, 0.f, 0.f, 1.f);
+            uint32_t ctype = 0u;
+            if (active && hit.id >= 0) {
+                const float4 raw = __ldg(reinterpret_cast<const float4*>(sc.col_info + hit.id));
+                const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
+                const uint32_t depth = meta_depth(r.meta), dr = meta_dr(r.meta);
+                ctype = ci.type;
+                if (ci.kind == SP_MAT_DIFFUSE) {
+                    if (dr < 1u) fan_class = ci.fan_class;
+                    else if ((int)dr < (int)ci.max_dr) fan_class = 0;
+                    if (fan_class >= 0) lite = sh.lite[hit.id];
+                } else if (ci.kind == SP_MAT_EMISSIVE) {          // emissive.py:21-23
+                    lite = sh.lite[hit.id];
+                    const float3 add = r.thr * xyz(lite);
+                    float* px = reinterpret_cast<float*>(a.accum + r.pix);
+                    if (add.x != 0.f) atomicAdd(px, add.x);
+                    if (add.y != 0.f) atomicAdd(px + 1, add.y);
+                    if (add.z != 0.f) atomicAdd(px + 2, add.z);
+                } else {                                          // Refractive; black past max_ray_depth (refractive.py:38)
+                    glass = (int)depth < (int)ci.max_ray_depth;
+                }
+            }
+
+            // ---- 4. Diffuse hits: fan record for the next level (diffuse.py:25-124) ----------------------------
+            {
+                uint32_t todo = __ballot_sync(0xffffffffu, fan_class >= 0);
+                while (todo) {                                    // one round per fan class present in the warp
+                    const int c = __shfl_sync(0xffffffffu, fan_class, __ffs(todo) - 1);
+                    const uint32_t bc = __ballot_sync(0xffffffffu, fan_class == c);
+                    todo &= ~bc;
+                    const SlabGrant g = sp_slab_alloc(slabs + 2 * (1 + c), __popc(bc), 1u + (uint32_t)c, slab_size, a.out, lane);
+                    if (fan_class == c) {
+                        const uint32_t slot = sp_slab_pos(g, __popc(bc & lt_mask));
+                        if (slot != SP_SLOT_NONE) {
+                            const float inv_m = (meta_dr(r.meta) < 1u) ? lite.w : 1.f;
+                            const float3 thr = r.thr * xyz(lite) * inv_m;
+                            if (any_nonzero(thr)) {
+                                const DCollider& col = sc.colliders[hit.id];
+                                const float3 P = fma3(r.d, hit.t, r.o);
+                                const float3 Nc = to_f3(sp_collider_normal<float>((int)ctype, col.p, from_f3<float>(P)));
+                                const float orient = (float)hit.orient;
+                                const float3 N = Nc * orient;
+                                const float side_plus = dot(N, Nc) >= 0.f ? 1.f : -1.f;
+                                const bool planar = (ctype == SP_COLLIDER_PLANE || ctype == SP_COLLIDER_TRIANGLE);
+                                const uint32_t mode = (planar || side_plus > 0.f) ? SP_SELF_SKIP : SP_SELF_FAR;
+                                const uint32_t meta = sp_pack_meta(meta_depth(r.meta) + 1u, meta_dr(r.meta) + 1u, meta_medium(r.meta),
+                                                                   (uint32_t)hit.id, mode);
+                                sp_write_record(a.out.fans, slot, fma3(N, 1e-6f, P), N, thr, r.pix, r.path, meta);
+                            } else {
+                                sp_write_dead(a.out.fans, slot);
+                            }
+                        }
+                    }
+                }
+            }
+
+            // ---- 5. Refractive hits: stash, shade 32 at a time ---------------------------------------------------
+            {
+                const uint32_t bg = __ballot_sync(0xffffffffu, glass);
+                if (bg) {
+                    if (glass) {
+                        uint32_t* st = stash + n_st + __popc(bg & lt_mask);
+                        st[0 * SPW_STASH_CAP] = __float_as_uint(r.o.x); st[1 * SPW_STASH_CAP] = __float_as_uint(r.o.y); st[2 * SPW_STASH_CAP] = __float_as_uint(r.o.z);
+                        st[3 * SPW_STASH_CAP] = __float_as_uint(r.d.x); st[4 * SPW_STASH_CAP] = __float_as_uint(r.d.y); st[5 * SPW_STASH_CAP] = __float_as_uint(r.d.z);
+                        st[6 * SPW_STASH_CAP] = __float_as_uint(r.thr.x); st[7 * SPW_STASH_CAP] = __float_as_uint(r.thr.y); st[8 * SPW_STASH_CAP] = __float_as_uint(r.thr.z);
+                        st[9 * SPW_STASH_CAP] = r.pix; st[10 * SPW_STASH_CAP] = r.path; st[11 * SPW_STASH_CAP] = r.meta;
+                        st[12 * SPW_STASH_CAP] = __float_as_uint(hit.t);
+                        st[13 * SPW_STASH_CAP] = (uint32_t)hit.id | (hit.orient > 0 ? 0x80000000u : 0u);
+                    }
+                    n_st += __popc(bg);
+                    __syncwarp();
+                    if (n_st >= 32u) {
+                        n_st -= 32u;
+                        sp_shade_stash<SP_F_REFR>(&sc, &a, stash, slabs, n_st, 32u, slab_size, lane);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- drain: what is left in the stash, then the unused tails of the slabs ---------------------------------
+    if (n_st) sp_shade_stash<SP_F_REFR>(&sc, &a, stash, slabs, 0u, n_st, slab_size, lane);
+    __syncwarp();
+    for (uint32_t q = 0; q < SPW_N_QUEUES; ++q) {
+        const uint32_t next = slabs[2 * q], end = slabs[2 * q + 1];
+        const RayQueue& rq = (q == 0) ? a.out.rays : a.out.fans;
+        for (uint32_t s = next + lane; s < end; s += 32u) sp_write_dead(rq, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
+    if (lane == 0 && traced) atomicAdd(&a.out.stats->rays[a.level], traced);
+}
