@@ -360,6 +360,12 @@ static BuiltStream build_stream(const std::vector<sp_collider>& cols, std::vecto
             const sp_collider& c = cols[ids[k]];
             const int t = st[ids[k]];
             pack_collider(c, t, fl + at);
+            if (t >= SP_ST_AAX) {
+                // third word of the second vector: position in the id array | (normal along +axis) << 31, which
+                // sp_intersect_lean turns into tag | orientation with one XOR (sp_geometry.cuh)
+                const uint32_t code = (uint32_t)(k - pos) | (fl[at + 3] > 0.f ? 0x80000000u : 0u);
+                memcpy(fl + at + 6, &code, sizeof code);
+            }
             at += 4 * type_vec4(t);
             idp[k - pos] = ids[k];
             // the three axis-aligned sections share one index space (code 4)

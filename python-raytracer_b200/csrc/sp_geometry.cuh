@@ -153,56 +153,130 @@ SP_DEV void sp_intersect_chunk(const float4* __restrict__ ch, float3 O, float3 D
     }
 }
 
-// The same walk with the ray's source collider named by its position in the chunk's id array (the value a
-// winning test leaves in best.idx) instead of a per-section index: one compare per test, nothing to decode.
-template <int A>
-SP_DEV void sp_intersect_aa_tag(const float4* __restrict__ aa, int first, int count, int id_base, float3 O, float3 D,
-                                float inv_da, int self_tag, ChunkBest& best) {
-#pragma unroll 2
-    for (int i = first; i < first + count; ++i)
-        sp_item_aa<A>(aa[2 * i], aa[2 * i + 1], O, D, inv_da, id_base + i == self_tag, id_base + i, best);
+// ---- lean walk for the warp-autonomous kernel (sp_warp_kernel.cuh) ---------------------------------------
+// The same tests in the same order, with less bookkeeping per test: the ray's source collider is named by its
+// position in the chunk's id array ("tag"), the winner is kept as one word  tag | (inner face) << 31, and an
+// axis-aligned rectangle brings that word along (packed by the host), so its orientation costs one XOR with
+// the sign of the ray's direction component.
+SP_DEV void sp_lean_sphere(float4 s, float3 O, float3 D, bool is_self, uint32_t mode, uint32_t tag, float& bt, uint32_t& bcode) {
+    float3 oc = O - xyz(s);
+    float b = dot(D, oc);
+    float3 q = fma3(D, -b, oc);
+    float disc = s.w - dot(q, q);
+    if (disc > 0.f) {
+        float sq = fast_sqrt(disc);
+        float h0 = -b - sq, h1 = -b + sq;
+        bool near_ok = (h0 > 0.f) && !is_self;             // SP_SELF_FAR: only the far root
+        float t = near_ok ? h0 : h1;
+        bool ok = (t > 0.f) && !(is_self && mode != SP_SELF_FAR) && (t < bt);
+        if (ok) { bt = t; bcode = near_ok ? tag : (tag | 0x80000000u); }
+    }
 }
 
-SP_DEV void sp_intersect_chunk_tag(const float4* __restrict__ ch, float3 O, float3 D, int self_tag, uint32_t mode,
-                                   ChunkBest& best) {
-    const GeomChunkHeader* h = reinterpret_cast<const GeomChunkHeader*>(ch);
-    const int n_sphere = h->n_sphere, n_plane = h->n_plane, n_cuboid = h->n_cuboid, n_tri = h->n_tri;
+SP_DEV void sp_lean_plane(float4 a, float4 c, float4 u4, float4 v4, float3 O, float3 D, bool is_self, uint32_t tag,
+                          float& bt, uint32_t& bcode) {
+    float3 N = xyz(a), oc = O - xyz(c);
+    float nd = dot(N, D);
+    nd = (nd == 0.f) ? 1e-4f : nd;
+    float k = -dot(N, oc);
+    float t = __fdividef(k, nd);
+    float u = fmaf(t, dot(xyz(u4), D), dot(xyz(u4), oc));
+    float v = fmaf(t, dot(xyz(v4), D), dot(xyz(v4), oc));
+    bool ok = (fabsf(u) <= a.w) && (fabsf(v) <= c.w) && (k * nd > 0.f) && !is_self && (t < bt);
+    if (ok) { bt = t; bcode = nd < 0.f ? tag : (tag | 0x80000000u); }
+}
+
+SP_DEV void sp_lean_cuboid(float4 r0, float4 r1, float4 r2, float4 c, float4 e, float3 O, float3 D, bool is_self,
+                           uint32_t mode, uint32_t tag, float& bt, uint32_t& bcode) {
+    float3 oc = O - xyz(c);
+    float3 Ol = v3(dot(xyz(r0), oc), dot(xyz(r1), oc), dot(xyz(r2), oc));
+    float3 Dl = v3(dot(xyz(r0), D), dot(xyz(r1), D), dot(xyz(r2), D));
+    float ix = fast_rcp(Dl.x), iy = fast_rcp(Dl.y), iz = fast_rcp(Dl.z);   // +-inf for axis-parallel rays, as 1/0
+    float t1 = (r0.w - Ol.x) * ix, t2 = (c.w - Ol.x) * ix;
+    float t3 = (r1.w - Ol.y) * iy, t4 = (e.x - Ol.y) * iy;
+    float t5 = (r2.w - Ol.z) * iz, t6 = (e.y - Ol.z) * iz;
+    float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+    float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+    bool miss = (tmax < 0.f) || (tmin > tmax);
+    bool inside = (tmin < 0.f) || is_self;                 // SP_SELF_FAR: exit point only
+    float t = inside ? tmax : tmin;
+    bool ok = !miss && !(is_self && mode != SP_SELF_FAR) && (t < bt);
+    if (ok) { bt = t; bcode = inside ? (tag | 0x80000000u) : tag; }
+}
+
+SP_DEV void sp_lean_triangle(float4 m0, float4 m1, float4 m2, float3 O, float3 D, bool is_self, uint32_t tag, float& bt,
+                             uint32_t& bcode) {
+    float nd = dot(xyz(m2), D);
+    nd = (nd == 0.f) ? 1e-4f : nd;
+    const float w0 = dot(xyz(m2), O) + m2.w;
+    const float t = -w0 * fast_rcp(nd);
+    const float u = fmaf(t, dot(xyz(m0), D), dot(xyz(m0), O) + m0.w);
+    const float v = fmaf(t, dot(xyz(m1), D), dot(xyz(m1), O) + m1.w);
+    const bool ok = (u >= 0.f) && (v >= 0.f) && (u + v <= 1.f) && (t > 0.f) && !is_self && (t < bt);
+    if (ok) { bt = t; bcode = nd < 0.f ? tag : (tag | 0x80000000u); }
+}
+
+template <int A>
+SP_DEV void sp_lean_aa(const float4* __restrict__ aa, int first, int count, int self_i, float3 O, float3 D, float& bt,
+                       uint32_t& bcode) {
+    const float oa = A == 0 ? O.x : (A == 1 ? O.y : O.z), da = A == 0 ? D.x : (A == 1 ? D.y : D.z);
+    const float ob = A == 0 ? O.y : O.x, db = A == 0 ? D.y : D.x;
+    const float oc = A == 2 ? O.y : O.z, dc = A == 2 ? D.y : D.z;
+    const float inv_da = fast_rcp(da);                        // 1/0 = inf sends the hit point out of bounds
+    const uint32_t flip = __float_as_uint(da) & 0x80000000u;
+#pragma unroll 2
+    for (int i = first; i < first + count; ++i) {
+        const float4 r0 = aa[2 * i], r1 = aa[2 * i + 1];
+        const float ca = A == 0 ? r0.x : (A == 1 ? r0.y : r0.z);
+        const float cb = A == 0 ? r0.y : r0.x, cc = A == 2 ? r0.y : r0.z;
+        const float t = (ca - oa) * inv_da;
+        const float pb = fmaf(t, db, ob) - cb, pc = fmaf(t, dc, oc) - cc;
+        const bool ok = (fabsf(pb) <= r1.x) && (fabsf(pc) <= r1.y) && (t > 0.f) && (t < bt) && (i != self_i);
+        if (ok) { bt = t; bcode = __float_as_uint(r1.z) ^ flip; }
+    }
+}
+
+// Nearest hit over one staged chunk: bt = distance (+inf: none), bcode = tag | (inner face) << 31.
+SP_DEV void sp_intersect_lean(const float4* __restrict__ ch, float3 O, float3 D, int self_tag, uint32_t mode, float& bt,
+                              uint32_t& bcode) {
+    const int4 hn = *reinterpret_cast<const int4*>(ch);            // n_sphere n_plane n_cuboid n_tri
+    const int4 ho = *reinterpret_cast<const int4*>(ch + 1);        // off_sphere off_plane off_cuboid off_tri
     int tag = 0;
     {
-        const float4* sp = ch + h->off_sphere;
-#pragma unroll 4
-        for (int i = 0; i < n_sphere; ++i) sp_item_sphere(sp[i], O, D, i == self_tag, mode, i, best);
-        tag += n_sphere;
-    }
-    {
-        const float4* pl = ch + h->off_plane;
+        const float4* sp = ch + ho.x;
 #pragma unroll 2
-        for (int i = 0; i < n_plane; ++i)
-            sp_item_plane(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3], O, D, tag + i == self_tag, tag + i, best);
-        tag += n_plane;
+        for (int i = 0; i < hn.x; ++i) sp_lean_sphere(sp[i], O, D, i == self_tag, mode, (uint32_t)i, bt, bcode);
+        tag += hn.x;
     }
-    {
-        const float4* cb = ch + h->off_cuboid;
-        for (int i = 0; i < n_cuboid; ++i)
-            sp_item_cuboid(cb[5 * i], cb[5 * i + 1], cb[5 * i + 2], cb[5 * i + 3], cb[5 * i + 4], O, D, tag + i == self_tag,
-                           mode, tag + i, best);
-        tag += n_cuboid;
-    }
-    {
-        const float4* tr = ch + h->off_tri;
+    if (hn.y > 0) {
+        const float4* pl = ch + ho.y;
 #pragma unroll 2
-        for (int i = 0; i < n_tri; ++i)
-            sp_item_triangle(tr[3 * i], tr[3 * i + 1], tr[3 * i + 2], O, D, tag + i == self_tag, tag + i, best);
-        tag += n_tri;
+        for (int i = 0; i < hn.y; ++i)
+            sp_lean_plane(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3], O, D, tag + i == self_tag, (uint32_t)(tag + i), bt, bcode);
+        tag += hn.y;
     }
     {
-        const int n_aax = h->n_aax, n_aay = h->n_aay, n_aaz = h->n_aaz;
-        if (n_aax + n_aay + n_aaz > 0) {
-            const float4* aa = ch + h->off_aa;
-            if (n_aax > 0) sp_intersect_aa_tag<0>(aa, 0, n_aax, tag, O, D, fast_rcp(D.x), self_tag, best);
-            if (n_aay > 0) sp_intersect_aa_tag<1>(aa, n_aax, n_aay, tag, O, D, fast_rcp(D.y), self_tag, best);
-            if (n_aaz > 0) sp_intersect_aa_tag<2>(aa, n_aax + n_aay, n_aaz, tag, O, D, fast_rcp(D.z), self_tag, best);
-        }
+        const float4* cb = ch + ho.z;
+        for (int i = 0; i < hn.z; ++i)
+            sp_lean_cuboid(cb[5 * i], cb[5 * i + 1], cb[5 * i + 2], cb[5 * i + 3], cb[5 * i + 4], O, D, tag + i == self_tag,
+                           mode, (uint32_t)(tag + i), bt, bcode);
+        tag += hn.z;
+    }
+    if (hn.w > 0) {
+        const float4* tr = ch + ho.w;
+#pragma unroll 2
+        for (int i = 0; i < hn.w; ++i)
+            sp_lean_triangle(tr[3 * i], tr[3 * i + 1], tr[3 * i + 2], O, D, tag + i == self_tag, (uint32_t)(tag + i), bt, bcode);
+        tag += hn.w;
+    }
+    {
+        const int4 ha = *reinterpret_cast<const int4*>(ch + 2);    // off_ids n_vec4 n_aax n_aay
+        const int4 hb = *reinterpret_cast<const int4*>(ch + 3);    // n_aaz off_aa - -
+        const float4* aa = ch + hb.y;
+        const int self_i = self_tag - tag;
+        if (ha.z > 0) sp_lean_aa<0>(aa, 0, ha.z, self_i, O, D, bt, bcode);
+        if (ha.w > 0) sp_lean_aa<1>(aa, ha.z, ha.w, self_i, O, D, bt, bcode);
+        if (hb.x > 0) sp_lean_aa<2>(aa, ha.z + ha.w, hb.x, self_i, O, D, bt, bcode);
     }
 }
 

@@ -36,6 +36,8 @@
 struct WarpShared {
     uint32_t stash[SPW_WARPS][SPW_STASH_WORDS][SPW_STASH_CAP];
     uint32_t slab[SPW_WARPS][SPW_N_QUEUES][2];     // per warp and output queue: next free slot, end of the slab
+    uint32_t seg[SPW_N_QUEUES][8];                 // per work-item segment: SPW_SEG_* constants
+    float4 cinfo[SPW_MAX_COLLIDERS];               // DColInfo of every collider
     float2 src_info[SPW_MAX_COLLIDERS];            // per collider: position in the chunk's id array (as int bits), cosine-pdf weight
     float4 lite[SPW_MAX_COLLIDERS];                // per collider: albedo / emitted colour, 1 / diffuse_rays
 };
@@ -123,37 +125,55 @@ __device__ __noinline__ void sp_shade_stash(const DScene* scp, const LevelArgs* 
     }
 }
 
-template <uint32_t FEAT>
-__global__ void __launch_bounds__(SPW_BLOCK, 4)
+SP_DEV uint32_t sp_lane_id() { uint32_t r; asm("mov.u32 %0, %%laneid;" : "=r"(r)); return r; }
+SP_DEV uint32_t sp_lanemask_lt() { uint32_t r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
+
+// per-segment constants (shared memory, read where they are needed instead of living in registers)
+enum { SPW_SEG_ITEMS = 0, SPW_SEG_MULT, SPW_SEG_BASE, SPW_SEG_INV24, SPW_SEG_STEP_REC, SPW_SEG_STEP_REM, SPW_SEG_SLAB, SPW_SEG_WORDS = 8 };
+
+template <uint32_t FEAT, int CTAS>
+__global__ void __launch_bounds__(SPW_BLOCK, CTAS)
 sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
     static_assert((FEAT & ~(SP_F_DIFFUSE | SP_F_REFR)) == 0u, "inline shading covers untextured Diffuse / Emissive only");
     extern __shared__ float4 s_geom[];
     __shared__ WarpShared sh;
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t tid = threadIdx.x;
 
     // ---- work items of this launch -------------------------------------------------------------------
     const uint32_t n_rays = min(__ldg(a.in_counts), a.in_rays.capacity);
     uint32_t total = n_rays;
     for (int c = 0; c < sc.n_fan_classes; ++c) total += min(__ldg(a.in_counts + 1 + c), a.in_fan_cap[c]) * (uint32_t)sc.fan_mult[c];
     if (total == 0u) return;
-    // slots per slab: about an eighth of what a warp can emit in this launch, so that the unused tails stay a
-    // few per cent of the queue even for small launches; a power of two in [32, 256]
-    uint32_t slab_size = 32u;
-    {
-        const uint32_t per_warp = total / (gridDim.x * SPW_WARPS * 8u);
-        while (slab_size < 256u && slab_size * 2u <= per_warp) slab_size *= 2u;
-    }
 
     sp_stage_chunk(s_geom, sc, sc.all, 0);
     for (uint32_t i = tid; i < (uint32_t)sc.n_colliders; i += SPW_BLOCK) {
         const float4 raw = __ldg(reinterpret_cast<const float4*>(sc.col_info + i));
-        const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
-        sh.src_info[i].y = ci.w_cos;
+        sh.cinfo[i] = raw;
+        sh.src_info[i].y = reinterpret_cast<const DColInfo*>(&raw)->w_cos;
         sh.lite[i] = __ldg(sc.col_lite + i);
     }
     if (tid < SPW_WARPS * SPW_N_QUEUES * 2) reinterpret_cast<uint32_t*>(sh.slab)[tid] = 0u;
+    if (tid <= (uint32_t)sc.n_fan_classes) {
+        // slots per slab: about an eighth of what a warp can emit in this launch, so that the unused tails stay a
+        // few per cent of the queue even for small launches; a power of two in [32, 256]
+        uint32_t slab_size = 32u;
+        const uint32_t per_warp = total / (gridDim.x * SPW_WARPS * 8u);
+        while (slab_size < 256u && slab_size * 2u <= per_warp) slab_size *= 2u;
+        // segment 0: explicit ray records; segment 1 + c: the children of fan class c
+        const uint32_t stride = gridDim.x * SPW_WARPS * 32u;
+        uint32_t mult = 1u, n_items = n_rays, fan_base = 0u;
+        if (tid > 0) {
+            mult = (uint32_t)sc.fan_mult[tid - 1];
+            n_items = min(__ldg(a.in_counts + tid), a.in_fan_cap[tid - 1]) * mult;
+            fan_base = a.in_fan_base[tid - 1];
+        }
+        uint32_t* sg = sh.seg[tid];
+        sg[SPW_SEG_ITEMS] = n_items; sg[SPW_SEG_MULT] = mult; sg[SPW_SEG_BASE] = fan_base;
+        sg[SPW_SEG_INV24] = (1u << 24) / mult + 1u;            // floor(x / mult) == (x * inv24) >> 24 for x * mult < 2^24
+        sg[SPW_SEG_STEP_REC] = stride / mult; sg[SPW_SEG_STEP_REM] = stride % mult;
+        sg[SPW_SEG_SLAB] = slab_size;
+    }
     __syncthreads();
     {
         const GeomChunkHeader* gh = reinterpret_cast<const GeomChunkHeader*>(s_geom);
@@ -163,35 +183,29 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
     }
     __syncthreads();
 
+    const uint32_t warp = tid >> 5;
     uint32_t* const stash = &sh.stash[warp][0][0];
     uint32_t* const slabs = &sh.slab[warp][0][0];
     uint32_t n_st = 0;                                         // entries in the stash (warp-uniform)
-    unsigned long long traced = 0;
-    const uint32_t n_warps = gridDim.x * SPW_WARPS;
-    const uint32_t stride = n_warps * 32u;
+    uint32_t traced = 0;
+    const uint32_t stride = gridDim.x * SPW_WARPS * 32u;
 
     for (int seg = 0; seg <= sc.n_fan_classes; ++seg) {
-        // segment 0: explicit ray records; segment 1 + c: the children of fan class c
-        uint32_t mult = 1u, n_items = n_rays, fan_base = 0u;
-        if (seg > 0) {
-            mult = (uint32_t)sc.fan_mult[seg - 1];
-            n_items = min(__ldg(a.in_counts + seg), a.in_fan_cap[seg - 1]) * mult;
-            fan_base = a.in_fan_base[seg - 1];
-        }
+        const volatile uint32_t* sg = sh.seg[seg];
+        const uint32_t n_items = sg[SPW_SEG_ITEMS];
         // item = rec * mult + child, kept up to date incrementally: (rec0, rem0) belong to the warp's first item
-        const uint32_t inv24 = (1u << 24) / mult + 1u;         // floor(x / mult) == (x * inv24) >> 24 for x * mult < 2^24
-        const uint32_t step_rec = stride / mult, step_rem = stride % mult;
         uint32_t wb = (blockIdx.x * SPW_WARPS + warp) * 32u;
-        uint32_t rec0 = wb / mult, rem0 = wb % mult;
+        uint32_t rec0 = wb / sg[SPW_SEG_MULT], rem0 = wb % sg[SPW_SEG_MULT];
 #pragma unroll 1
         for (; wb < n_items; wb += stride) {
-            const uint32_t item = wb + lane;
-            bool active = item < n_items;
+            const uint32_t lane = sp_lane_id();
+            bool active = wb + lane < n_items;
             Ray r;
             r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
             // ---- 1. the ray of this item -----------------------------------------------------------------
             if (seg == 0) {
                 if (active) {
+                    const uint32_t item = wb + lane;
                     const float4 q2 = a.in_rays.q2[item];
                     r.meta = __float_as_uint(q2.w);
                     if (r.meta == SP_META_DEAD) {
@@ -203,13 +217,14 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                     }
                 }
             } else {
+                const uint32_t mult = sg[SPW_SEG_MULT];
                 const uint32_t x = rem0 + lane;
-                const uint32_t qd = (x * inv24) >> 24;
+                const uint32_t qd = (x * sg[SPW_SEG_INV24]) >> 24;
                 const uint32_t rec = rec0 + qd, child = x - qd * mult;
-                rec0 += step_rec; rem0 += step_rem;
+                rec0 += sg[SPW_SEG_STEP_REC]; rem0 += sg[SPW_SEG_STEP_REM];
                 if (rem0 >= mult) { rem0 -= mult; rec0 += 1u; }
                 if (active) {
-                    const uint32_t s = fan_base + rec;
+                    const uint32_t s = sg[SPW_SEG_BASE] + rec;
                     const float4 q2 = a.in_fans.q2[s];
                     r.meta = __float_as_uint(q2.w);
                     if (r.meta == SP_META_DEAD) {
@@ -228,47 +243,43 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             }
 
             // ---- 2. nearest hit over the chunk --------------------------------------------------------------
-            HitRec hit; hit.t = SP_INF; hit.id = -1; hit.orient = 0;
+            float hit_t = SP_INF;
+            int hit_id = -1;
+            bool outer = true;                                 // hit.orient > 0
             if (active) {
                 const uint32_t src = meta_src(r.meta), mode = meta_mode(r.meta);
                 int self_tag = -1;
-                bool need_test = true;
-                if (src != SP_SRC_NONE) {
-                    if (mode == SP_SELF_ZERO) {
-                        // the ray dives back into the surface it starts on: immediate hit at t = 0 (sp_kernels.cu)
-                        const DCollider& c0 = sc.colliders[src];
-                        float3 Nc = to_f3(sp_collider_normal<float>(c0.type, c0.p, from_f3<float>(r.o)));
-                        hit.t = 0.f; hit.id = (int)src; hit.orient = dot(r.d, Nc) < 0.f ? 1 : -1;
-                        need_test = false;
-                    } else {
-                        self_tag = __float_as_int(sh.src_info[src].x);
+                if (src != SP_SRC_NONE) self_tag = __float_as_int(sh.src_info[src].x);
+                if (src != SP_SRC_NONE && mode == SP_SELF_ZERO) {
+                    // the ray dives back into the surface it starts on: immediate hit at t = 0 (sp_kernels.cu)
+                    const DCollider& c0 = sc.colliders[src];
+                    float3 Nc = to_f3(sp_collider_normal<float>(c0.type, c0.p, from_f3<float>(r.o)));
+                    hit_t = 0.f; hit_id = (int)src; outer = dot(r.d, Nc) < 0.f;
+                } else {
+                    uint32_t bcode = 0xFFFFFFFFu;
+                    sp_intersect_lean(s_geom, r.o, r.d, self_tag, mode, hit_t, bcode);
+                    if (hit_t < SP_INF) {
+                        hit_id = reinterpret_cast<const int*>(s_geom + reinterpret_cast<const GeomChunkHeader*>(s_geom)->off_ids)[bcode & 0x7FFFFFFFu];
+                        outer = (bcode & 0x80000000u) == 0u;
                     }
                 }
-                if (need_test) {
-                    ChunkBest best; best.t = SP_INF; best.idx = -1; best.orient = 0;
-                    sp_intersect_chunk_tag(s_geom, r.o, r.d, self_tag, mode, best);
-                    if (best.idx >= 0) { hit.t = best.t; hit.orient = best.orient; hit.id = sp_chunk_id(s_geom, best.idx); }
-                }
-                traced += 1;
+                traced += 1u;
             }
 
             // ---- 3. what the hit does -------------------------------------------------------------------------
             int fan_class = -1;
             bool glass = false;
-            float4 lite = make_float4(0.f, 0.f, 0.f, 1.f);
             uint32_t ctype = 0u;
-            if (active && hit.id >= 0) {
-                const float4 raw = __ldg(reinterpret_cast<const float4*>(sc.col_info + hit.id));
+            if (hit_id >= 0) {
+                const float4 raw = sh.cinfo[hit_id];
                 const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
                 const uint32_t depth = meta_depth(r.meta), dr = meta_dr(r.meta);
                 ctype = ci.type;
                 if (ci.kind == SP_MAT_DIFFUSE) {
                     if (dr < 1u) fan_class = ci.fan_class;
                     else if ((int)dr < (int)ci.max_dr) fan_class = 0;
-                    if (fan_class >= 0) lite = sh.lite[hit.id];
                 } else if (ci.kind == SP_MAT_EMISSIVE) {          // emissive.py:21-23
-                    lite = sh.lite[hit.id];
-                    const float3 add = r.thr * xyz(lite);
+                    const float3 add = r.thr * xyz(sh.lite[hit_id]);
                     float* px = reinterpret_cast<float*>(a.accum + r.pix);
                     if (add.x != 0.f) atomicAdd(px, add.x);
                     if (add.y != 0.f) atomicAdd(px + 1, add.y);
@@ -285,23 +296,24 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                     const int c = __shfl_sync(0xffffffffu, fan_class, __ffs(todo) - 1);
                     const uint32_t bc = __ballot_sync(0xffffffffu, fan_class == c);
                     todo &= ~bc;
-                    const SlabGrant g = sp_slab_alloc(slabs + 2 * (1 + c), __popc(bc), 1u + (uint32_t)c, slab_size, a.out, lane);
+                    const SlabGrant g = sp_slab_alloc(slabs + 2 * (1 + c), __popc(bc), 1u + (uint32_t)c, sg[SPW_SEG_SLAB], a.out, lane);
                     if (fan_class == c) {
-                        const uint32_t slot = sp_slab_pos(g, __popc(bc & lt_mask));
+                        const uint32_t slot = sp_slab_pos(g, __popc(bc & sp_lanemask_lt()));
                         if (slot != SP_SLOT_NONE) {
+                            const float4 lite = sh.lite[hit_id];
                             const float inv_m = (meta_dr(r.meta) < 1u) ? lite.w : 1.f;
                             const float3 thr = r.thr * xyz(lite) * inv_m;
                             if (any_nonzero(thr)) {
-                                const DCollider& col = sc.colliders[hit.id];
-                                const float3 P = fma3(r.d, hit.t, r.o);
+                                const DCollider& col = sc.colliders[hit_id];
+                                const float3 P = fma3(r.d, hit_t, r.o);
                                 const float3 Nc = to_f3(sp_collider_normal<float>((int)ctype, col.p, from_f3<float>(P)));
-                                const float orient = (float)hit.orient;
-                                const float3 N = Nc * orient;
-                                const float side_plus = dot(N, Nc) >= 0.f ? 1.f : -1.f;
+                                const float3 N = outer ? Nc : -Nc;
+                                // sampled directions lie in the hemisphere of N: they leave a planar / outer surface
+                                // and cross the interior of a convex collider hit from inside (sp_shade.cuh)
                                 const bool planar = (ctype == SP_COLLIDER_PLANE || ctype == SP_COLLIDER_TRIANGLE);
-                                const uint32_t mode = (planar || side_plus > 0.f) ? SP_SELF_SKIP : SP_SELF_FAR;
+                                const uint32_t mode = (planar || outer) ? SP_SELF_SKIP : SP_SELF_FAR;
                                 const uint32_t meta = sp_pack_meta(meta_depth(r.meta) + 1u, meta_dr(r.meta) + 1u, meta_medium(r.meta),
-                                                                   (uint32_t)hit.id, mode);
+                                                                   (uint32_t)hit_id, mode);
                                 sp_write_record(a.out.fans, slot, fma3(N, 1e-6f, P), N, thr, r.pix, r.path, meta);
                             } else {
                                 sp_write_dead(a.out.fans, slot);
@@ -316,19 +328,19 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                 const uint32_t bg = __ballot_sync(0xffffffffu, glass);
                 if (bg) {
                     if (glass) {
-                        uint32_t* st = stash + n_st + __popc(bg & lt_mask);
+                        uint32_t* st = stash + n_st + __popc(bg & sp_lanemask_lt());
                         st[0 * SPW_STASH_CAP] = __float_as_uint(r.o.x); st[1 * SPW_STASH_CAP] = __float_as_uint(r.o.y); st[2 * SPW_STASH_CAP] = __float_as_uint(r.o.z);
                         st[3 * SPW_STASH_CAP] = __float_as_uint(r.d.x); st[4 * SPW_STASH_CAP] = __float_as_uint(r.d.y); st[5 * SPW_STASH_CAP] = __float_as_uint(r.d.z);
                         st[6 * SPW_STASH_CAP] = __float_as_uint(r.thr.x); st[7 * SPW_STASH_CAP] = __float_as_uint(r.thr.y); st[8 * SPW_STASH_CAP] = __float_as_uint(r.thr.z);
                         st[9 * SPW_STASH_CAP] = r.pix; st[10 * SPW_STASH_CAP] = r.path; st[11 * SPW_STASH_CAP] = r.meta;
-                        st[12 * SPW_STASH_CAP] = __float_as_uint(hit.t);
-                        st[13 * SPW_STASH_CAP] = (uint32_t)hit.id | (hit.orient > 0 ? 0x80000000u : 0u);
+                        st[12 * SPW_STASH_CAP] = __float_as_uint(hit_t);
+                        st[13 * SPW_STASH_CAP] = (uint32_t)hit_id | (outer ? 0x80000000u : 0u);
                     }
                     n_st += __popc(bg);
                     __syncwarp();
                     if (n_st >= 32u) {
                         n_st -= 32u;
-                        sp_shade_stash<SP_F_REFR>(&sc, &a, stash, slabs, n_st, 32u, slab_size, lane);
+                        sp_shade_stash<SP_F_REFR>(&sc, &a, stash, slabs, n_st, 32u, sg[SPW_SEG_SLAB], lane);
                     }
                 }
             }
@@ -336,7 +348,8 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
     }
 
     // ---- drain: what is left in the stash, then the unused tails of the slabs ---------------------------------
-    if (n_st) sp_shade_stash<SP_F_REFR>(&sc, &a, stash, slabs, 0u, n_st, slab_size, lane);
+    const uint32_t lane = sp_lane_id();
+    if (n_st) sp_shade_stash<SP_F_REFR>(&sc, &a, stash, slabs, 0u, n_st, sh.seg[0][SPW_SEG_SLAB], lane);
     __syncwarp();
     for (uint32_t q = 0; q < SPW_N_QUEUES; ++q) {
         const uint32_t next = slabs[2 * q], end = slabs[2 * q + 1];
@@ -345,5 +358,5 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
-    if (lane == 0 && traced) atomicAdd(&a.out.stats->rays[a.level], traced);
+    if (lane == 0 && traced) atomicAdd(&a.out.stats->rays[a.level], (unsigned long long)traced);
 }
