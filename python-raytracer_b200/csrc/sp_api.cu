@@ -1078,6 +1078,10 @@ static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what
     CUDA_TRY(cudaSetDevice(g_device));
     s->d.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull);
     s->d.seed_hi = (uint32_t)(seed >> 32);
+    for (uint32_t r = 0; r < 10; ++r) {
+        s->d.philox_keys[2 * r] = s->d.seed_lo + r * 0x9E3779B9u;
+        s->d.philox_keys[2 * r + 1] = s->d.seed_hi + r * 0xBB67AE85u;
+    }
     if (st) memset(st, 0, sizeof *st);
     CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
     return ensure_queues(s, primaries);

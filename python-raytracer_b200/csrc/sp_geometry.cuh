@@ -217,21 +217,21 @@ SP_DEV void sp_lean_triangle(float4 m0, float4 m1, float4 m2, float3 O, float3 D
 }
 
 template <int A>
-SP_DEV void sp_lean_aa(const float4* __restrict__ aa, int first, int count, int self_i, float3 O, float3 D, float& bt,
-                       uint32_t& bcode) {
+SP_DEV void sp_lean_aa(const float4* __restrict__ p, const float4* __restrict__ end, const float4* __restrict__ self_p,
+                       float3 O, float3 D, float& bt, uint32_t& bcode) {
     const float oa = A == 0 ? O.x : (A == 1 ? O.y : O.z), da = A == 0 ? D.x : (A == 1 ? D.y : D.z);
     const float ob = A == 0 ? O.y : O.x, db = A == 0 ? D.y : D.x;
     const float oc = A == 2 ? O.y : O.z, dc = A == 2 ? D.y : D.z;
     const float inv_da = fast_rcp(da);                        // 1/0 = inf sends the hit point out of bounds
     const uint32_t flip = __float_as_uint(da) & 0x80000000u;
-#pragma unroll 2
-    for (int i = first; i < first + count; ++i) {
-        const float4 r0 = aa[2 * i], r1 = aa[2 * i + 1];
+#pragma unroll 1
+    for (; p != end; p += 2) {
+        const float4 r0 = p[0], r1 = p[1];
         const float ca = A == 0 ? r0.x : (A == 1 ? r0.y : r0.z);
         const float cb = A == 0 ? r0.y : r0.x, cc = A == 2 ? r0.y : r0.z;
         const float t = (ca - oa) * inv_da;
         const float pb = fmaf(t, db, ob) - cb, pc = fmaf(t, dc, oc) - cc;
-        const bool ok = (fabsf(pb) <= r1.x) && (fabsf(pc) <= r1.y) && (t > 0.f) && (t < bt) && (i != self_i);
+        const bool ok = (fabsf(pb) <= r1.x) && (fabsf(pc) <= r1.y) && (t > 0.f) && (t < bt) && (p != self_p);
         if (ok) { bt = t; bcode = __float_as_uint(r1.z) ^ flip; }
     }
 }
@@ -244,7 +244,7 @@ SP_DEV void sp_intersect_lean(const float4* __restrict__ ch, float3 O, float3 D,
     int tag = 0;
     {
         const float4* sp = ch + ho.x;
-#pragma unroll 2
+#pragma unroll 1
         for (int i = 0; i < hn.x; ++i) sp_lean_sphere(sp[i], O, D, i == self_tag, mode, (uint32_t)i, bt, bcode);
         tag += hn.x;
     }
@@ -273,10 +273,13 @@ SP_DEV void sp_intersect_lean(const float4* __restrict__ ch, float3 O, float3 D,
         const int4 ha = *reinterpret_cast<const int4*>(ch + 2);    // off_ids n_vec4 n_aax n_aay
         const int4 hb = *reinterpret_cast<const int4*>(ch + 3);    // n_aaz off_aa - -
         const float4* aa = ch + hb.y;
-        const int self_i = self_tag - tag;
-        if (ha.z > 0) sp_lean_aa<0>(aa, 0, ha.z, self_i, O, D, bt, bcode);
-        if (ha.w > 0) sp_lean_aa<1>(aa, ha.z, ha.w, self_i, O, D, bt, bcode);
-        if (hb.x > 0) sp_lean_aa<2>(aa, ha.z + ha.w, hb.x, self_i, O, D, bt, bcode);
+        const float4* self_p = aa + 2 * (self_tag - tag);         // outside the section if the source is not a rectangle
+        const float4* e0 = aa + 2 * ha.z;
+        const float4* e1 = e0 + 2 * ha.w;
+        const float4* e2 = e1 + 2 * hb.x;
+        sp_lean_aa<0>(aa, e0, self_p, O, D, bt, bcode);
+        sp_lean_aa<1>(e0, e1, self_p, O, D, bt, bcode);
+        sp_lean_aa<2>(e1, e2, self_p, O, D, bt, bcode);
     }
 }
 

@@ -31,6 +31,25 @@ SP_DEV uint32_t sp_child_path(uint32_t path, uint32_t k) {
 }
 SP_DEV uint32_t sp_root_path(uint32_t sample) { return sp_child_path(0x811C9DC5u, sample); }
 
+// The same generator with the ten round keys (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85) read from a table the
+// host fills per call (DScene::philox_keys, kernel parameter space): the key schedule costs no instructions.
+SP_DEV void sp_philox4x32_10_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* __restrict__ keys,
+                                   uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ keys[2 * r]; c1 = lo1; c2 = hi0 ^ c3 ^ keys[2 * r + 1]; c3 = lo0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+SP_DEV void sp_draw4_keys(uint32_t pix, uint32_t path, uint32_t block, const uint32_t* __restrict__ keys, float u[4]) {
+    uint32_t w[4];
+    sp_philox4x32_10_keys(pix, path, block, 0u, keys, w);
+    u[0] = sp_u01(w[0]); u[1] = sp_u01(w[1]); u[2] = sp_u01(w[2]); u[3] = sp_u01(w[3]);
+}
+
 SP_DEV void sp_draw4(uint32_t pix, uint32_t path, uint32_t block, uint32_t k0, uint32_t k1, float u[4]) {
     uint32_t w[4];
     sp_philox4x32_10(pix, path, block, 0u, k0, k1, w);

@@ -40,7 +40,7 @@ SP_DEV void sp_camera_ray(const DCamera& cam, uint32_t pixel, uint32_t sample, u
 SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float w_cos, uint32_t pix,
                                uint32_t path, float3& dir) {
     float u[4];
-    sp_draw4(pix, path, SP_BLOCK_DIRECTION, sc.seed_lo, sc.seed_hi, u);
+    sp_draw4_keys(pix, path, SP_BLOCK_DIRECTION, sc.philox_keys, u);
     float sn, cs;
     fast_sincos_2pi(u[1], sn, cs);
     const int l = sc.n_importance;

@@ -352,7 +352,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
         uint32_t mode_t = sp_self_mode(ctype, -side_plus, dot(Tdir, g.Nc), zo);
         if (prim.mc) {
             float u[4];
-            sp_draw4(r.pix, r.path, SP_BLOCK_MATERIAL, sc.seed_lo, sc.seed_hi, u);
+            sp_draw4_keys(r.pix, r.path, SP_BLOCK_MATERIAL, sc.philox_keys, u);
             bool pick = (u[0] > (F.x + F.y + F.z) / 3.f) && non_tir;
             if (pick) sp_emit_ray(cx_, r, nudged_in, Tdir, thr, 0u, med2, dr, h.id, mode_t);
             else      sp_emit_ray(cx_, r, nudged, R, thr, 0u, medium, dr, h.id, mode_refl);

@@ -124,6 +124,7 @@ struct DScene {
     unsigned long long fan_magic[SP_MAX_FAN_CLASSES];   // ceil(2^64 / fan_mult): n / mult == __umul64hi(n, magic) for n < 2^32
     int fan_mult[SP_MAX_FAN_CLASSES];     // rays per fan record of each class (class 0: 1)
     uint32_t seed_lo, seed_hi;
+    uint32_t philox_keys[20];          // the ten Philox round key pairs of (seed_lo, seed_hi), filled per call
 };
 
 // ---- kernel specialisation ------------------------------------------------------------------------

@@ -37,8 +37,9 @@ struct WarpShared {
     uint32_t stash[SPW_WARPS][SPW_STASH_WORDS][SPW_STASH_CAP];
     uint32_t slab[SPW_WARPS][SPW_N_QUEUES][2];     // per warp and output queue: next free slot, end of the slab
     uint32_t seg[SPW_N_QUEUES][8];                 // per work-item segment: SPW_SEG_* constants
-    float4 cinfo[SPW_MAX_COLLIDERS];               // DColInfo of every collider
+    uint2 cls[SPW_MAX_COLLIDERS];                  // per collider: what a hit does (sp_hit_class below)
     float2 src_info[SPW_MAX_COLLIDERS];            // per collider: position in the chunk's id array (as int bits), cosine-pdf weight
+    int ids[SPW_MAX_COLLIDERS];                    // position in the chunk's id array -> collider id
     float4 lite[SPW_MAX_COLLIDERS];                // per collider: albedo / emitted colour, 1 / diffuse_rays
 };
 
@@ -52,9 +53,8 @@ SP_DEV uint32_t sp_slab_pos(const SlabGrant& g, uint32_t x) {
 
 SP_DEV SlabGrant sp_slab_alloc(uint32_t* slab, uint32_t tot, uint32_t q, uint32_t slab_size, const LevelOut& out, uint32_t lane) {
     SlabGrant g;
-    const uint32_t next = slab[0], end = slab[1];
-    g.first = next; g.rem = end - next; g.fresh = SP_SLOT_NONE;
-    uint32_t new_next = next + tot, new_end = end;
+    uint2 st = *reinterpret_cast<const uint2*>(slab);         // x = next free slot, y = end of the slab
+    g.first = st.x; g.rem = st.y - st.x; g.fresh = SP_SLOT_NONE;
     if (tot > g.rem) {                                        // warp-uniform: finish this slab, open another
         uint32_t b = 0;
         if (lane == 0) {
@@ -65,13 +65,36 @@ SP_DEV SlabGrant sp_slab_alloc(uint32_t* slab, uint32_t tot, uint32_t q, uint32_
         }
         b = __shfl_sync(0xffffffffu, b, 0);
         g.fresh = b;
-        if (b == SP_SLOT_NONE) { new_next = 0u; new_end = 0u; }
-        else { new_next = b + (tot - g.rem); new_end = b + slab_size; }
+        st.x = b + (tot - g.rem); st.y = b + slab_size;
+        if (b == SP_SLOT_NONE) st.x = st.y = 0u;
+    } else {
+        st.x += tot;
     }
     __syncwarp();
-    if (lane == 0) { slab[0] = new_next; slab[1] = new_end; }
+    *reinterpret_cast<uint2*>(slab) = st;                     // every lane writes the same value
     __syncwarp();
     return g;
+}
+
+// What a hit on a collider does, as two words the level loop can test with a few instructions:
+//   x: byte d = fan class a Diffuse hit emits for a ray with diffuse_reflections == d (diffuse.py:34, 85), 0xFF = none
+//   y: [0:8) max_ray_depth if the material is Refractive (refractive.py:38) else 0, bit 8 Emissive, [16:24) collider type
+SP_DEV uint2 sp_hit_class(const DColInfo& ci) {
+    uint32_t fan = 0xFFFFFFFFu, misc = (uint32_t)ci.type << 16;
+    if (ci.kind == SP_MAT_DIFFUSE) {
+        fan = 0u;
+        for (int dr = 0; dr < 4; ++dr) {
+            uint32_t c = 0xFFu;
+            if (dr < 1) c = ci.fan_class;
+            else if (dr < (int)ci.max_dr) c = 0u;
+            fan |= c << (8 * dr);
+        }
+    } else if (ci.kind == SP_MAT_EMISSIVE) {
+        misc |= 0x100u;
+    } else if (ci.kind == SP_MAT_REFRACTIVE) {
+        misc |= (uint32_t)min(max((int)ci.max_ray_depth, 0), 255);
+    }
+    return make_uint2(fan, misc);
 }
 
 // Shade the top n (<= 32) entries of the warp's stash: all Refractive hits that can still spawn children.
@@ -149,7 +172,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
     sp_stage_chunk(s_geom, sc, sc.all, 0);
     for (uint32_t i = tid; i < (uint32_t)sc.n_colliders; i += SPW_BLOCK) {
         const float4 raw = __ldg(reinterpret_cast<const float4*>(sc.col_info + i));
-        sh.cinfo[i] = raw;
+        sh.cls[i] = sp_hit_class(*reinterpret_cast<const DColInfo*>(&raw));
         sh.src_info[i].y = reinterpret_cast<const DColInfo*>(&raw)->w_cos;
         sh.lite[i] = __ldg(sc.col_lite + i);
     }
@@ -179,7 +202,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
         const GeomChunkHeader* gh = reinterpret_cast<const GeomChunkHeader*>(s_geom);
         const int n_items = gh->n_sphere + gh->n_plane + gh->n_cuboid + gh->n_tri + gh->n_aax + gh->n_aay + gh->n_aaz;
         const int* ids = reinterpret_cast<const int*>(s_geom + gh->off_ids);
-        for (int k = (int)tid; k < n_items; k += SPW_BLOCK) sh.src_info[ids[k]].x = __int_as_float(k);
+        for (int k = (int)tid; k < n_items; k += SPW_BLOCK) { sh.src_info[ids[k]].x = __int_as_float(k); sh.ids[k] = ids[k]; }
     }
     __syncthreads();
 
@@ -202,6 +225,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             bool active = wb + lane < n_items;
             Ray r;
             r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
+            int self_tag = -1;                                 // the source collider's position in the chunk's id array
             // ---- 1. the ray of this item -----------------------------------------------------------------
             if (seg == 0) {
                 if (active) {
@@ -214,6 +238,8 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                         const float4 q0 = a.in_rays.q0[item], q1 = a.in_rays.q1[item];
                         r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
                         r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
+                        const uint32_t src = meta_src(r.meta);
+                        if (src != SP_SRC_NONE) self_tag = __float_as_int(sh.src_info[src].x);
                     }
                 }
             } else {
@@ -234,8 +260,9 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                         r.o = xyz(q0); r.thr = xyz(q2);
                         r.pix = __float_as_uint(q0.w);
                         r.path = sp_child_path(__float_as_uint(q1.w), child);
-                        const float w_cos = sh.src_info[meta_src(r.meta)].y;
-                        const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), w_cos, r.pix, r.path, r.d);
+                        const float2 si = sh.src_info[meta_src(r.meta)];      // fan records always name their source
+                        self_tag = __float_as_int(si.x);
+                        const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), si.y, r.pix, r.path, r.d);
                         r.thr = r.thr * weight;
                         active = weight > 0.f;                 // zero-weight samples cannot contribute: not traced
                     }
@@ -247,11 +274,10 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             int hit_id = -1;
             bool outer = true;                                 // hit.orient > 0
             if (active) {
-                const uint32_t src = meta_src(r.meta), mode = meta_mode(r.meta);
-                int self_tag = -1;
-                if (src != SP_SRC_NONE) self_tag = __float_as_int(sh.src_info[src].x);
-                if (src != SP_SRC_NONE && mode == SP_SELF_ZERO) {
+                const uint32_t mode = meta_mode(r.meta);
+                if (self_tag >= 0 && mode == SP_SELF_ZERO) {
                     // the ray dives back into the surface it starts on: immediate hit at t = 0 (sp_kernels.cu)
+                    const uint32_t src = meta_src(r.meta);
                     const DCollider& c0 = sc.colliders[src];
                     float3 Nc = to_f3(sp_collider_normal<float>(c0.type, c0.p, from_f3<float>(r.o)));
                     hit_t = 0.f; hit_id = (int)src; outer = dot(r.d, Nc) < 0.f;
@@ -259,7 +285,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                     uint32_t bcode = 0xFFFFFFFFu;
                     sp_intersect_lean(s_geom, r.o, r.d, self_tag, mode, hit_t, bcode);
                     if (hit_t < SP_INF) {
-                        hit_id = reinterpret_cast<const int*>(s_geom + reinterpret_cast<const GeomChunkHeader*>(s_geom)->off_ids)[bcode & 0x7FFFFFFFu];
+                        hit_id = sh.ids[bcode & 0x7FFFFFFFu];
                         outer = (bcode & 0x80000000u) == 0u;
                     }
                 }
@@ -271,54 +297,53 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             bool glass = false;
             uint32_t ctype = 0u;
             if (hit_id >= 0) {
-                const float4 raw = sh.cinfo[hit_id];
-                const DColInfo ci = *reinterpret_cast<const DColInfo*>(&raw);
-                const uint32_t depth = meta_depth(r.meta), dr = meta_dr(r.meta);
-                ctype = ci.type;
-                if (ci.kind == SP_MAT_DIFFUSE) {
-                    if (dr < 1u) fan_class = ci.fan_class;
-                    else if ((int)dr < (int)ci.max_dr) fan_class = 0;
-                } else if (ci.kind == SP_MAT_EMISSIVE) {          // emissive.py:21-23
+                const uint2 hc = sh.cls[hit_id];
+                ctype = (hc.y >> 16) & 255u;
+                fan_class = (int)(int8_t)(hc.x >> ((r.meta >> 3) & 24u));          // byte diffuse_reflections of the fan word
+                glass = meta_depth(r.meta) < (hc.y & 255u);
+                if (hc.y & 0x100u) {                              // emissive.py:21-23
                     const float3 add = r.thr * xyz(sh.lite[hit_id]);
                     float* px = reinterpret_cast<float*>(a.accum + r.pix);
                     if (add.x != 0.f) atomicAdd(px, add.x);
                     if (add.y != 0.f) atomicAdd(px + 1, add.y);
                     if (add.z != 0.f) atomicAdd(px + 2, add.z);
-                } else {                                          // Refractive; black past max_ray_depth (refractive.py:38)
-                    glass = (int)depth < (int)ci.max_ray_depth;
                 }
             }
 
             // ---- 4. Diffuse hits: fan record for the next level (diffuse.py:25-124) ----------------------------
             {
-                uint32_t todo = __ballot_sync(0xffffffffu, fan_class >= 0);
-                while (todo) {                                    // one round per fan class present in the warp
+                uint32_t slot = SP_SLOT_NONE;
+                const uint32_t b0 = __ballot_sync(0xffffffffu, fan_class == 0);     // single-ray fans: the common case
+                if (b0) {
+                    const SlabGrant g = sp_slab_alloc(slabs + 2, __popc(b0), 1u, sg[SPW_SEG_SLAB], a.out, lane);
+                    if (fan_class == 0) slot = sp_slab_pos(g, __popc(b0 & sp_lanemask_lt()));
+                }
+                uint32_t todo = __ballot_sync(0xffffffffu, fan_class > 0);
+                while (todo) {                                    // one round per other fan class present in the warp
                     const int c = __shfl_sync(0xffffffffu, fan_class, __ffs(todo) - 1);
                     const uint32_t bc = __ballot_sync(0xffffffffu, fan_class == c);
                     todo &= ~bc;
                     const SlabGrant g = sp_slab_alloc(slabs + 2 * (1 + c), __popc(bc), 1u + (uint32_t)c, sg[SPW_SEG_SLAB], a.out, lane);
-                    if (fan_class == c) {
-                        const uint32_t slot = sp_slab_pos(g, __popc(bc & sp_lanemask_lt()));
-                        if (slot != SP_SLOT_NONE) {
-                            const float4 lite = sh.lite[hit_id];
-                            const float inv_m = (meta_dr(r.meta) < 1u) ? lite.w : 1.f;
-                            const float3 thr = r.thr * xyz(lite) * inv_m;
-                            if (any_nonzero(thr)) {
-                                const DCollider& col = sc.colliders[hit_id];
-                                const float3 P = fma3(r.d, hit_t, r.o);
-                                const float3 Nc = to_f3(sp_collider_normal<float>((int)ctype, col.p, from_f3<float>(P)));
-                                const float3 N = outer ? Nc : -Nc;
-                                // sampled directions lie in the hemisphere of N: they leave a planar / outer surface
-                                // and cross the interior of a convex collider hit from inside (sp_shade.cuh)
-                                const bool planar = (ctype == SP_COLLIDER_PLANE || ctype == SP_COLLIDER_TRIANGLE);
-                                const uint32_t mode = (planar || outer) ? SP_SELF_SKIP : SP_SELF_FAR;
-                                const uint32_t meta = sp_pack_meta(meta_depth(r.meta) + 1u, meta_dr(r.meta) + 1u, meta_medium(r.meta),
-                                                                   (uint32_t)hit_id, mode);
-                                sp_write_record(a.out.fans, slot, fma3(N, 1e-6f, P), N, thr, r.pix, r.path, meta);
-                            } else {
-                                sp_write_dead(a.out.fans, slot);
-                            }
-                        }
+                    if (fan_class == c) slot = sp_slab_pos(g, __popc(bc & sp_lanemask_lt()));
+                }
+                if (slot != SP_SLOT_NONE) {
+                    const float4 lite = sh.lite[hit_id];
+                    const float inv_m = (meta_dr(r.meta) < 1u) ? lite.w : 1.f;
+                    const float3 thr = r.thr * xyz(lite) * inv_m;
+                    if (any_nonzero(thr)) {
+                        const DCollider& col = sc.colliders[hit_id];
+                        const float3 P = fma3(r.d, hit_t, r.o);
+                        const float3 Nc = to_f3(sp_collider_normal<float>((int)ctype, col.p, from_f3<float>(P)));
+                        const float3 N = outer ? Nc : -Nc;
+                        // sampled directions lie in the hemisphere of N: they leave a planar / outer surface
+                        // and cross the interior of a convex collider hit from inside (sp_shade.cuh)
+                        const bool planar = (ctype == SP_COLLIDER_PLANE || ctype == SP_COLLIDER_TRIANGLE);
+                        const uint32_t mode = (planar || outer) ? SP_SELF_SKIP : SP_SELF_FAR;
+                        const uint32_t meta = sp_pack_meta(meta_depth(r.meta) + 1u, meta_dr(r.meta) + 1u, meta_medium(r.meta),
+                                                           (uint32_t)hit_id, mode);
+                        sp_write_record(a.out.fans, slot, fma3(N, 1e-6f, P), N, thr, r.pix, r.path, meta);
+                    } else {
+                        sp_write_dead(a.out.fans, slot);
                     }
                 }
             }
