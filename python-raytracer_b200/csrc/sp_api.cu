@@ -876,6 +876,10 @@ int sp_scene_commit(sp_scene* s) {
         double ab[3];
         for (int c = 0; c < 3; ++c) ab[c] = 2.0 * s->media_im[3 * (size_t)i + c] * 2.0 * M_PI / lambda[c] * 1e9;
         med[i].absorb = f3(ab);
+        const double* re = &s->media_re[3 * (size_t)i];
+        const double* im = &s->media_im[3 * (size_t)i];
+        med[i].grey = ((float)re[0] == (float)re[1] && (float)re[1] == (float)re[2] && re[0] > 0.0 &&
+                       std::fabs(im[0]) <= 1e-4 * re[0] && std::fabs(im[1]) <= 1e-4 * re[0] && std::fabs(im[2]) <= 1e-4 * re[0]) ? 1 : 0;
     }
     CUDA_TRY(s->d_media.upload(med));
 

@@ -513,11 +513,6 @@ static LevelKernel level_kernel(uint32_t material_set, bool level0) {
 
 // Queue-fed levels of small untextured Monte-Carlo scenes run the warp-autonomous kernel (sp_warp_kernel.cuh).
 // SIGHTPY_WARP_KERNEL=0 keeps them on sp_level_kernel (A/B measurements).
-static int sp_warp_ctas() {          // SIGHTPY_WARP_CTAS=3: the 80-register build (A/B measurements)
-    static const int v = [] { const char* e = getenv("SIGHTPY_WARP_CTAS"); return (e && e[0] == '3') ? 3 : 4; }();
-    return v;
-}
-
 bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set) {
     static const bool enabled = [] { const char* e = getenv("SIGHTPY_WARP_KERNEL"); return !(e && e[0] == '0'); }();
     if (!enabled || material_set != SP_SET_MC) return false;
@@ -531,7 +526,7 @@ int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool leve
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (!level0 && sp_use_warp_kernel(sc, material_set)) {
-        auto k = sp_warp_ctas() == 3 ? sp_warp_kernel<SP_SET_MC, 3> : sp_warp_kernel<SP_SET_MC, 4>;
+        auto k = sp_warp_kernel<SP_SET_MC>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
         int per_sm = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SPW_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
@@ -548,8 +543,7 @@ int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool leve
 
 cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st) {
     if (a.source == SP_SRC_QUEUES && a.run == SP_RUN_FULL && sp_use_warp_kernel(sc, material_set)) {
-        if (sp_warp_ctas() == 3) sp_warp_kernel<SP_SET_MC, 3><<<grid, SPW_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
-        else sp_warp_kernel<SP_SET_MC, 4><<<grid, SPW_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
+        sp_warp_kernel<SP_SET_MC><<<grid, SPW_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
         return cudaGetLastError();
     }
     level_kernel(material_set, a.source != SP_SRC_QUEUES)<<<grid, SP_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);

@@ -331,16 +331,32 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
         float Fc[3];
         const float re1[3] = {n1.re.x, n1.re.y, n1.re.z}, im1[3] = {n1.im.x, n1.im.y, n1.im.z};
         const float re2[3] = {n2.re.x, n2.re.y, n2.re.z}, im2[3] = {n2.im.x, n2.im.y, n2.im.z};
+        if (n1.grey && n2.grey) {
+            // real indices, one value for the three channels: cos_t is real, or imaginary under total internal
+            // reflection, where |r_per| = |r_par| = 1 (the complex evaluation below gives the same to ~1e-8)
+            const float a_ = re1[0], b_ = re2[0];
+            const float ratio = __fdividef(a_, b_);
+            const float c2 = 1.f - ratio * ratio * s2;
+            float Fr = 1.f;
+            if (c2 >= 0.f) {
+                const float cos_t = sqrtf(c2);
+                const float aci = a_ * cos_i, bct = b_ * cos_t, act = a_ * cos_t, bci = b_ * cos_i;
+                const float per = __fdividef(aci - bct, aci + bct), par = __fdividef(act - bci, act + bci);
+                Fr = 0.5f * (per * per + par * par);
+            }
+            Fc[0] = Fc[1] = Fc[2] = Fr;
+        } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            cplx a = cx(re1[c], im1[c]), b = cx(re2[c], im2[c]);
-            cplx ratio = a / b;
-            cplx cos_t = csqrt(cx(1.f) - ratio * ratio * s2);
-            // |r|^2 = |numerator|^2 / |denominator|^2: no complex division needed
-            cplx aci = a * cos_i, bct = b * cos_t, act = a * cos_t, bci = b * cos_i;
-            float per = __fdividef(cabs2(aci - bct), cabs2(aci + bct));
-            float par = __fdividef(cabs2(act - bci), cabs2(act + bci));
-            Fc[c] = 0.5f * (per + par);
+            for (int c = 0; c < 3; ++c) {
+                cplx a = cx(re1[c], im1[c]), b = cx(re2[c], im2[c]);
+                cplx ratio = a / b;
+                cplx cos_t = csqrt(cx(1.f) - ratio * ratio * s2);
+                // |r|^2 = |numerator|^2 / |denominator|^2: no complex division needed
+                cplx aci = a * cos_i, bct = b * cos_t, act = a * cos_t, bci = b * cos_i;
+                float per = __fdividef(cabs2(aci - bct), cabs2(aci + bct));
+                float par = __fdividef(cabs2(act - bci), cabs2(act + bci));
+                Fc[c] = 0.5f * (per + par);
+            }
         }
         float3 F = v3(Fc[0], Fc[1], Fc[2]);
         float eta = (__fdividef(re1[0], re2[0]) + __fdividef(re1[1], re2[1]) + __fdividef(re1[2], re2[2])) * (1.f / 3.f);

@@ -83,7 +83,10 @@ struct DTexture {
 
 struct DLight { int kind; float3 vec; float3 color; };
 struct DImportance { float3 center; float radius; };
-struct DMedium { float3 re, im, absorb; };   // absorb = 2*Im(n)*2*pi/lambda*1e9  (refractive.py:113-121)
+// absorb = 2*Im(n)*2*pi/lambda*1e9  (refractive.py:113-121)
+// grey: the three channels share one real index and |Im n| <= 1e-4 |Re n| — ordinary glass.  Between two such media
+// the Fresnel reflectance is evaluated once, in real arithmetic (it differs from the complex one by (Im/Re)^2 <= 1e-8).
+struct DMedium { float3 re, im, absorb; int grey; };
 
 // bounding-volume hierarchy over the small colliders of a large scene (layout: sp_geometry.cuh)
 struct DBvh {

@@ -17,8 +17,8 @@
 //     (per 64-256 records instead of per CTA iteration) and hands them out with ballot + popc.  A slab that
 //     cannot take a whole request is finished by the first ranks and the rest go to a fresh one, so the
 //     only unused slots are each warp's last slab; they are filled with dead records at exit;
-//   * work items are walked segment by segment (ray records, then each fan class), which makes the record /
-//     child split of a fan item an incremental update instead of a 64-bit magic division per ray.
+//   * work items are walked segment by segment (ray records, then each fan class), so the class of an item and
+//     its constants (multiplicity, magic divisor, queue base) are uniform and read from shared memory.
 // Eligibility (host, sp_use_warp_kernel): queue-fed level, material set Diffuse + Refractive + Emissive
 // without textures, one geometry chunk, no BVH, fewer than 64 colliders, fan multiplicities <= 1024.
 #pragma once
@@ -28,6 +28,10 @@
 
 #define SPW_BLOCK 256
 #define SPW_WARPS (SPW_BLOCK / 32)
+#ifndef SPW_PREFETCH
+#define SPW_PREFETCH 0            // L1 prefetch of the next iteration's records: measured, no gain (25.5 vs 25.8 Grays/s)
+#endif
+#define SPW_CTAS 4                   // resident CTAs per SM the register allocation aims for (64 registers; 3 CTAs at 80: -4 %)
 #define SPW_STASH_WORDS 14           // o d thr pix path meta t (id | orient)
 #define SPW_STASH_CAP 64             // < 32 left over + 32 pushed
 #define SPW_MAX_COLLIDERS 64           // = SP_BVH_MIN_COLLIDERS: larger scenes go through the BVH variant
@@ -148,14 +152,15 @@ __device__ __noinline__ void sp_shade_stash(const DScene* scp, const LevelArgs* 
     }
 }
 
+SP_DEV void sp_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 SP_DEV uint32_t sp_lane_id() { uint32_t r; asm("mov.u32 %0, %%laneid;" : "=r"(r)); return r; }
 SP_DEV uint32_t sp_lanemask_lt() { uint32_t r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
 
 // per-segment constants (shared memory, read where they are needed instead of living in registers)
-enum { SPW_SEG_ITEMS = 0, SPW_SEG_MULT, SPW_SEG_BASE, SPW_SEG_INV24, SPW_SEG_STEP_REC, SPW_SEG_STEP_REM, SPW_SEG_SLAB, SPW_SEG_WORDS = 8 };
+enum { SPW_SEG_ITEMS = 0, SPW_SEG_MULT, SPW_SEG_MAGIC_LO, SPW_SEG_MAGIC_HI, SPW_SEG_BASE, SPW_SEG_SLAB, SPW_SEG_WORDS = 8 };
 
-template <uint32_t FEAT, int CTAS>
-__global__ void __launch_bounds__(SPW_BLOCK, CTAS)
+template <uint32_t FEAT>
+__global__ void __launch_bounds__(SPW_BLOCK, SPW_CTAS)
 sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
     static_assert((FEAT & ~(SP_F_DIFFUSE | SP_F_REFR)) == 0u, "inline shading covers untextured Diffuse / Emissive only");
     extern __shared__ float4 s_geom[];
@@ -193,8 +198,9 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
         }
         uint32_t* sg = sh.seg[tid];
         sg[SPW_SEG_ITEMS] = n_items; sg[SPW_SEG_MULT] = mult; sg[SPW_SEG_BASE] = fan_base;
-        sg[SPW_SEG_INV24] = (1u << 24) / mult + 1u;            // floor(x / mult) == (x * inv24) >> 24 for x * mult < 2^24
-        sg[SPW_SEG_STEP_REC] = stride / mult; sg[SPW_SEG_STEP_REM] = stride % mult;
+        // item / mult == __umul64hi(item, ceil(2^64 / mult)) for 32-bit items (mult == 1 is special-cased)
+        const unsigned long long magic = tid > 0 ? sc.fan_magic[tid - 1] : 0ull;
+        sg[SPW_SEG_MAGIC_LO] = (uint32_t)magic; sg[SPW_SEG_MAGIC_HI] = (uint32_t)(magic >> 32);
         sg[SPW_SEG_SLAB] = slab_size;
     }
     __syncthreads();
@@ -216,9 +222,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
     for (int seg = 0; seg <= sc.n_fan_classes; ++seg) {
         const volatile uint32_t* sg = sh.seg[seg];
         const uint32_t n_items = sg[SPW_SEG_ITEMS];
-        // item = rec * mult + child, kept up to date incrementally: (rec0, rem0) belong to the warp's first item
         uint32_t wb = (blockIdx.x * SPW_WARPS + warp) * 32u;
-        uint32_t rec0 = wb / sg[SPW_SEG_MULT], rem0 = wb % sg[SPW_SEG_MULT];
 #pragma unroll 1
         for (; wb < n_items; wb += stride) {
             const uint32_t lane = sp_lane_id();
@@ -230,12 +234,11 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             if (seg == 0) {
                 if (active) {
                     const uint32_t item = wb + lane;
-                    const float4 q2 = a.in_rays.q2[item];
+                    const float4 q2 = a.in_rays.q2[item], q0 = a.in_rays.q0[item], q1 = a.in_rays.q1[item];
                     r.meta = __float_as_uint(q2.w);
                     if (r.meta == SP_META_DEAD) {
                         active = false;
                     } else {
-                        const float4 q0 = a.in_rays.q0[item], q1 = a.in_rays.q1[item];
                         r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
                         r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
                         const uint32_t src = meta_src(r.meta);
@@ -243,20 +246,27 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                     }
                 }
             } else {
-                const uint32_t mult = sg[SPW_SEG_MULT];
-                const uint32_t x = rem0 + lane;
-                const uint32_t qd = (x * sg[SPW_SEG_INV24]) >> 24;
-                const uint32_t rec = rec0 + qd, child = x - qd * mult;
-                rec0 += sg[SPW_SEG_STEP_REC]; rem0 += sg[SPW_SEG_STEP_REM];
-                if (rem0 >= mult) { rem0 -= mult; rec0 += 1u; }
+                // item = rec * mult + child
+                const uint32_t mult = sg[SPW_SEG_MULT], item = wb + lane;
+                uint32_t rec = item;
+                if (mult != 1u) {
+                    const unsigned long long magic = ((unsigned long long)sg[SPW_SEG_MAGIC_HI] << 32) | sg[SPW_SEG_MAGIC_LO];
+                    rec = (uint32_t)__umul64hi((unsigned long long)item, magic);
+                }
+                const uint32_t child = item - rec * mult;
                 if (active) {
                     const uint32_t s = sg[SPW_SEG_BASE] + rec;
-                    const float4 q2 = a.in_fans.q2[s];
+                    if (SPW_PREFETCH && wb + stride < n_items) {
+                        // the record this lane reads in the warp's next iteration (give or take one): have it in L1 by then
+                        const uint32_t sn = s + stride / mult;
+                        sp_prefetch_l1(a.in_fans.q0 + sn); sp_prefetch_l1(a.in_fans.q1 + sn); sp_prefetch_l1(a.in_fans.q2 + sn);
+                    }
+                    // all three vectors at once (one memory round trip; a dead record's q0 / q1 are simply ignored)
+                    const float4 q2 = a.in_fans.q2[s], q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
                     r.meta = __float_as_uint(q2.w);
                     if (r.meta == SP_META_DEAD) {
                         active = false;
                     } else {
-                        const float4 q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
                         r.o = xyz(q0); r.thr = xyz(q2);
                         r.pix = __float_as_uint(q0.w);
                         r.path = sp_child_path(__float_as_uint(q1.w), child);
