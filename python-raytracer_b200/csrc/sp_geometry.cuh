@@ -250,13 +250,14 @@ SP_DEV void sp_intersect_lean(const float4* __restrict__ ch, float3 O, float3 D,
     }
     if (hn.y > 0) {
         const float4* pl = ch + ho.y;
-#pragma unroll 2
+#pragma unroll 1
         for (int i = 0; i < hn.y; ++i)
             sp_lean_plane(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3], O, D, tag + i == self_tag, (uint32_t)(tag + i), bt, bcode);
         tag += hn.y;
     }
     {
         const float4* cb = ch + ho.z;
+#pragma unroll 1
         for (int i = 0; i < hn.z; ++i)
             sp_lean_cuboid(cb[5 * i], cb[5 * i + 1], cb[5 * i + 2], cb[5 * i + 3], cb[5 * i + 4], O, D, tag + i == self_tag,
                            mode, (uint32_t)(tag + i), bt, bcode);
@@ -264,7 +265,7 @@ SP_DEV void sp_intersect_lean(const float4* __restrict__ ch, float3 O, float3 D,
     }
     if (hn.w > 0) {
         const float4* tr = ch + ho.w;
-#pragma unroll 2
+#pragma unroll 1
         for (int i = 0; i < hn.w; ++i)
             sp_lean_triangle(tr[3 * i], tr[3 * i + 1], tr[3 * i + 2], O, D, tag + i == self_tag, (uint32_t)(tag + i), bt, bcode);
         tag += hn.w;

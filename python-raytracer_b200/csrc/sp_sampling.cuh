@@ -72,6 +72,7 @@ SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float 
     float pdf = ndl * (1.f / SP_PI);
     if (l > 0) {                                             // mixed_pdf.value
         float caps = 0.f;
+#pragma unroll 2
         for (int i = 0; i < l; ++i) {
             float3 to_c = sc.importance[i].center - origin;
             float d2 = dot(to_c, to_c);
