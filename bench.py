@@ -293,23 +293,24 @@ def run_native(args, emit=print):
     level_s = totals["level_ms"] * 1e-3
     n_launch = max(totals["level_launches"], 1)
     flops = FLOP_PER_RAY_CORNELL * totals["rays"]
-    traffic_file = REPO / "profiles" / "r1_v8_dram_per_ray.json"       # from the committed ncu --set full capture
+    traffic_file = REPO / "profiles" / "r1_v14_dram_per_ray.json"      # from the committed ncu launch list of this build
     dram_per_ray = json.loads(traffic_file.read_text())["dram_bytes_per_ray"] if traffic_file.exists() else None
     traffic = dram_per_ray * totals["rays"] / n_launch if dram_per_ray else None
     roofline = {
-        "bound": "fp32", "kernel": "sp_level_kernel",
+        "bound": "fp32", "kernel": "sp_warp_kernel (levels >= 1: 98 % of the rays) + sp_level_kernel (level 0)",
         "achieved": flops / level_s / 1e12, "peak": live["fp32_tflops"], "unit": "TFLOP/s",
         "frac": flops / level_s / 1e12 / live["fp32_tflops"],
         "peak_source": "FFMA chain micro-benchmark run by this process (sp_measure_peaks); MEASURED_PEAKS.json has no FP32 entry",
         "flop_per_ray": FLOP_PER_RAY_CORNELL, "rays_per_launch": totals["rays"] / n_launch,
         "avg_launch_ms": totals["level_ms"] / n_launch, "traffic": None,
         "note": "fused generate+intersect+shade kernel: neither HBM- nor tensor-bound; the binding resource is "
-                "instruction issue (ncu, profiles/r1_v13_level_kernel.md: 0.62-0.66 of 1.0 instructions per scheduler "
-                "per cycle, pipes FMA 20 % / ALU 43 % / MUFU 18 % / LSU 24 %, ~1700 warp instructions per 32 rays of "
-                "which the 8 collider tests are ~350)",
+                "instruction issue (ncu, profiles/r1_v14_warp_kernel.md: 0.67 of 1.0 instructions per scheduler per "
+                "cycle at 32 resident warps per SM, pipes FMA 24 % / ALU 44 % / MUFU 16 % / LSU 29 %, ~1000 warp "
+                "instructions per 32 rays of which the 8 collider tests are ~285; achieved counts only the "
+                "algorithmic intersection flops of SURVEY 8(d))",
     }
     roofline_hbm = {
-        "bound": "hbm", "kernel": "sp_level_kernel (queue records only)",
+        "bound": "hbm", "kernel": "sp_warp_kernel + sp_level_kernel (queue records only)",
         "achieved": totals["queue_bytes"] / level_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": totals["queue_bytes"] / level_s / 1e9 / hbm_peak, "peak_source": hbm_src,
         "bytes_per_record": 96, "traffic": traffic,
