@@ -212,11 +212,13 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
     }
     __syncthreads();
 
-    const uint32_t warp = tid >> 5;
+    // a warp-wide reduction hands the warp's index to the uniform datapath: everything derived from it (item
+    // cursor, stash / slab addresses) can then live in uniform registers instead of one copy per lane
+    const uint32_t warp = __reduce_max_sync(0xffffffffu, tid >> 5);
     uint32_t* const stash = &sh.stash[warp][0][0];
     uint32_t* const slabs = &sh.slab[warp][0][0];
     uint32_t n_st = 0;                                         // entries in the stash (warp-uniform)
-    uint32_t traced = 0;
+    uint32_t traced = 0;                                       // rays traced by this warp (warp-uniform)
     const uint32_t stride = gridDim.x * SPW_WARPS * 32u;
 
     for (int seg = 0; seg <= sc.n_fan_classes; ++seg) {
@@ -299,8 +301,9 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                         outer = (bcode & 0x80000000u) == 0u;
                     }
                 }
-                traced += 1u;
             }
+
+            traced += __popc(__ballot_sync(0xffffffffu, active));
 
             // ---- 3. what the hit does -------------------------------------------------------------------------
             int fan_class = -1;
@@ -391,7 +394,5 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
         const RayQueue& rq = (q == 0) ? a.out.rays : a.out.fans;
         for (uint32_t s = next + lane; s < end; s += 32u) sp_write_dead(rq, s);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
     if (lane == 0 && traced) atomicAdd(&a.out.stats->rays[a.level], (unsigned long long)traced);
 }
