@@ -31,7 +31,9 @@
 #ifndef SPW_PREFETCH
 #define SPW_PREFETCH 0            // L1 prefetch of the next iteration's records: measured, no gain (25.5 vs 25.8 Grays/s)
 #endif
-#define SPW_CTAS 4                   // resident CTAs per SM the register allocation aims for (64 registers; 3 CTAs at 80: -4 %)
+#ifndef SPW_CTAS
+#define SPW_CTAS 4                   // resident CTAs per SM the register allocation aims for (64 registers, no spills; measured: 3 CTAs at 80 registers -4 %, 5 at 48 -6 %, 6 at 40 -5 %)
+#endif
 #define SPW_STASH_WORDS 14           // o d thr pix path meta t (id | orient)
 #define SPW_STASH_CAP 64             // < 32 left over + 32 pushed
 #define SPW_MAX_COLLIDERS 64           // = SP_BVH_MIN_COLLIDERS: larger scenes go through the BVH variant
