@@ -117,6 +117,7 @@ typedef struct sp_stats {
     double   level_ms[SP_MAX_DEPTH_LEVELS];   /* level kernel time per recursion depth            */
     uint64_t peak_ray_records;      /* largest per-level queue occupancy seen (records)           */
     uint64_t peak_fan_records;
+    uint64_t warp_kernel_launches;  /* of level_kernel_launches: those that ran the warp-autonomous variant */
 } sp_stats;
 
 typedef struct sp_scene sp_scene;
@@ -196,7 +197,9 @@ int  sp_distances(sp_scene*, uint64_t seed, float* out_t);
 /* options: "ray_queue_capacity", "fan_queue_capacity" (records), "chunk_primaries" (0 = auto),
  * "max_levels" (debugging: trace only the first k recursion depths, 0 = all),
  * "bvh" (1 = scenes with >= 64 colliders put their small colliders into a bounding-volume hierarchy, the
- *        default; 0 = every ray tests every collider) */
+ *        default; 0 = every ray tests every collider),
+ * "warp_kernel" (1 = queue-fed levels of small untextured Diffuse / Refractive / Emissive scenes run the
+ *        warp-autonomous kernel, the default; 0 = the CTA-cooperative kernel everywhere; same rays, same results) */
 int  sp_set_option(sp_scene*, const char* name, int64_t value);
 /* Roofline denominators measured on the bound device: dependent-free FFMA chains (TFLOP/s, 2 flop
  * per FFMA) and a float4 copy (GB/s, read + write bytes). */

@@ -158,7 +158,7 @@ struct sp_scene {
     std::vector<sp_light> lights;
     std::vector<int32_t> importance, shadow_ids;
     // ---- options ------------------------------------------------------------------------------------
-    int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0, opt_bvh = 1;
+    int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0, opt_bvh = 1, opt_warp = 1;
     // ---- device residency -----------------------------------------------------------------------------
     DScene d{};
     int n_levels = 1;
@@ -965,6 +965,7 @@ int sp_scene_commit(sp_scene* s) {
     }
     if (d.bvh.n_nodes > 0) needed |= SP_F_BVH;
     s->material_set = sp_pick_material_set(needed);
+    s->d.use_warp_kernel = s->opt_warp ? 1 : 0;
     s->grid0 = sp_level_grid(g_device, s->d, s->material_set, true);
     s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false);
     s->use_ray = s->use_fan = 0.0;
@@ -1061,6 +1062,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
         st->chunks += 1;
         st->kernel_launches += (uint64_t)n_levels;
         st->level_kernel_launches += (uint64_t)n_levels;
+        if (job.run == SP_RUN_FULL && sp_use_warp_kernel(s->d, s->material_set)) st->warp_kernel_launches += (uint64_t)(n_levels - 1);
         st->peak_ray_records = std::max<uint64_t>(st->peak_ray_records, peak_r);
         st->peak_fan_records = std::max<uint64_t>(st->peak_fan_records, peak_f);
         for (int L = 0; L < n_levels; ++L) {
@@ -1309,6 +1311,13 @@ int sp_set_option(sp_scene* s, const char* name, int64_t value) {
     else if (!strcmp(name, "bvh")) {
         s->opt_bvh = value;
         if (s->committed) return sp_scene_commit(s);             // the geometry tables depend on it
+    }
+    else if (!strcmp(name, "warp_kernel")) {
+        s->opt_warp = value;
+        if (s->committed) {
+            s->d.use_warp_kernel = value ? 1 : 0;
+            s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false);
+        }
     }
     else return fail("sp_set_option: unknown option '%s'", name);
     s->use_ray = s->use_fan = 0.0;

@@ -515,7 +515,7 @@ static LevelKernel level_kernel(uint32_t material_set, bool level0) {
 // SIGHTPY_WARP_KERNEL=0 keeps them on sp_level_kernel (A/B measurements).
 bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set) {
     static const bool enabled = [] { const char* e = getenv("SIGHTPY_WARP_KERNEL"); return !(e && e[0] == '0'); }();
-    if (!enabled || material_set != SP_SET_MC) return false;
+    if (!enabled || !sc.use_warp_kernel || material_set != SP_SET_MC) return false;
     if (sc.all.n_chunks != 1 || sc.bvh.n_nodes != 0 || sc.n_colliders > SPW_MAX_COLLIDERS) return false;
     for (int c = 0; c < sc.n_fan_classes; ++c)
         if (sc.fan_mult[c] > 1024) return false;

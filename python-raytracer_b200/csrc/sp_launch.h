@@ -37,6 +37,7 @@ struct ResolveArgs {
 };
 
 uint32_t sp_pick_material_set(uint32_t needed_features);          // smallest compiled kernel variant covering them
+bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set);      // queue-fed levels run sp_warp_kernel (sp_warp_kernel.cuh)
 int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0);   // CTAs of a persistent launch
 cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);

@@ -579,3 +579,94 @@ def test_tiny_and_ragged_sizes():
         ref = sum(orc.trace(*nat.camera_rays(sample=s, seed=2), sample=s)["rgb"] for s in range(5)) / 5
         np.testing.assert_allclose(lin.reshape(3, -1).T, ref, rtol=2e-3, atol=2e-4)
         nat.close()
+
+
+def _plain_mc_scene(seed):
+    """Untextured Diffuse / Refractive / Emissive scene (the material set the warp-autonomous kernel takes): a room of
+    axis-aligned and tilted walls with three fan sizes, a rotated box, emitters of three collider types, glass spheres
+    with different depth limits — ordinary glass, glass with per-channel indices (complex Fresnel path) and a
+    Monte-Carlo-picking one — and two importance-sampled primitives."""
+    import sightpy as sp
+    v, rgb = sp.vec3, sp.rgb
+    rng = np.random.default_rng(900 + seed)
+    U = lambda lo, hi, *shape: rng.uniform(lo, hi, size=shape or None)   # noqa: E731
+    col = lambda: rgb(*map(float, U(0.15, 0.9, 3)))                      # noqa: E731
+    sc = sp.Scene(ambient_color=rgb(0.0, 0.0, 0.0))
+    sc.add_Camera(look_from=v(0.2, 2.0, 7.5), look_at=v(0.0, 2.0, 0.0), screen_width=40, screen_height=30, field_of_view=50)
+    fans = [20, 5, 1]
+    walls = [((0, 0, 0), (1, 0, 0), (0, 0, -1)), ((0, 2, -2), (1, 0, 0), (0, 1, 0)), ((-2, 2, 0), (0, 0, 1), (0, 1, 0)),
+             ((2, 2, 0), (0, 0, -1), (0, 1, 0)), ((0, 4, 0), (1, 0, 0), (0, 0, 1))]
+    for i, (c, ua, va) in enumerate(walls):
+        m = sp.Diffuse(diff_color=col(), diffuse_rays=fans[i % 3], ambient_weight=float(rng.choice([0.5, 0.3, 0.8])))
+        sc.add(sp.Plane(material=m, center=v(*map(float, c)), width=4.0, height=4.0, u_axis=v(*map(float, ua)),
+                        v_axis=v(*map(float, va))))
+    tilted = sp.Plane(material=sp.Diffuse(diff_color=col(), diffuse_rays=5), center=v(-1.0, 0.7, -1.0), width=0.9, height=0.6,
+                      u_axis=v(1.0, 0, 0), v_axis=v(0, 0, -1.0))
+    tilted.rotate(θ=25.0, u=v(0.3, 0.2, 1.0))
+    sc.add(tilted)
+    box = sp.Cuboid(material=sp.Diffuse(diff_color=col()), center=v(-0.8, 1.0, -0.6), width=1.0, height=2.0, length=1.0)
+    box.rotate(θ=float(U(5, 40)), u=v(0, 1, 0))
+    sc.add(box)
+    lamp = sp.Emissive(color=rgb(12.0, 11.0, 9.0))
+    sc.add(sp.Plane(material=lamp, center=v(0.0, 3.98, 0.0), width=1.2, height=0.9, u_axis=v(1.0, 0, 0), v_axis=v(0, 0, 1.0)),
+           importance_sampled=True)
+    sc.add(sp.Sphere(material=sp.Emissive(color=rgb(2.0, 3.0, 6.0)), center=v(1.4, 3.0, -1.2), radius=0.25))
+    glow = sp.Cuboid(material=sp.Emissive(color=rgb(3.0, 1.0, 1.0)), center=v(-1.5, 3.2, -1.4), width=0.4, height=0.3, length=0.4)
+    sc.add(glow)
+    sc.add(sp.Sphere(material=sp.Refractive(n=v(1.5 + 4e-9j, 1.5 + 1e-9j, 1.5 + 0j)), center=v(0.9, 0.7, 0.4), radius=0.7,
+                     max_ray_depth=3), importance_sampled=True)
+    sc.add(sp.Sphere(material=sp.Refractive(n=v(1.45 + 2e-3j, 1.5 + 0j, 1.6 + 1e-3j)), center=v(-0.2, 2.6, -0.9), radius=0.45,
+                     max_ray_depth=4))
+    sc.add(sp.Sphere(material=sp.Refractive(n=v(1.33 + 0j, 1.33 + 0j, 1.33 + 0j)), center=v(0.3, 0.4, 1.3), radius=0.4,
+                     max_ray_depth=5, mc=True))
+    return sc
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_warp_autonomous_and_cooperative_kernels_agree(seed):
+    """Queue-fed levels of small untextured Diffuse / Refractive / Emissive scenes run sp_warp_kernel (warp-private
+    stash and slabs, inline Diffuse / Emissive); option "warp_kernel" = 0 sends them through sp_level_kernel.  Both
+    trace the same rays (same Philox keys): identical hit ids and ray counts per depth, radiance equal up to the
+    order of the float additions, and both agree with the oracle."""
+    from sightpy.backend import NativeScene
+    flat = flatten_scene(_plain_mc_scene(seed))
+    nat = NativeScene(flat)
+    o, d = nat.camera_rays(sample=2, seed=11)
+    warp = nat.trace(o, d, seed=11)
+    assert warp["stats"]["warp_kernel_launches"] > 0, "the warp-autonomous kernel did not run"
+    _, frame_w, st_w = nat.render(3, seed=4)
+    nat.set_option("warp_kernel", 0)
+    coop = nat.trace(o, d, seed=11)
+    assert coop["stats"]["warp_kernel_launches"] == 0
+    _, frame_c, st_c = nat.render(3, seed=4)
+    nat.close()
+    assert np.array_equal(warp["hit_id"], coop["hit_id"])
+    assert warp["stats"]["rays_per_depth"] == coop["stats"]["rays_per_depth"]
+    assert st_w["rays_per_depth"] == st_c["rays_per_depth"]
+    np.testing.assert_allclose(warp["rgb"], coop["rgb"], rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(frame_w, frame_c, rtol=2e-4, atol=1e-5)
+    want = Oracle(flat, rng="philox", seed=11).trace(o, d)
+    assert np.mean(warp["hit_id"] != want["hit_id"]) < 0.002
+    same = warp["hit_id"] == want["hit_id"]
+    err = np.abs(warp["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[same]
+    scale = 1.0 + np.abs(want["rgb"]).max(axis=1)[same]
+    assert float(np.mean(err > RGB_TOL * scale)) < 0.03, float(np.mean(err > RGB_TOL * scale))
+    assert abs(warp["rgb"].mean() - want["rgb"].mean()) < 0.02 * want["rgb"].mean()
+
+
+def test_warp_kernel_slabs_survive_tiny_chunks_and_report_overflow():
+    """Warp-private slabs: a frame cut into 1024-primary chunks (every launch smaller than the grid: most warps
+    never open a slab, the others leave dead tails) equals the frame rendered in one chunk, and a ray queue that
+    cannot hold the glass children is reported, not silently dropped."""
+    nat, _ = native_for("cornell")
+    _, a, sa = nat.render(3, seed=9)
+    assert sa["warp_kernel_launches"] > 0
+    nat.set_option("chunk_primaries", 1024)
+    _, b, sb = nat.render(3, seed=9)
+    assert sb["chunks"] > sa["chunks"] and sa["rays_per_depth"] == sb["rays_per_depth"]
+    np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-6)
+    nat.set_option("chunk_primaries", 0)
+    nat.set_option("ray_queue_capacity", 32)
+    with pytest.raises(RuntimeError, match="overflow"):
+        nat.render(2, seed=0)
+    nat.close()
