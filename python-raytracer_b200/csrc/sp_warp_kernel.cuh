@@ -28,9 +28,6 @@
 
 #define SPW_BLOCK 256
 #define SPW_WARPS (SPW_BLOCK / 32)
-#ifndef SPW_PREFETCH
-#define SPW_PREFETCH 0            // L1 prefetch of the next iteration's records: measured, no gain (25.5 vs 25.8 Grays/s)
-#endif
 #ifndef SPW_CTAS
 #define SPW_CTAS 4                   // resident CTAs per SM the register allocation aims for (64 registers, no spills; measured: 3 CTAs at 80 registers -4 %, 5 at 48 -6 %, 6 at 40 -5 %)
 #endif
@@ -41,6 +38,7 @@
 
 struct WarpShared {
     uint32_t stash[SPW_WARPS][SPW_STASH_WORDS][SPW_STASH_CAP];
+    float4 rec[SPW_WARPS][3][32];                  // the record each lane reads in its next iteration (cp.async)
     uint32_t slab[SPW_WARPS][SPW_N_QUEUES][2];     // per warp and output queue: next free slot, end of the slab
     uint32_t seg[SPW_N_QUEUES][8];                 // per work-item segment: SPW_SEG_* constants
     uint2 cls[SPW_MAX_COLLIDERS];                  // per collider: what a hit does (sp_hit_class below)
@@ -154,7 +152,12 @@ __device__ __noinline__ void sp_shade_stash(const DScene* scp, const LevelArgs* 
     }
 }
 
-SP_DEV void sp_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+// 16-byte asynchronous copy global -> shared (LDGSTS: no register staging, completes in the background)
+SP_DEV void sp_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+SP_DEV void sp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+SP_DEV void sp_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 SP_DEV uint32_t sp_lane_id() { uint32_t r; asm("mov.u32 %0, %%laneid;" : "=r"(r)); return r; }
 SP_DEV uint32_t sp_lanemask_lt() { uint32_t r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
 
@@ -227,6 +230,28 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
         const volatile uint32_t* sg = sh.seg[seg];
         const uint32_t n_items = sg[SPW_SEG_ITEMS];
         uint32_t wb = (blockIdx.x * SPW_WARPS + warp) * 32u;
+        // Record pipeline: the three vectors of the record a lane needs in iteration i + 1 are copied into the lane's
+        // own shared-memory slot (cp.async, no registers) while iteration i runs; the global-memory round trip, a
+        // quarter of the stall samples of the single-ray levels, is off the critical path.
+        float4* const my_rec = &sh.rec[warp][0][sp_lane_id()];
+        auto fetch = [&](uint32_t first) {                     // first item of the iteration the copy is for
+            const uint32_t item = first + sp_lane_id();
+            if (item < n_items) {
+                uint32_t rec = item;
+                const RayQueue* q = &a.in_rays;
+                if (seg != 0) {
+                    if (sg[SPW_SEG_MULT] != 1u) {
+                        const unsigned long long magic = ((unsigned long long)sg[SPW_SEG_MAGIC_HI] << 32) | sg[SPW_SEG_MAGIC_LO];
+                        rec = (uint32_t)__umul64hi((unsigned long long)item, magic);
+                    }
+                    rec += sg[SPW_SEG_BASE];
+                    q = &a.in_fans;
+                }
+                sp_cp_async16(my_rec, q->q0 + rec); sp_cp_async16(my_rec + 32, q->q1 + rec); sp_cp_async16(my_rec + 64, q->q2 + rec);
+            }
+            sp_cp_async_commit();
+        };
+        if (wb < n_items) fetch(wb);
 #pragma unroll 1
         for (; wb < n_items; wb += stride) {
             const uint32_t lane = sp_lane_id();
@@ -235,52 +260,35 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
             int self_tag = -1;                                 // the source collider's position in the chunk's id array
             // ---- 1. the ray of this item -----------------------------------------------------------------
+            sp_cp_async_wait_all();
+            float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = make_float4(0.f, 0.f, 0.f, __uint_as_float(SP_META_DEAD));
+            if (active) { q0 = my_rec[0]; q1 = my_rec[32]; q2 = my_rec[64]; }
+            r.meta = __float_as_uint(q2.w);
+            active = active && r.meta != SP_META_DEAD;
+            if (wb + stride < n_items) fetch(wb + stride);     // the slot has been read: refill it for the next iteration
             if (seg == 0) {
                 if (active) {
-                    const uint32_t item = wb + lane;
-                    const float4 q2 = a.in_rays.q2[item], q0 = a.in_rays.q0[item], q1 = a.in_rays.q1[item];
-                    r.meta = __float_as_uint(q2.w);
-                    if (r.meta == SP_META_DEAD) {
-                        active = false;
-                    } else {
-                        r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
-                        r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
-                        const uint32_t src = meta_src(r.meta);
-                        if (src != SP_SRC_NONE) self_tag = __float_as_int(sh.src_info[src].x);
-                    }
+                    r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
+                    r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
+                    const uint32_t src = meta_src(r.meta);
+                    if (src != SP_SRC_NONE) self_tag = __float_as_int(sh.src_info[src].x);
                 }
-            } else {
+            } else if (active) {
                 // item = rec * mult + child
                 const uint32_t mult = sg[SPW_SEG_MULT], item = wb + lane;
-                uint32_t rec = item;
+                uint32_t child = 0u;
                 if (mult != 1u) {
                     const unsigned long long magic = ((unsigned long long)sg[SPW_SEG_MAGIC_HI] << 32) | sg[SPW_SEG_MAGIC_LO];
-                    rec = (uint32_t)__umul64hi((unsigned long long)item, magic);
+                    child = item - (uint32_t)__umul64hi((unsigned long long)item, magic) * mult;
                 }
-                const uint32_t child = item - rec * mult;
-                if (active) {
-                    const uint32_t s = sg[SPW_SEG_BASE] + rec;
-                    if (SPW_PREFETCH && wb + stride < n_items) {
-                        // the record this lane reads in the warp's next iteration (give or take one): have it in L1 by then
-                        const uint32_t sn = s + stride / mult;
-                        sp_prefetch_l1(a.in_fans.q0 + sn); sp_prefetch_l1(a.in_fans.q1 + sn); sp_prefetch_l1(a.in_fans.q2 + sn);
-                    }
-                    // all three vectors at once (one memory round trip; a dead record's q0 / q1 are simply ignored)
-                    const float4 q2 = a.in_fans.q2[s], q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
-                    r.meta = __float_as_uint(q2.w);
-                    if (r.meta == SP_META_DEAD) {
-                        active = false;
-                    } else {
-                        r.o = xyz(q0); r.thr = xyz(q2);
-                        r.pix = __float_as_uint(q0.w);
-                        r.path = sp_child_path(__float_as_uint(q1.w), child);
-                        const float2 si = sh.src_info[meta_src(r.meta)];      // fan records always name their source
-                        self_tag = __float_as_int(si.x);
-                        const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), si.y, r.pix, r.path, r.d);
-                        r.thr = r.thr * weight;
-                        active = weight > 0.f;                 // zero-weight samples cannot contribute: not traced
-                    }
-                }
+                r.o = xyz(q0); r.thr = xyz(q2);
+                r.pix = __float_as_uint(q0.w);
+                r.path = sp_child_path(__float_as_uint(q1.w), child);
+                const float2 si = sh.src_info[meta_src(r.meta)];      // fan records always name their source
+                self_tag = __float_as_int(si.x);
+                const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), si.y, r.pix, r.path, r.d);
+                r.thr = r.thr * weight;
+                active = weight > 0.f;                         // zero-weight samples cannot contribute: not traced
             }
 
             // ---- 2. nearest hit over the chunk --------------------------------------------------------------
