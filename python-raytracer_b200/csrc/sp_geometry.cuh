@@ -216,6 +216,10 @@ SP_DEV void sp_lean_triangle(float4 m0, float4 m1, float4 m2, float3 O, float3 D
     if (ok) { bt = t; bcode = nd < 0.f ? tag : (tag | 0x80000000u); }
 }
 
+#ifndef SP_LEAN_AA_UNROLL
+#define SP_LEAN_AA_UNROLL 1
+#endif
+constexpr int kLeanAaUnroll = SP_LEAN_AA_UNROLL;
 template <int A>
 SP_DEV void sp_lean_aa(const float4* __restrict__ p, const float4* __restrict__ end, const float4* __restrict__ self_p,
                        float3 O, float3 D, float& bt, uint32_t& bcode) {
@@ -224,7 +228,7 @@ SP_DEV void sp_lean_aa(const float4* __restrict__ p, const float4* __restrict__ 
     const float oc = A == 2 ? O.y : O.z, dc = A == 2 ? D.y : D.z;
     const float inv_da = fast_rcp(da);                        // 1/0 = inf sends the hit point out of bounds
     const uint32_t flip = __float_as_uint(da) & 0x80000000u;
-#pragma unroll 1
+#pragma unroll kLeanAaUnroll
     for (; p != end; p += 2) {
         const float4 r0 = p[0], r1 = p[1];
         const float ca = A == 0 ? r0.x : (A == 1 ? r0.y : r0.z);

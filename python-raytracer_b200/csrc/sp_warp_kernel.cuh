@@ -26,7 +26,9 @@
 #include "sp_sampling.cuh"
 #include "sp_shade.cuh"
 
+#ifndef SPW_BLOCK
 #define SPW_BLOCK 256
+#endif
 #define SPW_WARPS (SPW_BLOCK / 32)
 #ifndef SPW_CTAS
 #define SPW_CTAS 4                   // resident CTAs per SM the register allocation aims for (64 registers, no spills; measured: 3 CTAs at 80 registers -4 %, 5 at 48 -6 %, 6 at 40 -5 %)
