@@ -63,14 +63,23 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
+    PERIOD_MS = 50
+
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -79,7 +88,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -91,18 +100,35 @@ class ClockSampler:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        """Median SM clock and throttle reasons over the samples taken inside the timed region (the sampler runs
+        from before the warm-up, so nvidia-smi is already up when a short timed region starts).  A region
+        shorter than the sampling period falls back to the sample nearest to it and says so."""
+        lo = self.t_begin if self.t_begin is not None else float("-inf")
+        hi = (self.t_end if self.t_end is not None else float("inf")) + 1e-3 * self.PERIOD_MS
+        parsed = []
+        for t, r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                parsed.append((t, float(r[0]), float(r[1]), r[3:7]))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+        inside = [p for p in parsed if lo <= p[0] <= hi]
+        note = None
+        if not inside and parsed:
+            mid = 0.5 * (lo + hi) if self.t_begin is not None and self.t_end is not None else parsed[-1][0]
+            inside = [min(parsed, key=lambda p: abs(p[0] - mid))]
+            note = "timed region shorter than the sampling period: nearest sample (%.0f ms away)" % (abs(inside[0][0] - mid) * 1e3)
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = set()
+        for _, _, _, flags in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(p[1] for p in inside), "sm_max_mhz": max(p[2] for p in inside),
+               "reasons": sorted(reasons), "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ---- CPU arm: the oracle port of the reference on the host cores ----------------------------------
@@ -207,14 +233,14 @@ def run_native(args, emit=print):
             native.resolve_on_device(args.spp)
         return st
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     totals = {"rays": 0, "launches": 0, "level_ms": 0.0, "level_launches": 0, "queue_bytes": 0, "shadow": 0}
     per_depth = None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:                  # started before the warm-up, samples filtered to the timed region
+        for _ in range(args.warmup):
+            step()
         barrier()
+        clocks.mark_begin()
         t_wall = time.perf_counter()
         ev0.record(stream)
         for _ in range(args.steps):
@@ -226,6 +252,7 @@ def run_native(args, emit=print):
         ev1.record(stream)
         barrier()
         wall = time.perf_counter() - t_wall
+        clocks.mark_end()
     dev_ms = ev0.elapsed_time(ev1)
     clock_summary = clocks.summary()
 
