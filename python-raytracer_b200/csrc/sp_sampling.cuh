@@ -37,8 +37,11 @@ SP_DEV void sp_camera_ray(const DCamera& cam, uint32_t pixel, uint32_t sample, u
 
 // Sample a direction for a diffuse bounce at `origin` with shading normal N; returns the estimator
 // weight  clip(N.d, 0, 1) / pdf(d) / pi  (diffuse.py:76-81), 0 if the sample carries nothing.
-SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float w_cos, uint32_t pix,
-                               uint32_t path, float3& dir) {
+// `imp`: the importance list (centre.xyz, radius).  sc.importance lives in the kernel-parameter bank, where the
+// per-lane index of the picked cap serialises the access; callers that keep a copy in shared memory pass that.
+template <typename ImpList>
+SP_DEV float sp_sample_diffuse_with(const DScene& sc, const ImpList& imp, float3 origin, float3 N, float w_cos, uint32_t pix,
+                                    uint32_t path, float3& dir) {
     float u[4];
     sp_draw4_keys(pix, path, SP_BLOCK_DIRECTION, sc.philox_keys, u);
     float sn, cs;
@@ -55,11 +58,12 @@ SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float 
         z = fast_sqrt(1.f - u[2]);
     } else {                                                 // spherical_caps_pdf.generate
         int pick = min((int)(u[3] * (float)l), l - 1);
-        float3 to_c = sc.importance[pick].center - origin;
+        const float4 ip = imp(pick);
+        float3 to_c = xyz(ip) - origin;
         float d2 = dot(to_c, to_c);
         float inv = rsqrtf(d2);
         w = to_c * inv;
-        float ratio = clamp01(sc.importance[pick].radius * inv);
+        float ratio = clamp01(ip.w * inv);
         float cmax = fast_sqrt(1.f - ratio * ratio);
         z = 1.f + u[2] * (cmax - 1.f);
         s = fast_sqrt(fmaxf(1.f - z * z, 0.f));
@@ -74,14 +78,22 @@ SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float 
         float caps = 0.f;
 #pragma unroll 2
         for (int i = 0; i < l; ++i) {
-            float3 to_c = sc.importance[i].center - origin;
+            const float4 ii = imp(i);
+            float3 to_c = xyz(ii) - origin;
             float d2 = dot(to_c, to_c);
             float inv = rsqrtf(d2);
-            float ratio = clamp01(sc.importance[i].radius * inv);
+            float ratio = clamp01(ii.w * inv);
             float cmax = fast_sqrt(1.f - ratio * ratio);
             if (dot(dir, to_c) * inv > cmax) caps += __fdividef(1.f, (1.f - cmax) * 2.f * SP_PI);
         }
         pdf = pdf * w_cos + (caps * sc.inv_n_importance) * (1.f - w_cos);
     }
     return __fdividef(ndl, pdf) * (1.f / SP_PI);
+}
+
+SP_DEV float sp_sample_diffuse(const DScene& sc, float3 origin, float3 N, float w_cos, uint32_t pix,
+                               uint32_t path, float3& dir) {
+    auto imp = [&](int i) { return make_float4(sc.importance[i].center.x, sc.importance[i].center.y, sc.importance[i].center.z,
+                                               sc.importance[i].radius); };
+    return sp_sample_diffuse_with(sc, imp, origin, N, w_cos, pix, path, dir);
 }

@@ -45,6 +45,7 @@ struct WarpShared {
     uint32_t seg[SPW_N_QUEUES][8];                 // per work-item segment: SPW_SEG_* constants
     uint2 cls[SPW_MAX_COLLIDERS];                  // per collider: what a hit does (sp_hit_class below)
     float2 src_info[SPW_MAX_COLLIDERS];            // per collider: position in the chunk's id array (as int bits), cosine-pdf weight
+    float4 imp[SP_MAX_IMPORTANCE];                 // importance list (centre, radius): indexed per lane when a cap is picked
     int ids[SPW_MAX_COLLIDERS];                    // position in the chunk's id array -> collider id
     float4 lite[SPW_MAX_COLLIDERS];                // per collider: albedo / emitted colour, 1 / diffuse_rays
 };
@@ -188,6 +189,8 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
         sh.src_info[i].y = reinterpret_cast<const DColInfo*>(&raw)->w_cos;
         sh.lite[i] = __ldg(sc.col_lite + i);
     }
+    if (tid < (uint32_t)sc.n_importance)
+        sh.imp[tid] = make_float4(sc.importance[tid].center.x, sc.importance[tid].center.y, sc.importance[tid].center.z, sc.importance[tid].radius);
     if (tid < SPW_WARPS * SPW_N_QUEUES * 2) reinterpret_cast<uint32_t*>(sh.slab)[tid] = 0u;
     if (tid <= (uint32_t)sc.n_fan_classes) {
         // slots per slab: about an eighth of what a warp can emit in this launch, so that the unused tails stay a
@@ -288,7 +291,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                 r.path = sp_child_path(__float_as_uint(q1.w), child);
                 const float2 si = sh.src_info[meta_src(r.meta)];      // fan records always name their source
                 self_tag = __float_as_int(si.x);
-                const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), si.y, r.pix, r.path, r.d);
+                const float weight = sp_sample_diffuse_with(sc, [&](int i) { return sh.imp[i]; }, r.o, xyz(q1), si.y, r.pix, r.path, r.d);
                 r.thr = r.thr * weight;
                 active = weight > 0.f;                         // zero-weight samples cannot contribute: not traced
             }
