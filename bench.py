@@ -331,8 +331,8 @@ def run_native(args, emit=print):
         "flop_per_ray": FLOP_PER_RAY_CORNELL, "rays_per_launch": totals["rays"] / n_launch,
         "avg_launch_ms": totals["level_ms"] / n_launch, "traffic": None,
         "note": "fused generate+intersect+shade kernel: neither HBM- nor tensor-bound; the binding resource is "
-                "instruction issue (ncu, profiles/r1_v14_warp_kernel.md: 0.67 of 1.0 instructions per scheduler per "
-                "cycle at 32 resident warps per SM, pipes FMA 24 % / ALU 44 % / MUFU 16 % / LSU 29 %, ~1000 warp "
+                "instruction issue (ncu, profiles/r1_v14_warp_kernel.md: 0.71 of 1.0 instructions per scheduler per "
+                "cycle at 32 resident warps per SM, pipes FMA 26 % / ALU 47 % / MUFU 17 % / LSU 29 %, ~950 warp "
                 "instructions per 32 rays of which the 8 collider tests are ~285; achieved counts only the "
                 "algorithmic intersection flops of SURVEY 8(d))",
     }
