@@ -1073,7 +1073,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
         }
         // records written by level L-1 and read by level L: 48 B each way
         for (int L = 1; L <= n_levels; ++L)
-            for (int k = 0; k < ncl; ++k) st->queue_bytes += 2ull * 48ull * counts[(size_t)L * ncl + k];
+            for (int k = 0; k < 1 + SP_MAX_FAN_CLASSES; ++k) st->queue_bytes += 2ull * 48ull * counts[(size_t)L * ncl + k];
     }
     return 0;
 }

@@ -176,8 +176,10 @@ struct RayQueue {
 
 #define SP_MAX_LEVELS 64
 // Per-level counters live in one device array so a whole chunk of levels needs a single memset:
-//   counts[level][0] = ray-queue records, counts[level][1 + c] = fan-queue records of class c
-#define SP_COUNTS_PER_LEVEL (1 + SP_MAX_FAN_CLASSES)
+//   counts[level][0] = ray-queue records, counts[level][1 + c] = fan-queue records of class c,
+//   counts[level][1 + SP_MAX_FAN_CLASSES + k] = work counter of segment k of the launch that consumes the level
+//   (sp_warp_kernel.cuh: items handed out so far)
+#define SP_COUNTS_PER_LEVEL (2 * (1 + SP_MAX_FAN_CLASSES))
 
 struct DeviceStats;
 struct LevelOut {

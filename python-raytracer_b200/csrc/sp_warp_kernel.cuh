@@ -33,6 +33,7 @@
 #ifndef SPW_CTAS
 #define SPW_CTAS 4                   // resident CTAs per SM the register allocation aims for (64 registers, no spills; measured: 3 CTAs at 80 registers -4 %, 5 at 48 -6 %, 6 at 40 -5 %)
 #endif
+#define SPW_BATCH 4                  // iterations (of 32 items) a warp draws from the work counter at a time
 #define SPW_STASH_WORDS 14           // o d thr pix path meta t (id | orient)
 #define SPW_STASH_CAP 64             // < 32 left over + 32 pushed
 #define SPW_MAX_COLLIDERS 64           // = SP_BVH_MIN_COLLIDERS: larger scenes go through the BVH variant
@@ -199,7 +200,6 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
         const uint32_t per_warp = total / (gridDim.x * SPW_WARPS * 8u);
         while (slab_size < 256u && slab_size * 2u <= per_warp) slab_size *= 2u;
         // segment 0: explicit ray records; segment 1 + c: the children of fan class c
-        const uint32_t stride = gridDim.x * SPW_WARPS * 32u;
         uint32_t mult = 1u, n_items = n_rays, fan_base = 0u;
         if (tid > 0) {
             mult = (uint32_t)sc.fan_mult[tid - 1];
@@ -229,12 +229,10 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
     uint32_t* const slabs = &sh.slab[warp][0][0];
     uint32_t n_st = 0;                                         // entries in the stash (warp-uniform)
     uint32_t traced = 0;                                       // rays traced by this warp (warp-uniform)
-    const uint32_t stride = gridDim.x * SPW_WARPS * 32u;
 
     for (int seg = 0; seg <= sc.n_fan_classes; ++seg) {
         const volatile uint32_t* sg = sh.seg[seg];
         const uint32_t n_items = sg[SPW_SEG_ITEMS];
-        uint32_t wb = (blockIdx.x * SPW_WARPS + warp) * 32u;
         // Record pipeline: the three vectors of the record a lane needs in iteration i + 1 are copied into the lane's
         // own shared-memory slot (cp.async, no registers) while iteration i runs; the global-memory round trip, a
         // quarter of the stall samples of the single-ray levels, is off the critical path.
@@ -256,9 +254,19 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             }
             sp_cp_async_commit();
         };
-        if (wb < n_items) fetch(wb);
+        // Work distribution: warps draw batches of SPW_BATCH consecutive iterations from a per-segment counter (the
+        // level's queue-count block holds it, zeroed by the host with the counts).  A static split leaves a fifth of
+        // the warp slots idle at the end of a launch (rays differ in cost: glass, stash shading); the counter's round
+        // trip is hidden by drawing the next batch while the current one runs.
+        uint32_t* const work = const_cast<uint32_t*>(a.in_counts) + SPW_N_QUEUES + seg;
+        uint32_t pending = 0;                                  // lane 0: start of the batch after the current one
+        auto draw = [&]() { if (sp_lane_id() == 0) pending = atomicAdd(work, 32u * SPW_BATCH); };
+        auto drawn = [&]() { return __reduce_max_sync(0xffffffffu, sp_lane_id() == 0 ? pending : 0u); };
+        draw();
+        uint32_t wb = drawn(), left = SPW_BATCH;
+        if (wb < n_items) { draw(); fetch(wb); }
 #pragma unroll 1
-        for (; wb < n_items; wb += stride) {
+        while (wb < n_items) {
             const uint32_t lane = sp_lane_id();
             bool active = wb + lane < n_items;
             Ray r;
@@ -270,7 +278,13 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             if (active) { q0 = my_rec[0]; q1 = my_rec[32]; q2 = my_rec[64]; }
             r.meta = __float_as_uint(q2.w);
             active = active && r.meta != SP_META_DEAD;
-            if (wb + stride < n_items) fetch(wb + stride);     // the slot has been read: refill it for the next iteration
+            // first item of the next iteration: the next 32 of this batch, or the batch drawn earlier
+            uint32_t next = wb + 32u;
+            if (--left == 0u) {
+                next = drawn(); left = SPW_BATCH;
+                if (next < n_items) draw();
+            }
+            if (next < n_items) fetch(next);                   // the slot has been read: refill it for the next iteration
             if (seg == 0) {
                 if (active) {
                     r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
@@ -397,6 +411,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                     }
                 }
             }
+            wb = next;
         }
     }
 
