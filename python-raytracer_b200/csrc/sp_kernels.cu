@@ -33,6 +33,9 @@
 #ifndef SP_CTAS_FULL
 #define SP_CTAS_FULL 4
 #endif
+#ifndef SP_LEVEL_DYNAMIC
+#define SP_LEVEL_DYNAMIC 1
+#endif
 #define SP_CTAS_PER_SM(FEAT) ((((FEAT) & (SP_F_TEX | SP_F_GLOSSY | SP_F_THIN | SP_F_SKY | SP_F_BVH)) == 0u) ? SP_CTAS_MC : SP_CTAS_FULL)
 
 SP_DEV void sp_stage_chunk(float4* __restrict__ dst, const DScene& sc, const GeomStream& gs, int c) {
@@ -125,16 +128,27 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         for (uint32_t i = tid; i < 256u; i += SP_BLOCK) s_lin_lut[i] = c_decode[SP_DECODE_LINEAR][i];
     ctx.lin_lut = s_lin_lut;
     if (tid < sizeof(sh.cnt) / sizeof(uint32_t)) reinterpret_cast<uint32_t*>(sh.cnt)[tid] = 0u;
+    // Work distribution of full runs: CTAs draw their 512-item iterations from a counter (first word of the work
+    // block behind the level's queue counts, zeroed by the host) instead of striding over them; rays differ in
+    // cost, and a static split leaves SMs idle at the end of every launch.  The draw for iteration i + 1 is issued
+    // at the top of iteration i and handed to the CTA through shared memory behind barrier (C).
+    __shared__ uint32_t s_work[2];
+    const bool dynamic = SP_LEVEL_DYNAMIC && a.run == SP_RUN_FULL;
+    uint32_t* const work = const_cast<uint32_t*>(a.in_counts) + SP_COUNTS_PER_LEVEL / 2;
+    if (dynamic && tid == 0) s_work[0] = atomicAdd(work, (uint32_t)SP_BATCH);
     __syncthreads();
 #ifdef SP_PHASE_TIMING
     unsigned long long phase_acc[6] = {0, 0, 0, 0, 0, 0};
     long long tick__ = clock64();
 #endif
     uint32_t parity = 0;
-    for (unsigned long long base64 = (unsigned long long)blockIdx.x * SP_BATCH; base64 < total;
-         base64 += (unsigned long long)gridDim.x * SP_BATCH, parity ^= 1u) {
+    for (unsigned long long base64 = dynamic ? (unsigned long long)s_work[0] : (unsigned long long)blockIdx.x * SP_BATCH;
+         base64 < total;
+         base64 = dynamic ? (unsigned long long)s_work[parity ^ 1u] : base64 + (unsigned long long)gridDim.x * SP_BATCH, parity ^= 1u) {
         IterCounters& cn = sh.cnt[parity];
         const uint32_t base = (uint32_t)base64;
+        uint32_t drawn = 0;
+        if (dynamic && tid == 0) drawn = atomicAdd(work, (uint32_t)SP_BATCH);
         // the pass loop is deliberately not unrolled: one copy of the generate/intersect code in the
         // instruction cache
 #pragma unroll 1
@@ -406,6 +420,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
             }
         }
         SP_TICK(4);
+        if (dynamic && tid == 0) s_work[parity ^ 1u] = drawn;
         __syncthreads();                                                            // (C) the exchange area is free again
         SP_TICK(5);
     }

@@ -33,7 +33,9 @@
 #ifndef SPW_CTAS
 #define SPW_CTAS 4                   // resident CTAs per SM the register allocation aims for (64 registers, no spills; measured: 3 CTAs at 80 registers -4 %, 5 at 48 -6 %, 6 at 40 -5 %)
 #endif
-#define SPW_BATCH 4                  // iterations (of 32 items) a warp draws from the work counter at a time
+#ifndef SPW_BATCH
+#define SPW_BATCH 8                  // iterations (of 32 items) a warp draws from the work counter at a time; measured on the
+#endif                               // headline frame: 1 -> 17.5, 2 -> 24.9, 4 -> 34.1, 8 -> 35.5, 16 -> 35.4 Grays/s (same-address atomics)
 #define SPW_STASH_WORDS 14           // o d thr pix path meta t (id | orient)
 #define SPW_STASH_CAP 64             // < 32 left over + 32 pushed
 #define SPW_MAX_COLLIDERS 64           // = SP_BVH_MIN_COLLIDERS: larger scenes go through the BVH variant
@@ -166,7 +168,7 @@ SP_DEV uint32_t sp_lane_id() { uint32_t r; asm("mov.u32 %0, %%laneid;" : "=r"(r)
 SP_DEV uint32_t sp_lanemask_lt() { uint32_t r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
 
 // per-segment constants (shared memory, read where they are needed instead of living in registers)
-enum { SPW_SEG_ITEMS = 0, SPW_SEG_MULT, SPW_SEG_MAGIC_LO, SPW_SEG_MAGIC_HI, SPW_SEG_BASE, SPW_SEG_SLAB, SPW_SEG_WORDS = 8 };
+enum { SPW_SEG_ITEMS = 0, SPW_SEG_MULT, SPW_SEG_MAGIC_LO, SPW_SEG_MAGIC_HI, SPW_SEG_BASE, SPW_SEG_SLAB, SPW_SEG_BATCH, SPW_SEG_WORDS = 8 };
 
 template <uint32_t FEAT>
 __global__ void __launch_bounds__(SPW_BLOCK, SPW_CTAS)
@@ -212,6 +214,9 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
         const unsigned long long magic = tid > 0 ? sc.fan_magic[tid - 1] : 0ull;
         sg[SPW_SEG_MAGIC_LO] = (uint32_t)magic; sg[SPW_SEG_MAGIC_HI] = (uint32_t)(magic >> 32);
         sg[SPW_SEG_SLAB] = slab_size;
+        // iterations per draw.  Shrinking it for short segments (so that every warp gets a share) measured slower on the
+        // headline frame (33.2 vs 35.3 Grays/s): warps that find a short segment drained simply move on to the next one.
+        sg[SPW_SEG_BATCH] = (uint32_t)SPW_BATCH;
     }
     __syncthreads();
     {
@@ -254,16 +259,17 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             }
             sp_cp_async_commit();
         };
-        // Work distribution: warps draw batches of SPW_BATCH consecutive iterations from a per-segment counter (the
+        // Work distribution: warps draw batches of up to SPW_BATCH consecutive iterations from a per-segment counter (the
         // level's queue-count block holds it, zeroed by the host with the counts).  A static split leaves a fifth of
         // the warp slots idle at the end of a launch (rays differ in cost: glass, stash shading); the counter's round
         // trip is hidden by drawing the next batch while the current one runs.
         uint32_t* const work = const_cast<uint32_t*>(a.in_counts) + SPW_N_QUEUES + seg;
         uint32_t pending = 0;                                  // lane 0: start of the batch after the current one
-        auto draw = [&]() { if (sp_lane_id() == 0) pending = atomicAdd(work, 32u * SPW_BATCH); };
+        const uint32_t batch = sg[SPW_SEG_BATCH];
+        auto draw = [&]() { if (sp_lane_id() == 0) pending = atomicAdd(work, 32u * batch); };
         auto drawn = [&]() { return __reduce_max_sync(0xffffffffu, sp_lane_id() == 0 ? pending : 0u); };
         draw();
-        uint32_t wb = drawn(), left = SPW_BATCH;
+        uint32_t wb = drawn(), left = batch;
         if (wb < n_items) { draw(); fetch(wb); }
 #pragma unroll 1
         while (wb < n_items) {
@@ -281,7 +287,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             // first item of the next iteration: the next 32 of this batch, or the batch drawn earlier
             uint32_t next = wb + 32u;
             if (--left == 0u) {
-                next = drawn(); left = SPW_BATCH;
+                next = drawn(); left = sg[SPW_SEG_BATCH];
                 if (next < n_items) draw();
             }
             if (next < n_items) fetch(next);                   // the slot has been read: refill it for the next iteration
