@@ -320,7 +320,7 @@ def run_native(args, emit=print):
     level_s = totals["level_ms"] * 1e-3
     n_launch = max(totals["level_launches"], 1)
     flops = FLOP_PER_RAY_CORNELL * totals["rays"]
-    traffic_file = REPO / "profiles" / "r1_v14_dram_per_ray.json"      # from the committed ncu launch list of this build
+    traffic_file = REPO / "profiles" / "r1_v15_dram_per_ray.json"      # from the committed ncu launch list of this build
     dram_per_ray = json.loads(traffic_file.read_text())["dram_bytes_per_ray"] if traffic_file.exists() else None
     traffic = dram_per_ray * totals["rays"] / n_launch if dram_per_ray else None
     roofline = {
@@ -331,7 +331,7 @@ def run_native(args, emit=print):
         "flop_per_ray": FLOP_PER_RAY_CORNELL, "rays_per_launch": totals["rays"] / n_launch,
         "avg_launch_ms": totals["level_ms"] / n_launch, "traffic": None,
         "note": "fused generate+intersect+shade kernel: neither HBM- nor tensor-bound; the binding resource is "
-                "instruction issue (ncu, profiles/r1_v14_warp_kernel.md: 0.71 of 1.0 instructions per scheduler per "
+                "instruction issue (ncu, profiles/r1_v15_warp_kernel.md: 0.73 of 1.0 instructions per scheduler per "
                 "cycle at 32 resident warps per SM, pipes FMA 26 % / ALU 47 % / MUFU 17 % / LSU 29 %, ~950 warp "
                 "instructions per 32 rays of which the 8 collider tests are ~285; achieved counts only the "
                 "algorithmic intersection flops of SURVEY 8(d))",

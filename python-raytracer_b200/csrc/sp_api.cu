@@ -976,11 +976,11 @@ int sp_scene_commit(sp_scene* s) {
 // =================================================================================================
 // wavefront driver
 // =================================================================================================
-#define SP_DEFAULT_CHUNK ((int64_t)4 << 20)      /* primaries per chunk: measured 262 Ki -> 16.6, 1 Mi -> 18.4, 4 Mi -> 18.9 Grays/s */
+#define SP_DEFAULT_CHUNK ((int64_t)8 << 20)      /* primaries per chunk: measured 4 Mi -> 35.3, 8 Mi -> 35.7, 16 Mi -> 35.8 Grays/s (v14; 262 Ki -> 16.6, 4 Mi -> 18.9 with v10) */
 
 static int ensure_queues(sp_scene* s, uint64_t primaries) {
     // Queues are sized for 24 records per primary of a chunk (a diffuse first bounce turns 1 primary into
-    // diffuse_rays secondary hits): 96 Mi records (27 GB with two fan classes) for a full 4 Mi-primary
+    // diffuse_rays secondary hits): 192 Mi records (54 GB with two fan classes) for a full 8 Mi-primary
     // chunk, proportionally less for small jobs.  The driver below measures the real occupancy on a small
     // first chunk and then sizes later chunks to fit.
     const int64_t chunk = s->opt_chunk > 0 ? s->opt_chunk : SP_DEFAULT_CHUNK;
