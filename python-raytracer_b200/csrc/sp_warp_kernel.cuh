@@ -6,7 +6,7 @@
 // iteration in shared memory, regroups them by the material they hit and shades them behind a CTA barrier;
 // ncu put a third of its warp instructions into that bookkeeping (shared-memory atomics, ballots, list
 // handling, chunk hand-out) and 8 % of its issue cycles into the two barriers.  Here every warp is on its
-// own — there is no barrier and no atomic in the loop:
+// own — no barrier and no shared-memory atomic in the loop, one global atomic per 8 iterations:
 //   * the cheap, common outcomes of a hit are handled on the spot: a Diffuse hit writes its fan record
 //     (diffuse.py:25-124: hit point, shading normal, throughput x albedo), an Emissive hit adds
 //     throughput x colour to its pixel (emissive.py:21-23), a hit that is black by construction does nothing;
@@ -18,7 +18,13 @@
 //     cannot take a whole request is finished by the first ranks and the rest go to a fresh one, so the
 //     only unused slots are each warp's last slab; they are filled with dead records at exit;
 //   * work items are walked segment by segment (ray records, then each fan class), so the class of an item and
-//     its constants (multiplicity, magic divisor, queue base) are uniform and read from shared memory.
+//     its constants (multiplicity, magic divisor, queue base) are uniform and read from shared memory; inside a
+//     segment the warps draw batches of 8 iterations from a counter (rays differ in cost; a static split left a
+//     fifth of the warp slots idle at the end of every launch);
+//   * the record a lane needs in its next iteration is copied into the lane's shared-memory slot with cp.async
+//     while the current iteration runs;
+//   * the warp's index goes through __reduce_max_sync, which puts it and everything derived from it (item cursor,
+//     stash / slab addresses, counters) on the uniform datapath: 64 registers, 4 CTAs per SM, no spills to speak of.
 // Eligibility (host, sp_use_warp_kernel): queue-fed level, material set Diffuse + Refractive + Emissive
 // without textures, one geometry chunk, no BVH, fewer than 64 colliders, fan multiplicities <= 1024.
 #pragma once
