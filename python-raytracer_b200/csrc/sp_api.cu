@@ -434,7 +434,7 @@ struct BuiltBvh {
 };
 
 static int bvh_build_rec(BuiltBvh& out, std::vector<int>& order, int first, int count, const std::vector<Aabb>& boxes,
-                         const std::vector<int>& item_of, Aabb& bounds) {
+                         const std::vector<int>& item_of, Aabb& bounds, int depth = 0) {
     // returns the child code of this subtree (>= 0 node index, < 0 leaf) and its bounds
     for (int k = 0; k < 3; ++k) { bounds.lo[k] = 1e300; bounds.hi[k] = -1e300; }
     for (int i = first; i < first + count; ++i)
@@ -453,17 +453,74 @@ static int bvh_build_rec(BuiltBvh& out, std::vector<int>& order, int first, int 
             const double c = 0.5 * (boxes[order[i]].lo[k] + boxes[order[i]].hi[k]);
             clo[k] = std::min(clo[k], c); chi[k] = std::max(chi[k], c);
         }
-    int axis = 0;
-    for (int k = 1; k < 3; ++k) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
-    const int half = count / 2;
-    std::nth_element(order.begin() + first, order.begin() + first + half, order.begin() + first + count, [&](int a, int b) {
-        return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis];
-    });
+    // Binned surface-area heuristic: 16 bins of box centres per axis, the split that minimises
+    // area(left) * n_left + area(right) * n_right.  Falls back to the median along the widest axis when no bin
+    // boundary separates the centres, or when the tree gets so deep that only balanced splits keep it within the
+    // traversal stack (32 entries).
+    auto half_area = [](const Aabb& b) {
+        const double dx = std::max(b.hi[0] - b.lo[0], 0.0), dy = std::max(b.hi[1] - b.lo[1], 0.0), dz = std::max(b.hi[2] - b.lo[2], 0.0);
+        return dx * dy + dy * dz + dz * dx;
+    };
+    const int NB = 16;
+    int best_axis = -1, best_bin = -1;
+    double best_cost = 1e300;
+    int log2_count = 0;
+    while ((1 << log2_count) < count) ++log2_count;
+    if (depth + log2_count < 28) {                           // a median split from here on still fits the 32-entry stack
+        for (int k = 0; k < 3; ++k) {
+            const double ext = chi[k] - clo[k];
+            if (!(ext > 0.0)) continue;
+            Aabb bb_[NB]; int cnt[NB];
+            for (int b = 0; b < NB; ++b) { cnt[b] = 0; for (int q = 0; q < 3; ++q) { bb_[b].lo[q] = 1e300; bb_[b].hi[q] = -1e300; } }
+            for (int i = first; i < first + count; ++i) {
+                const Aabb& bx = boxes[order[i]];
+                const double c = 0.5 * (bx.lo[k] + bx.hi[k]);
+                const int b = std::min(NB - 1, (int)((c - clo[k]) / ext * NB));
+                cnt[b]++;
+                for (int q = 0; q < 3; ++q) { bb_[b].lo[q] = std::min(bb_[b].lo[q], bx.lo[q]); bb_[b].hi[q] = std::max(bb_[b].hi[q], bx.hi[q]); }
+            }
+            double right_area[NB]; int right_cnt[NB];
+            Aabb acc; for (int q = 0; q < 3; ++q) { acc.lo[q] = 1e300; acc.hi[q] = -1e300; }
+            int n = 0;
+            for (int b = NB - 1; b > 0; --b) {
+                for (int q = 0; q < 3; ++q) { acc.lo[q] = std::min(acc.lo[q], bb_[b].lo[q]); acc.hi[q] = std::max(acc.hi[q], bb_[b].hi[q]); }
+                n += cnt[b];
+                right_area[b] = n ? half_area(acc) : 0.0; right_cnt[b] = n;
+            }
+            for (int q = 0; q < 3; ++q) { acc.lo[q] = 1e300; acc.hi[q] = -1e300; }
+            n = 0;
+            for (int b = 0; b + 1 < NB; ++b) {                 // split after bin b
+                for (int q = 0; q < 3; ++q) { acc.lo[q] = std::min(acc.lo[q], bb_[b].lo[q]); acc.hi[q] = std::max(acc.hi[q], bb_[b].hi[q]); }
+                n += cnt[b];
+                if (n == 0 || right_cnt[b + 1] == 0) continue;
+                const double cost = half_area(acc) * n + right_area[b + 1] * right_cnt[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = k; best_bin = b; }
+            }
+        }
+    }
+    int half;
+    if (best_axis >= 0) {
+        const int k = best_axis;
+        const double ext = chi[k] - clo[k];
+        auto bin_of = [&](int id) {
+            const double c = 0.5 * (boxes[id].lo[k] + boxes[id].hi[k]);
+            return std::min(NB - 1, (int)((c - clo[k]) / ext * NB));
+        };
+        auto mid = std::partition(order.begin() + first, order.begin() + first + count, [&](int id) { return bin_of(id) <= best_bin; });
+        half = (int)(mid - (order.begin() + first));
+    } else {
+        int axis = 0;
+        for (int k = 1; k < 3; ++k) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+        half = count / 2;
+        std::nth_element(order.begin() + first, order.begin() + first + half, order.begin() + first + count, [&](int a, int b) {
+            return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis];
+        });
+    }
     const int me = (int)out.nodes.size() / 4;
     out.nodes.resize(out.nodes.size() + 4);
     Aabb ba, bb;
-    const int ca = bvh_build_rec(out, order, first, half, boxes, item_of, ba);
-    const int cb = bvh_build_rec(out, order, first + half, count - half, boxes, item_of, bb);
+    const int ca = bvh_build_rec(out, order, first, half, boxes, item_of, ba, depth + 1);
+    const int cb = bvh_build_rec(out, order, first + half, count - half, boxes, item_of, bb, depth + 1);
     out.nodes[4 * me] = make_float4((float)ba.lo[0], (float)ba.lo[1], (float)ba.lo[2], (float)ba.hi[0]);
     out.nodes[4 * me + 1] = make_float4((float)ba.hi[1], (float)ba.hi[2], (float)bb.lo[0], (float)bb.lo[1]);
     out.nodes[4 * me + 2] = make_float4((float)bb.lo[2], (float)bb.hi[0], (float)bb.hi[1], (float)bb.hi[2]);
