@@ -181,12 +181,12 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 active = false;
             } else if (item < n_rays) {
                 const uint32_t s = (uint32_t)item;
-                const float4 q2 = a.in_rays.q2[s];
+                // all three vectors at once: one memory round trip (a dead record's q0 / q1 are simply ignored)
+                const float4 q2 = a.in_rays.q2[s], q0 = a.in_rays.q0[s], q1 = a.in_rays.q1[s];
                 r.meta = __float_as_uint(q2.w);
                 if (r.meta == SP_META_DEAD) {
                     active = false;
                 } else {
-                    const float4 q0 = a.in_rays.q0[s], q1 = a.in_rays.q1[s];
                     r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
                     r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
                 }
@@ -204,12 +204,11 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 const uint32_t rec = (m == 1u) ? local : (uint32_t)__umul64hi((unsigned long long)local, sc.fan_magic[c]);
                 const uint32_t child = local - rec * m;
                 const uint32_t s = a.in_fan_base[c] + rec;
-                const float4 q2 = a.in_fans.q2[s];
+                const float4 q2 = a.in_fans.q2[s], q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
                 r.meta = __float_as_uint(q2.w);
                 if (r.meta == SP_META_DEAD) {
                     active = false;
                 } else {
-                    const float4 q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
                     r.o = xyz(q0); r.thr = xyz(q2);
                     r.pix = __float_as_uint(q0.w);
                     r.path = sp_child_path(__float_as_uint(q1.w), child);
