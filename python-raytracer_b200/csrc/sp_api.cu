@@ -159,6 +159,8 @@ struct sp_scene {
     std::vector<int32_t> importance, shadow_ids;
     // ---- options ------------------------------------------------------------------------------------
     int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0, opt_bvh = 1, opt_warp = 1;
+    int64_t opt_chunk_fixed = 0;                 // 1: a chunk that overflows is an error instead of being retried smaller
+    int64_t chunk_limit = 0;                     // learnt from overflows: no chunk larger than this
     // ---- device residency -----------------------------------------------------------------------------
     DScene d{};
     int n_levels = 1;
@@ -167,7 +169,7 @@ struct sp_scene {
     DevBuf<float> d_lin;                // resolve outputs (device copies, reused across frames)
     DevBuf<uint8_t> d_u8;
     std::vector<cudaEvent_t> events;
-    DevBuf<float4> geom_all, geom_shadow, accum;
+    DevBuf<float4> geom_all, geom_shadow, accum, scratch;
     DevBuf<int> off_all, off_shadow;
     DevBuf<int2> slot_shadow;
     DevBuf<DCollider> d_cols;
@@ -188,7 +190,11 @@ struct sp_scene {
     uint32_t ray_cap = 0, fan_cap = 0;
     uint32_t chunk_primaries = 0;
     double use_ray = 0.0, use_fan = 0.0;         // peak records per primary seen so far
-    int grid0 = 0, grid_q = 0;                   // CTAs of level-0 / queue-fed launches
+    int grid0 = 0, grid_q = 0;                   // CTAs of level-0 / queue-fed launches of sp_level_kernel
+    int pgrid0 = 0, pgrid_q = 0;                 // the same for sp_path_kernel
+    bool use_path = false;                       // full runs go through sp_path_kernel
+    DevBuf<uint2> d_colcls;
+    DevBuf<float2> d_colsrc;
     uint32_t material_set = 0;                   // compiled kernel variant (sp_pick_material_set)
 
     ~sp_scene() { release_device(); release_textures(); }
@@ -205,8 +211,8 @@ struct sp_scene {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
 
-        geom_all.release(); geom_shadow.release(); accum.release(); off_all.release(); off_shadow.release();
-        slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
+        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); off_all.release(); off_shadow.release();
+        slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); d_colcls.release(); d_colsrc.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
         for (auto e : events) g_event_pool.push_back(e);
@@ -593,6 +599,20 @@ static BuiltBvh build_bvh(const std::vector<sp_collider>& cols, const std::vecto
     return out;
 }
 
+// Launch geometry of the two kernel families for this scene; sp_path_kernel is used when the scene qualifies and fits.
+static int pick_kernels(sp_scene* s) {
+    s->grid0 = sp_level_grid(g_device, s->d, s->material_set, true, false);
+    s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false, false);
+    if (s->grid0 < 1 || s->grid_q < 1) return fail("sp_level_kernel does not fit this device");
+    s->use_path = sp_use_path_kernel(s->d, s->material_set);
+    if (s->use_path) {
+        s->pgrid0 = sp_level_grid(g_device, s->d, s->material_set, true, true);
+        s->pgrid_q = sp_level_grid(g_device, s->d, s->material_set, false, true);
+        if (s->pgrid0 < 1 || s->pgrid_q < 1) s->use_path = false;
+    }
+    return 0;
+}
+
 // =================================================================================================
 // lifetime
 // =================================================================================================
@@ -861,7 +881,10 @@ int sp_scene_commit(sp_scene* s) {
     CUDA_TRY(s->d_prims.upload(dp));
     // deepest ray.depth that can exist: specular children stop at max_ray_depth, every diffuse
     // bounce adds one more level (diffuse.py tests diffuse_reflections, not depth)
-    s->n_levels = std::min(max_depth + max_dr + 1, SP_MAX_LEVELS - 1);
+    // (a first Diffuse hit always fans out, whatever max_diffuse_reflections says: diffuse.py:34)
+    bool any_diffuse = false;
+    for (int i = 0; i < n_mat; ++i) any_diffuse = any_diffuse || s->mats[i].kind == SP_MAT_DIFFUSE;
+    s->n_levels = std::min(max_depth + (any_diffuse ? std::max(max_dr, 1) : 0) + 1, SP_MAX_LEVELS - 1);
 
     std::vector<DCollider> dc((size_t)n_col);
     const int PL = 44;                                   // SP_DEV_PAYLOAD: 40 ABI slots + derived reciprocals
@@ -966,6 +989,60 @@ int sp_scene_commit(sp_scene* s) {
     }
     if (all.chunk_off.size() - 1 > 255) return fail("too many geometry chunks");
     CUDA_TRY(s->d_colinfo.upload(dinfo));
+    // What a hit on a collider does, as two words sp_path_kernel tests with a few instructions:
+    //   x: byte d = fan class an untextured Diffuse hit emits for a ray with diffuse_reflections == d (diffuse.py:34, 85), 0xFF = none
+    //   y: [0:8) the hit is stashed for its material's shading code while ray.depth < this, bit 8 untextured Emissive
+    //      (emissive.py:21-23, added on the spot), [9:12) 1 + stash bin (SP_BIN_*), [16:24) collider type
+    // and where the collider sits in the staged chunk (the ray's own collider is skipped there by position).
+    std::vector<uint2> dcls((size_t)n_col);
+    std::vector<float2> dsrc((size_t)n_col);
+    bool bin_used[SP_N_BINS] = {false, false, false, false, false};
+    {
+        std::vector<int> tag_of((size_t)n_col, -1);
+        if (all.chunk_off.size() == 2) {                  // one staged chunk: positions in its id array
+            GeomChunkHeader h0;
+            memcpy(&h0, all.data.data(), sizeof h0);
+            const int n_items = h0.n_sphere + h0.n_plane + h0.n_cuboid + h0.n_tri + h0.n_aax + h0.n_aay + h0.n_aaz;
+            const int* ids0 = reinterpret_cast<const int*>(all.data.data() + h0.off_ids);
+            for (int k = 0; k < n_items; ++k) tag_of[(size_t)ids0[k]] = k;
+        }
+        for (int i = 0; i < n_col; ++i) {
+            const sp_primitive& pr = s->prims[s->cols[i].primitive];
+            const sp_material& m = s->mats[pr.material];
+            const bool textured = m.color_tex >= 0 || m.normalmap_tex >= 0;
+            uint32_t fan = 0xFFFFFFFFu, misc = (uint32_t)s->cols[i].type << 16, limit = 255u;
+            int bin = -1;
+            switch (m.kind) {
+            case SP_MAT_DIFFUSE:
+                if (textured) { bin = SP_BIN_GENERIC; break; }
+                fan = 0u;
+                for (int dr = 0; dr < 4; ++dr) {
+                    uint32_t c = 0xFFu;
+                    if (dr < 1) c = (uint32_t)dm[pr.material].fan_class;
+                    else if (dr < m.max_diffuse_reflections) c = 0u;
+                    fan |= c << (8 * dr);
+                }
+                break;
+            case SP_MAT_EMISSIVE: if (m.color_tex >= 0) bin = SP_BIN_GENERIC; else misc |= 0x100u; break;
+            case SP_MAT_REFRACTIVE: bin = SP_BIN_REFR; limit = (uint32_t)std::min(std::max(pr.max_ray_depth, 0), 255); break;
+            case SP_MAT_THINFILM: bin = SP_BIN_THIN; limit = (uint32_t)std::min(std::max(pr.max_ray_depth, 0), 255); break;
+            case SP_MAT_GLOSSY: bin = SP_BIN_GLOSSY; break;
+            default: bin = SP_BIN_SKY; break;
+            }
+            if (bin >= 0) { misc |= ((uint32_t)(bin + 1) << 9) | limit; bin_used[bin] = true; }
+            dcls[(size_t)i] = make_uint2(fan, misc);
+            float2 src;
+            memcpy(&src.x, &tag_of[(size_t)i], sizeof(int));
+            src.y = (float)m.ambient_weight;
+            dsrc[(size_t)i] = src;
+        }
+    }
+    CUDA_TRY(s->d_colcls.upload(dcls));
+    CUDA_TRY(s->d_colsrc.upload(dsrc));
+    d.col_cls = s->d_colcls.p; d.col_src = s->d_colsrc.p;
+    d.n_stash_bins = 0;
+    for (int b = 0; b < 8; ++b) d.stash_slot[b] = -1;
+    for (int b = 0; b < SP_N_BINS; ++b) if (bin_used[b]) d.stash_slot[b] = d.n_stash_bins++;
     CUDA_TRY(s->geom_all.upload(all.data));
     CUDA_TRY(s->off_all.upload(all.chunk_off));
     CUDA_TRY(s->geom_shadow.upload(shadow.data));
@@ -1020,12 +1097,12 @@ int sp_scene_commit(sp_scene* s) {
         default: break;
         }
     }
-    if (d.bvh.n_nodes > 0) needed |= SP_F_BVH;
+    if (d.bvh.n_nodes > 0 || n_col > SP_SMALL_COLLIDERS) needed |= SP_F_BVH;     // large scenes: per-collider tables stay in global memory
     s->material_set = sp_pick_material_set(needed);
     s->d.use_warp_kernel = s->opt_warp ? 1 : 0;
-    s->grid0 = sp_level_grid(g_device, s->d, s->material_set, true);
-    s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false);
+    if (int rc = pick_kernels(s)) return rc;
     s->use_ray = s->use_fan = 0.0;
+    s->chunk_limit = 0;
     s->committed = true;
     return 0;
 }
@@ -1033,19 +1110,30 @@ int sp_scene_commit(sp_scene* s) {
 // =================================================================================================
 // wavefront driver
 // =================================================================================================
-#define SP_DEFAULT_CHUNK ((int64_t)8 << 20)      /* primaries per chunk: measured 4 Mi -> 35.3, 8 Mi -> 35.7, 16 Mi -> 35.8 Grays/s (v14; 262 Ki -> 16.6, 4 Mi -> 18.9 with v10) */
+// Primaries per chunk and records per queue when the caller sets neither.
+//   sp_path_kernel: a Diffuse bounce stays in registers / shared memory, only specular children and the fans behind
+//   them are queued (Cornell box: ~3 records per primary), so queues of 32 Mi records (1.5 GB per queue side; 9 GB in
+//   all for a scene with one fan class > 1) carry chunks of tens of millions of primaries.
+//   sp_level_kernel (option "warp_kernel" = 0, multi-chunk exhaustive walks): every bounce goes through the queues,
+//   24 records per primary of a chunk: 192 Mi records each (54 GB with two fan classes) for a full 8 Mi-primary
+//   chunk, proportionally less for small jobs.
+// A chunk that overflows a queue all the same is rendered again at half the size (see render loop below).
+#define SP_DEFAULT_CHUNK_LEVEL ((int64_t)8 << 20)
+#define SP_DEFAULT_CHUNK_PATH ((int64_t)64 << 20)
+#define SP_DEFAULT_CAP_PATH ((int64_t)32 << 20)
+
+static int64_t default_chunk(const sp_scene* s) {
+    return s->opt_chunk > 0 ? s->opt_chunk : (s->use_path ? SP_DEFAULT_CHUNK_PATH : SP_DEFAULT_CHUNK_LEVEL);
+}
 
 static int ensure_queues(sp_scene* s, uint64_t primaries) {
-    // Queues are sized for 24 records per primary of a chunk (a diffuse first bounce turns 1 primary into
-    // diffuse_rays secondary hits): 192 Mi records (54 GB with two fan classes) for a full 8 Mi-primary
-    // chunk, proportionally less for small jobs.  The driver below measures the real occupancy on a small
-    // first chunk and then sizes later chunks to fit.
-    const int64_t chunk = s->opt_chunk > 0 ? s->opt_chunk : SP_DEFAULT_CHUNK;
+    const int64_t chunk = default_chunk(s);
     int64_t auto_cap = 24 * (int64_t)std::min<uint64_t>(std::max<uint64_t>(primaries, 1), (uint64_t)chunk);
+    if (s->use_path) auto_cap = std::min<int64_t>(auto_cap, SP_DEFAULT_CAP_PATH);
     auto_cap = std::max<int64_t>((auto_cap + 0xFFFFF) & ~(int64_t)0xFFFFF, (int64_t)1 << 20);
     uint32_t want_ray = (uint32_t)std::min<int64_t>(s->opt_ray_cap > 0 ? s->opt_ray_cap : auto_cap, 0x7FFFFFF0ll);
     uint32_t want_fan = (uint32_t)std::min<int64_t>(s->opt_fan_cap > 0 ? s->opt_fan_cap : auto_cap, 0x7FFFFFF0ll);
-    for (int c = 0; c < s->d.n_fan_classes; ++c)       // the kernel counts work items in 32 bits
+    for (int c = 0; c < s->d.n_fan_classes; ++c)       // the kernels count work items in 32 bits
         want_fan = (uint32_t)std::min<uint64_t>(want_fan, 0x7FFFFFFFull / (uint64_t)std::max(s->d.fan_mult[c], 1));
     if (s->opt_ray_cap == 0 && s->ray_cap >= want_ray) want_ray = s->ray_cap;       // never shrink on our own
     if (s->opt_fan_cap == 0 && s->fan_cap >= want_fan) want_fan = s->fan_cap;
@@ -1067,12 +1155,16 @@ struct ChunkJob {
     float4* accum; int32_t* out_hit; float* out_t; float* out_o; float* out_d;
 };
 
-// Enqueue all levels of one chunk, wait, fold its counters into `st`.
-static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
+// Enqueue all levels of one chunk, wait, fold its counters into `st`.  `overflow` comes back true when a queue was
+// too small for the chunk: what the chunk added to job.accum is then incomplete and the caller discards it.
+static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overflow) {
+    overflow = false;
     int n_levels = (job.run == SP_RUN_FULL) ? s->n_levels : 1;
     if (s->opt_max_levels > 0) n_levels = std::min<int>(n_levels, (int)s->opt_max_levels);   // debugging aid
     const int ncl = SP_COUNTS_PER_LEVEL;
+    const bool path = s->use_path && job.run == SP_RUN_FULL;
     CUDA_TRY(cudaMemsetAsync(s->counts.p, 0, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
     for (int L = 0; L < n_levels; ++L) {
         LevelArgs a;
         memset(&a, 0, sizeof a);
@@ -1095,11 +1187,14 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
         a.out_hit = job.out_hit; a.out_t = job.out_t; a.out_o = job.out_o; a.out_d = job.out_d;
         a.shadow_slot = s->slot_shadow.p;
         CUDA_TRY(cudaEventRecord(s->events[L], s->stream));
-        CUDA_TRY(sp_launch_level(s->d, a, s->material_set, L == 0 ? s->grid0 : s->grid_q, s->stream));
+        const int grid = path ? (L == 0 ? s->pgrid0 : s->pgrid_q) : (L == 0 ? s->grid0 : s->grid_q);
+        CUDA_TRY(sp_launch_level(s->d, a, s->material_set, grid, path, s->stream));
     }
     CUDA_TRY(cudaEventRecord(s->events[n_levels], s->stream));
     std::vector<uint32_t> counts((size_t)(n_levels + 1) * ncl);
+    DeviceStats ds;
     CUDA_TRY(cudaMemcpyAsync(counts.data(), s->counts.p, counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(&ds, s->d_stats.p, sizeof ds, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
 
     uint64_t peak_r = 0, peak_f = 0;
@@ -1107,19 +1202,28 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
         peak_r = std::max<uint64_t>(peak_r, counts[(size_t)L * ncl]);
         for (int c = 0; c < s->d.n_fan_classes; ++c) peak_f = std::max<uint64_t>(peak_f, counts[(size_t)L * ncl + 1 + c]);
     }
+    if (ds.overflow >> 16)
+        return fail("internal consistency check failed in the wavefront kernels (SP_CHECKED build): code mask 0x%x", ds.overflow >> 16);
     if (job.n_items > 0) {
-        s->use_ray = std::max(s->use_ray, (double)peak_r / job.n_items);
-        s->use_fan = std::max(s->use_fan, (double)peak_f / job.n_items);
+        // a queue that overflowed stopped counting at the level that failed: later levels may have needed more
+        const double grow = (ds.overflow || peak_r > s->ray_cap || peak_f > s->fan_cap) ? 1.5 : 1.0;
+        s->use_ray = std::max(s->use_ray, grow * (double)peak_r / job.n_items);
+        s->use_fan = std::max(s->use_fan, grow * (double)peak_f / job.n_items);
     }
-    if (peak_r > s->ray_cap || peak_f > s->fan_cap)
-        return fail("wavefront queue overflow (%llu ray / %llu fan records for %u primaries; capacities %u / %u): "
-                    "raise ray_queue_capacity / fan_queue_capacity or lower chunk_primaries",
-                    (unsigned long long)peak_r, (unsigned long long)peak_f, job.n_items, s->ray_cap, s->fan_cap);
+    if (ds.overflow || peak_r > s->ray_cap || peak_f > s->fan_cap) {
+        overflow = true;
+        g_error = "wavefront queue overflow";
+        char buf[256];
+        snprintf(buf, sizeof buf, "wavefront queue overflow (%llu ray / %llu fan records for %u primaries; capacities %u / %u)",
+                 (unsigned long long)peak_r, (unsigned long long)peak_f, job.n_items, s->ray_cap, s->fan_cap);
+        g_error = buf;
+        return 0;
+    }
     if (st) {
         st->chunks += 1;
         st->kernel_launches += (uint64_t)n_levels;
         st->level_kernel_launches += (uint64_t)n_levels;
-        if (job.run == SP_RUN_FULL && sp_use_warp_kernel(s->d, s->material_set)) st->warp_kernel_launches += (uint64_t)(n_levels - 1);
+        if (path) st->warp_kernel_launches += (uint64_t)n_levels;
         st->peak_ray_records = std::max<uint64_t>(st->peak_ray_records, peak_r);
         st->peak_fan_records = std::max<uint64_t>(st->peak_fan_records, peak_f);
         for (int L = 0; L < n_levels; ++L) {
@@ -1131,6 +1235,20 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st) {
         // records written by level L-1 and read by level L: 48 B each way
         for (int L = 1; L <= n_levels; ++L)
             for (int k = 0; k < 1 + SP_MAX_FAN_CLASSES; ++k) st->queue_bytes += 2ull * 48ull * counts[(size_t)L * ncl + k];
+        for (int L = 0; L < SP_MAX_LEVELS && L < SP_MAX_DEPTH_LEVELS; ++L) {
+            st->rays_per_depth[L] += ds.rays[L];
+            st->rays_total += ds.rays[L];
+        }
+        st->shadow_rays += ds.shadow_rays;
+    }
+    if (getenv("SIGHTPY_PHASE_TIMING")) {             // only meaningful for -DSP_PHASE_TIMING builds of sp_kernels.cu
+        double tot = 0;
+        for (int k = 0; k < 6; ++k) tot += (double)ds.phase_cycles[k];
+        if (tot > 0)
+            fprintf(stderr, "[sightpy-b200] warp-cycles: generate %.1f %%, intersect %.1f %%, park+count %.1f %%, wait A %.1f %%, "
+                            "shade %.1f %%, wait C %.1f %%\n", 100.0 * ds.phase_cycles[0] / tot, 100.0 * ds.phase_cycles[1] / tot,
+                    100.0 * ds.phase_cycles[2] / tot, 100.0 * ds.phase_cycles[3] / tot, 100.0 * ds.phase_cycles[4] / tot,
+                    100.0 * ds.phase_cycles[5] / tot);
     }
     return 0;
 }
@@ -1146,46 +1264,44 @@ static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what
         s->d.philox_keys[2 * r + 1] = s->d.seed_hi + r * 0xBB67AE85u;
     }
     if (st) memset(st, 0, sizeof *st);
-    CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
     return ensure_queues(s, primaries);
 }
 
 static int end_call(sp_scene* s, sp_stats* st, cudaEvent_t t0, cudaEvent_t t1) {
-    DeviceStats ds;
-    CUDA_TRY(cudaMemcpyAsync(&ds, s->d_stats.p, sizeof ds, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaEventRecord(t1, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (st) {
-        for (int L = 0; L < SP_MAX_LEVELS && L < SP_MAX_DEPTH_LEVELS; ++L) {
-            st->rays_per_depth[L] = ds.rays[L];
-            st->rays_total += ds.rays[L];
-        }
-        st->shadow_rays = ds.shadow_rays;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, t0, t1);
         st->device_ms = ms;
     }
-    if (getenv("SIGHTPY_PHASE_TIMING")) {             // only meaningful for -DSP_PHASE_TIMING builds of sp_kernels.cu
-        double tot = 0;
-        for (int k = 0; k < 6; ++k) tot += (double)ds.phase_cycles[k];
-        if (tot > 0)
-            fprintf(stderr, "[sightpy-b200] warp-cycles: generate %.1f %%, intersect %.1f %%, park+count %.1f %%, wait A %.1f %%, "
-                            "shade %.1f %%, wait C %.1f %%\n", 100.0 * ds.phase_cycles[0] / tot, 100.0 * ds.phase_cycles[1] / tot,
-                    100.0 * ds.phase_cycles[2] / tot, 100.0 * ds.phase_cycles[3] / tot, 100.0 * ds.phase_cycles[4] / tot,
-                    100.0 * ds.phase_cycles[5] / tot);
-    }
-    if (ds.overflow) return fail("wavefront queue overflow: raise ray_queue_capacity / fan_queue_capacity or lower chunk_primaries");
     return 0;
 }
 
-// primaries per chunk given the occupancy seen so far
-static uint32_t pick_chunk(sp_scene* s, bool first) {
-    int64_t p = s->opt_chunk > 0 ? s->opt_chunk : SP_DEFAULT_CHUNK;
-    if (first && s->use_ray == 0.0 && s->use_fan == 0.0) p = std::min<int64_t>(p, 1 << 16);   // probe
+// Primaries of the next chunk given the queue occupancy seen so far.  Before anything is known the first chunk is
+// one sample of the whole region when that is at most 16 Mi primaries (representative of the frame, unlike its
+// first rows), else a 64 Ki-primary probe.
+static uint32_t pick_chunk(sp_scene* s, uint64_t region) {
+    int64_t p = default_chunk(s);
+    if (s->use_ray == 0.0 && s->use_fan == 0.0)
+        p = std::min<int64_t>(p, region <= ((uint64_t)16 << 20) ? (int64_t)std::max<uint64_t>(region, 1) : (int64_t)1 << 16);
     const double slack = 1.3;
     if (s->use_ray > 0.0) p = std::min<int64_t>(p, (int64_t)(s->ray_cap / (s->use_ray * slack)));
     if (s->use_fan > 0.0) p = std::min<int64_t>(p, (int64_t)(s->fan_cap / (s->use_fan * slack)));
+    if (s->chunk_limit > 0) p = std::min<int64_t>(p, s->chunk_limit);
     return (uint32_t)std::max<int64_t>(p, 1024);
+}
+
+// A chunk overflowed a queue: what to do next.  Returns non-zero (with the overflow message) when the chunk cannot
+// get any smaller.
+static int shrink_after_overflow(sp_scene* s, uint32_t n_items, sp_stats* st) {
+    if (st) st->chunk_retries += 1;
+    if (n_items <= 1024u || s->opt_chunk_fixed) {
+        const std::string msg = g_error;
+        return fail("%s: raise ray_queue_capacity / fan_queue_capacity or lower chunk_primaries", msg.c_str());
+    }
+    s->chunk_limit = std::max<int64_t>(n_items / 2, 1024);
+    return 0;
 }
 
 int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample_begin, int sample_end, uint64_t seed,
@@ -1201,27 +1317,42 @@ int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample
     ScopedEvent ev0, ev1;
     if (!ev0.e || !ev1.e) return fail("sp_render_region: cudaEventCreate failed");
     cudaEvent_t t0 = ev0.e, t1 = ev1.e;
+    // Chunks add their radiance to a scratch frame that is folded into the accumulation buffer once the chunk is
+    // known to be complete, so that a chunk whose queues overflowed can be rendered again in smaller pieces.
+    if (s->scratch.n != s->accum.n) {
+        CUDA_TRY(s->scratch.alloc(s->accum.n));
+        CUDA_TRY(cudaMemsetAsync(s->scratch.p, 0, s->scratch.n * sizeof(float4), s->stream));
+    }
     CUDA_TRY(cudaEventRecord(t0, s->stream));
     if (clear) CUDA_TRY(cudaMemsetAsync(s->accum.p, 0, s->accum.n * sizeof(float4), s->stream));
     const uint32_t first_pix = (uint32_t)pix_begin, n_region = (uint32_t)(pix_end - pix_begin);
     uint32_t sample = (uint32_t)sample_begin, pix = 0;          // pix: offset inside the region
-    bool first = true;
     while (n_region > 0 && sample < (uint32_t)sample_end && rc == 0) {
-        const uint32_t P = pick_chunk(s, first);
-        first = false;
+        const uint32_t P = pick_chunk(s, n_region);
         ChunkJob job{};
-        job.source = SP_SRC_CAMERA; job.run = SP_RUN_FULL; job.accum = s->accum.p;
+        job.source = SP_SRC_CAMERA; job.run = SP_RUN_FULL; job.accum = s->scratch.p;
+        uint32_t next_sample = sample, next_pix = pix;
         if (pix == 0 && P >= n_region) {                         // whole region x several samples
             const uint32_t ns = std::min<uint32_t>(P / n_region, (uint32_t)sample_end - sample);
             job.pix_begin = first_pix; job.n_pix = n_region; job.sample_begin = sample; job.n_items = ns * n_region;
-            sample += ns;
+            next_sample = sample + ns;
         } else {                                                 // a slice of the region, one sample
             const uint32_t n = std::min<uint32_t>(P, n_region - pix);
             job.pix_begin = first_pix + pix; job.n_pix = n; job.sample_begin = sample; job.n_items = n;
-            pix += n;
-            if (pix == n_region) { pix = 0; ++sample; }
+            next_pix = pix + n;
+            if (next_pix == n_region) { next_pix = 0; next_sample = sample + 1; }
         }
-        rc = run_chunk(s, job, st);
+        bool overflow = false;
+        rc = run_chunk(s, job, st, overflow);
+        if (rc) break;
+        if (overflow) {
+            CUDA_TRY(cudaMemsetAsync(s->scratch.p + job.pix_begin, 0, (size_t)job.n_pix * sizeof(float4), s->stream));
+            rc = shrink_after_overflow(s, job.n_items, st);
+            continue;
+        }
+        CUDA_TRY(sp_launch_fold(s->accum.p + job.pix_begin, s->scratch.p + job.pix_begin, job.n_pix, s->stream));
+        if (st) st->kernel_launches += 1;
+        sample = next_sample; pix = next_pix;
     }
     int rc2 = end_call(s, st, t0, t1);
     return rc ? rc : rc2;
@@ -1297,15 +1428,20 @@ int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64
     TRY_OR_CLEAN(cudaMemsetAsync(d_acc.p, 0, (size_t)n * sizeof(float4), s->stream));
     TRY_OR_CLEAN(cudaEventCreate(&t0)); TRY_OR_CLEAN(cudaEventCreate(&t1));
     TRY_OR_CLEAN(cudaEventRecord(t0, s->stream));
-    bool first = true;
     for (uint32_t base = 0; base < (uint32_t)n && rc == 0;) {
-        const uint32_t P = std::min<uint32_t>(pick_chunk(s, first), (uint32_t)n - base);
-        first = false;
+        const uint32_t P = std::min<uint32_t>(pick_chunk(s, (uint64_t)n), (uint32_t)n - base);
         ChunkJob job{};
         job.source = SP_SRC_USER; job.run = SP_RUN_FULL; job.accum = d_acc.p;
         job.user_base = base; job.n_items = P; job.user_o = d_o.p; job.user_d = d_d.p;
         job.out_hit = d_hit.p; job.out_t = d_t.p;
-        rc = run_chunk(s, job, st);
+        bool overflow = false;
+        rc = run_chunk(s, job, st, overflow);
+        if (rc) break;
+        if (overflow) {                                          // a ray's radiance lands in its own element: clear the chunk's and go again
+            TRY_OR_CLEAN(cudaMemsetAsync(d_acc.p + base, 0, (size_t)P * sizeof(float4), s->stream));
+            rc = shrink_after_overflow(s, P, st);
+            continue;
+        }
         base += P;
     }
     int rc2 = end_call(s, st, t0, t1);
@@ -1337,7 +1473,8 @@ static int primary_pass(sp_scene* s, int run, int sample, uint64_t seed, float* 
     job.source = SP_SRC_CAMERA; job.run = run; job.accum = s->accum.p;
     job.pix_begin = 0; job.n_pix = (uint32_t)n; job.sample_begin = (uint32_t)sample; job.n_items = (uint32_t)n;
     job.out_o = d_o.p; job.out_d = d_d.p; job.out_t = d_t.p;
-    rc = run_chunk(s, job, nullptr);
+    bool overflow = false;                                    // a level-0-only pass queues nothing
+    rc = run_chunk(s, job, nullptr, overflow);
     if (rc == 0 && run == SP_RUN_DUMP_RAYS) {
         TRY_OR_CLEAN(cudaMemcpy(out_o, d_o.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
         TRY_OR_CLEAN(cudaMemcpy(out_d, d_d.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1364,6 +1501,7 @@ int sp_set_option(sp_scene* s, const char* name, int64_t value) {
     if (!strcmp(name, "ray_queue_capacity")) s->opt_ray_cap = value;
     else if (!strcmp(name, "fan_queue_capacity")) s->opt_fan_cap = value;
     else if (!strcmp(name, "chunk_primaries")) s->opt_chunk = value;
+    else if (!strcmp(name, "fixed_chunks")) s->opt_chunk_fixed = value;
     else if (!strcmp(name, "max_levels")) s->opt_max_levels = value;
     else if (!strcmp(name, "bvh")) {
         s->opt_bvh = value;
@@ -1373,11 +1511,12 @@ int sp_set_option(sp_scene* s, const char* name, int64_t value) {
         s->opt_warp = value;
         if (s->committed) {
             s->d.use_warp_kernel = value ? 1 : 0;
-            s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false);
+            if (int rc = pick_kernels(s)) return rc;
         }
     }
     else return fail("sp_set_option: unknown option '%s'", name);
     s->use_ray = s->use_fan = 0.0;
+    s->chunk_limit = 0;
     return 0;
 }
 

@@ -14,6 +14,7 @@
 // count is read from device counters, so a whole chunk (all levels) is enqueued with no host
 // round trip.  The colliders are staged into shared memory in 32 KB type-sorted chunks and every
 // lane of a warp reads the same address (broadcast).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -89,6 +90,9 @@ __global__ void __launch_bounds__(SP_BLOCK, SP_CTAS_PER_SM(FEAT))
 sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
     extern __shared__ float4 s_geom[];                 // sized by the host to the scene's largest chunk
     __shared__ IterShared sh;
+
+    // a queue of an earlier level overflowed: its records are incomplete, the host discards the chunk
+    if (*reinterpret_cast<volatile const unsigned int*>(&a.out.stats->overflow)) return;
 
     // ---- work items of this launch ---------------------------------------------------------
     uint32_t n_rays = 0, fan_n[SP_MAX_FAN_CLASSES];
@@ -441,7 +445,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     }
 }
 
-#include "sp_warp_kernel.cuh"
+#include "sp_path_kernel.cuh"
 
 // ---- frame resolve: average, sRGB OETF, per-pixel max normalisation, truncation to uint8 ---------
 // scene.py:118-140 + colour_functions.py:4-18.  Double precision: the output is quantised by
@@ -476,6 +480,19 @@ __global__ void __launch_bounds__(256) sp_resolve_kernel(const ResolveArgs a) {
         const double s = 255.0 * e;
         a.out_srgb8[3 * (size_t)i + c] = (s == s) ? (uint8_t)s : (uint8_t)0;
     }
+}
+
+// A finished chunk's radiance moves from the scratch frame to the accumulation buffer (sp_api.cu: a chunk whose queues
+// overflowed is discarded and rendered again in smaller pieces, so it must not touch the frame before it is complete).
+__global__ void __launch_bounds__(256) sp_fold_kernel(float4* __restrict__ accum, float4* __restrict__ scratch, uint32_t n) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = scratch[i];
+    if (s.x == 0.f && s.y == 0.f && s.z == 0.f) return;
+    float4 a = accum[i];
+    a.x += s.x; a.y += s.y; a.z += s.z;
+    accum[i] = a;
+    scratch[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---- roofline denominators ----------------------------------------------------------------------
@@ -525,39 +542,47 @@ static LevelKernel level_kernel(uint32_t material_set, bool level0) {
     }
 }
 
-// Queue-fed levels of small untextured Monte-Carlo scenes run the warp-autonomous kernel (sp_warp_kernel.cuh).
-// SIGHTPY_WARP_KERNEL=0 keeps them on sp_level_kernel (A/B measurements).
-bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set) {
+// Full runs of scenes whose colliders fit one staged chunk (+ the BVH) go through sp_path_kernel (sp_path_kernel.cuh).
+// SIGHTPY_WARP_KERNEL=0 / option "warp_kernel" = 0 keeps them on sp_level_kernel (A/B measurements, parity tests).
+static LevelKernel path_kernel(uint32_t material_set, bool level0) {
+    switch (material_set) {
+    case SP_SET_MC: return level0 ? sp_path_kernel<SP_SET_MC | SP_F_LEVEL0> : sp_path_kernel<SP_SET_MC | SP_F_QUEUES>;
+    case SP_SET_WHITTED: return level0 ? sp_path_kernel<SP_SET_WHITTED | SP_F_LEVEL0> : sp_path_kernel<SP_SET_WHITTED | SP_F_QUEUES>;
+    case SP_SET_ALL_BVH: return level0 ? sp_path_kernel<SP_SET_ALL_BVH | SP_F_LEVEL0> : sp_path_kernel<SP_SET_ALL_BVH | SP_F_QUEUES>;
+    default: return level0 ? sp_path_kernel<SP_SET_ALL | SP_F_LEVEL0> : sp_path_kernel<SP_SET_ALL | SP_F_QUEUES>;
+    }
+}
+
+static size_t path_smem_bytes(const DScene& sc) {
+    return geom_smem_bytes(sc) + (size_t)sc.n_stash_bins * SPP_STASH_STRIDE * sizeof(uint32_t);
+}
+
+bool sp_use_path_kernel(const DScene& sc, uint32_t material_set) {
     static const bool enabled = [] { const char* e = getenv("SIGHTPY_WARP_KERNEL"); return !(e && e[0] == '0'); }();
-    if (!enabled || !sc.use_warp_kernel || material_set != SP_SET_MC) return false;
-    if (sc.all.n_chunks != 1 || sc.bvh.n_nodes != 0 || sc.n_colliders > SPW_MAX_COLLIDERS) return false;
-    for (int c = 0; c < sc.n_fan_classes; ++c)
-        if (sc.fan_mult[c] > 1024) return false;
+    if (!enabled || !sc.use_warp_kernel) return false;
+    if (sc.all.n_chunks != 1) return false;                  // exhaustive multi-chunk walks stay on sp_level_kernel
+    if (!(material_set & SP_F_BVH) && sc.n_colliders > SP_SMALL_COLLIDERS) return false;
     return true;
 }
 
-int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0) {
+int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0, bool path) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (!level0 && sp_use_warp_kernel(sc, material_set)) {
-        auto k = sp_warp_kernel<SP_SET_MC>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
-        int per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SPW_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
-            per_sm = 1;
-        return sms * per_sm;
+    LevelKernel k = path ? path_kernel(material_set, level0) : level_kernel(material_set, level0);
+    const size_t smem = path ? path_smem_bytes(sc) : geom_smem_bytes(sc);
+    const size_t opt_in = std::max<size_t>(smem, (size_t)SP_CHUNK_VEC4 * sizeof(float4));
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opt_in) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, path ? SPP_BLOCK : SP_BLOCK, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 0;                                             // does not fit (too many stash bins for the shared memory): caller falls back
     }
-    LevelKernel k = level_kernel(material_set, level0);
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SP_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
     return sms * per_sm;
 }
 
-cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st) {
-    if (a.source == SP_SRC_QUEUES && a.run == SP_RUN_FULL && sp_use_warp_kernel(sc, material_set)) {
-        sp_warp_kernel<SP_SET_MC><<<grid, SPW_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
+cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, bool path, cudaStream_t st) {
+    if (path && a.run == SP_RUN_FULL) {
+        path_kernel(material_set, a.source != SP_SRC_QUEUES)<<<grid, SPP_BLOCK, path_smem_bytes(sc), st>>>(sc, a);
         return cudaGetLastError();
     }
     level_kernel(material_set, a.source != SP_SRC_QUEUES)<<<grid, SP_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
@@ -567,6 +592,12 @@ cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t mater
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st) {
     if (a.n_pix == 0) return cudaSuccess;
     sp_resolve_kernel<<<(a.n_pix + 255u) / 256u, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st) {
+    if (n_pix == 0) return cudaSuccess;
+    sp_fold_kernel<<<(n_pix + 255u) / 256u, 256, 0, st>>>(accum, scratch, n_pix);
     return cudaGetLastError();
 }
 

@@ -37,10 +37,12 @@ struct ResolveArgs {
 };
 
 uint32_t sp_pick_material_set(uint32_t needed_features);          // smallest compiled kernel variant covering them
-bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set);      // queue-fed levels run sp_warp_kernel (sp_warp_kernel.cuh)
-int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0);   // CTAs of a persistent launch
-cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st);
+bool sp_use_path_kernel(const DScene& sc, uint32_t material_set);      // full runs go through sp_path_kernel (sp_path_kernel.cuh)
+// CTAs of a persistent launch (0: the kernel does not fit the SM with this scene's shared-memory needs)
+int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0, bool path);
+cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, bool path, cudaStream_t st);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
+cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st);   // accum += scratch; scratch = 0
 cudaError_t sp_upload_decode_tables(const float* plain256, const float* linear256);
 cudaError_t sp_bench_ffma(double* tflops, cudaStream_t st);
 cudaError_t sp_bench_copy(double* gbs, cudaStream_t st);

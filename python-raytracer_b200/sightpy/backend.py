@@ -27,7 +27,7 @@ class Stats(C.Structure):
         ("level_kernel_launches", C.c_uint64), ("queue_bytes", C.c_uint64),
         ("level_ms", C.c_double * SP_MAX_DEPTH_LEVELS),
         ("peak_ray_records", C.c_uint64), ("peak_fan_records", C.c_uint64),
-        ("warp_kernel_launches", C.c_uint64),
+        ("warp_kernel_launches", C.c_uint64), ("chunk_retries", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -43,7 +43,8 @@ class Stats(C.Structure):
                     level_ms=[float(v) for v in self.level_ms][:max(len(depth), 1)],
                     peak_ray_records=int(self.peak_ray_records),
                     peak_fan_records=int(self.peak_fan_records),
-                    warp_kernel_launches=int(self.warp_kernel_launches))
+                    warp_kernel_launches=int(self.warp_kernel_launches),
+                    chunk_retries=int(self.chunk_retries))
 
 
 def library_path():
