@@ -152,6 +152,14 @@ int  sp_scene_set_lights(sp_scene*, const sp_light*, int n);
 int  sp_scene_set_importance(sp_scene*, const int32_t* primitive_ids, int n);
 int  sp_scene_set_shadow_colliders(sp_scene*, const int32_t* collider_ids, int n);
 int  sp_scene_commit(sp_scene*);    /* validate + upload; must precede any render call            */
+/* Re-describing a committed scene (animation.py:27-31 calls update_scene + render per frame): any sp_scene_set_* may
+ * be called again, followed by sp_scene_commit.  Device buffers (wavefront queues, frame, keyed textures) are
+ * recycled, and while the scene keeps its shape (frame size, table sizes, material kinds, collider types) the
+ * queue-occupancy estimates of earlier frames are kept, so no probe chunk is rendered again.
+ * sp_scene_clear_textures empties the texture list before it is described anew (keyed texels stay resident).
+ * sp_scene_update_camera moves the camera of a committed scene without a commit (same frame size only). */
+int  sp_scene_clear_textures(sp_scene*);
+int  sp_scene_update_camera(sp_scene*, const sp_camera*);
 
 /* ---- rendering ----------------------------------------------------------------------------------
  * sp_render == Scene.render (scene.py:71-140): spp jittered samples per pixel, average, sRGB
@@ -171,6 +179,12 @@ int  sp_render_samples(sp_scene*, int sample_begin, int sample_end, uint64_t see
  * frame has fewer samples than there are GPUs. */
 int  sp_render_region(sp_scene*, int64_t pix_begin, int64_t pix_end, int sample_begin, int sample_end,
                       uint64_t seed, int clear, sp_stats* stats);
+/* Same for a list of square tiles (tile_size a power of two; tile ids are row-major over the frame's grid of
+ * ceil(W / tile_size) x ceil(H / tile_size) tiles): interleaved-tile sharding — rank r of R renders tiles r, r + R, ...
+ * — which balances scenes whose cost varies across the frame.  Replaces the per-batch fan-out of the reference's
+ * process pool (scene.py:78-116). */
+int  sp_render_tiles(sp_scene*, const int32_t* tile_ids, int n_tiles, int tile_size, int sample_begin, int sample_end,
+                     uint64_t seed, int clear, sp_stats* stats);
 void*    sp_accum_device_ptr(sp_scene*);      /* float4[H*W] on the scene's device                 */
 uint64_t sp_accum_bytes(sp_scene*);
 /* Resolve the accumulation buffer: divide by spp_total, tonemap (on the device), then copy to
@@ -193,6 +207,12 @@ int  sp_camera_rays(sp_scene*, int sample, uint64_t seed, float* out_origins, fl
 /* Nearest-hit distance of one jittered primary ray per pixel == ray.get_distances before its
  * clip/normalise step (ray.py:151-163); misses are +inf. */
 int  sp_distances(sp_scene*, uint64_t seed, float* out_t);
+
+/* Frame-level debug outputs of one jittered primary ray per pixel (the fields of the reference's Hit record,
+ * ray.py:97-119), each nullable: index into collider_list of the nearest hit (-1 = none), hit distance (+inf = none),
+ * and the collider normal at the hit point turned towards the ray (collider.get_Normal x orientation; 0 = none),
+ * H*W x 3 interleaved. */
+int  sp_aovs(sp_scene*, int sample, uint64_t seed, int32_t* out_hit_id, float* out_t, float* out_normal);
 
 /* ---- tuning / measurement ---------------------------------------------------------------------- */
 /* options: "ray_queue_capacity", "fan_queue_capacity" (records; 0 = auto: 32 Mi records = 1.5 GB per queue side with

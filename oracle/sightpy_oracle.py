@@ -649,6 +649,21 @@ class Oracle:
             D = D / np.sqrt(dot(D, D))
         return self.trace_columns(O, D, pix, sample)
 
+    def nearest(self, origins, dirs):
+        """Nearest collider index (-1 = none) and distance (inf = none) of (N, 3) rays: the first half of
+        get_raycolor (ray.py:124-128) without any shading — affordable on scenes of thousands of colliders."""
+        O = np.ascontiguousarray(np.asarray(origins, dtype=np.float64).T)
+        D = np.ascontiguousarray(np.asarray(dirs, dtype=np.float64).T)
+        D = D / np.sqrt(dot(D, D))
+        best = np.full(O.shape[1], FARAWAY)
+        hit = np.full(O.shape[1], -1, dtype=np.int32)
+        for ci in range(len(self.ctype)):
+            t, _ = self.intersect(ci, O, D)
+            closer = t < best                         # ties: the lowest index is reported, as in radiance()
+            hit[closer] = ci
+            best = np.where(closer, t, best)
+        return hit, np.where(best == FARAWAY, np.inf, best)
+
     def render_linear(self, spp, sample_begin=0):
         """Sum over samples / spp of get_raycolor(camera rays) -> (3, H*W) (scene.py:78-119)."""
         total = None

@@ -161,6 +161,7 @@ struct sp_scene {
     int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0, opt_bvh = 1, opt_warp = 1;
     int64_t opt_chunk_fixed = 0;                 // 1: a chunk that overflows is an error instead of being retried smaller
     int64_t chunk_limit = 0;                     // learnt from overflows: no chunk larger than this
+    uint64_t shape_sig = 0;                      // what the occupancy estimates below were measured on (shape_signature)
     // ---- device residency -----------------------------------------------------------------------------
     DScene d{};
     int n_levels = 1;
@@ -170,6 +171,7 @@ struct sp_scene {
     DevBuf<uint8_t> d_u8;
     std::vector<cudaEvent_t> events;
     DevBuf<float4> geom_all, geom_shadow, accum, scratch;
+    DevBuf<uint32_t> d_tiles;                    // tile list of the last sp_render_tiles call
     DevBuf<int> off_all, off_shadow;
     DevBuf<int2> slot_shadow;
     DevBuf<DCollider> d_cols;
@@ -191,10 +193,6 @@ struct sp_scene {
     uint32_t chunk_primaries = 0;
     double use_ray = 0.0, use_fan = 0.0;         // peak records per primary seen so far
     int grid0 = 0, grid_q = 0;                   // CTAs of level-0 / queue-fed launches of sp_level_kernel
-    int pgrid0 = 0, pgrid_q = 0;                 // the same for sp_path_kernel
-    bool use_path = false;                       // full runs go through sp_path_kernel
-    DevBuf<uint2> d_colcls;
-    DevBuf<float2> d_colsrc;
     uint32_t material_set = 0;                   // compiled kernel variant (sp_pick_material_set)
 
     ~sp_scene() { release_device(); release_textures(); }
@@ -211,8 +209,8 @@ struct sp_scene {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
 
-        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); off_all.release(); off_shadow.release();
-        slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); d_colcls.release(); d_colsrc.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
+        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); d_tiles.release(); off_all.release(); off_shadow.release();
+        slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
         for (auto e : events) g_event_pool.push_back(e);
@@ -599,17 +597,26 @@ static BuiltBvh build_bvh(const std::vector<sp_collider>& cols, const std::vecto
     return out;
 }
 
-// Launch geometry of the two kernel families for this scene; sp_path_kernel is used when the scene qualifies and fits.
+// Fingerprint of everything that decides how many records a primary ray puts into the queues *structurally*: frame
+// size, table sizes, material kinds / fan sizes / depth limits, collider types.  A scene that is re-described with
+// the same shape (an animation frame: moved colliders, another camera pose) keeps the queue-occupancy estimates of
+// the previous frames instead of probing again.
+static uint64_t shape_signature(const sp_scene* s) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](uint64_t v) { h ^= v; h *= 1099511628211ull; };
+    mix((uint64_t)s->cam.width); mix((uint64_t)s->cam.height);
+    mix(s->textures.size()); mix(s->lights.size()); mix(s->importance.size()); mix(s->shadow_ids.size());
+    for (const auto& t : s->textures) { mix((uint64_t)t.H); mix((uint64_t)t.W); }
+    for (const auto& m : s->mats) { mix((uint64_t)m.kind); mix((uint64_t)m.diffuse_rays); mix((uint64_t)m.max_diffuse_reflections); }
+    for (const auto& p : s->prims) { mix((uint64_t)p.material); mix((uint64_t)p.max_ray_depth); mix((uint64_t)p.mc); }
+    for (const auto& c : s->cols) { mix((uint64_t)c.type); mix((uint64_t)c.primitive); }
+    return h ? h : 1;
+}
+
+// Launch geometry of the level kernels for this scene.
 static int pick_kernels(sp_scene* s) {
-    s->grid0 = sp_level_grid(g_device, s->d, s->material_set, true, false);
-    s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false, false);
-    if (s->grid0 < 1 || s->grid_q < 1) return fail("sp_level_kernel does not fit this device");
-    s->use_path = sp_use_path_kernel(s->d, s->material_set);
-    if (s->use_path) {
-        s->pgrid0 = sp_level_grid(g_device, s->d, s->material_set, true, true);
-        s->pgrid_q = sp_level_grid(g_device, s->d, s->material_set, false, true);
-        if (s->pgrid0 < 1 || s->pgrid_q < 1) s->use_path = false;
-    }
+    s->grid0 = sp_level_grid(g_device, s->d, s->material_set, true);
+    s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false);
     return 0;
 }
 
@@ -706,6 +713,28 @@ int sp_scene_set_camera(sp_scene* s, const sp_camera* cam) {
     if ((uint64_t)cam->width * (uint64_t)cam->height > 0x7FFFFFFFull) return fail("sp_scene_set_camera: frame too large");
     s->cam = *cam;
     s->has_camera = true;
+    return 0;
+}
+
+int sp_scene_update_camera(sp_scene* s, const sp_camera* cam) {
+    SP_LOCK;
+    if (!s || !cam) return fail("sp_scene_update_camera: invalid arguments");
+    if (!s->committed || !s->has_camera) return fail("sp_scene_update_camera: scene not committed with a camera");
+    if (cam->width != s->cam.width || cam->height != s->cam.height)
+        return fail("sp_scene_update_camera: the frame size changed (%dx%d -> %dx%d): set the camera and commit again",
+                    s->cam.width, s->cam.height, cam->width, cam->height);
+    s->cam = *cam;
+    DCamera& c = s->d.cam;
+    c.look_from = f3(cam->look_from); c.right = f3(cam->right); c.up = f3(cam->up); c.fwd = f3(cam->fwd);
+    c.cam_w = (float)cam->cam_w; c.cam_h = (float)cam->cam_h; c.lens_radius = (float)cam->lens_radius;
+    c.focal_distance = (float)cam->focal_distance;
+    return 0;
+}
+
+int sp_scene_clear_textures(sp_scene* s) {
+    SP_LOCK;
+    NEED_SCENE(s);
+    s->textures.clear();
     return 0;
 }
 
@@ -989,60 +1018,6 @@ int sp_scene_commit(sp_scene* s) {
     }
     if (all.chunk_off.size() - 1 > 255) return fail("too many geometry chunks");
     CUDA_TRY(s->d_colinfo.upload(dinfo));
-    // What a hit on a collider does, as two words sp_path_kernel tests with a few instructions:
-    //   x: byte d = fan class an untextured Diffuse hit emits for a ray with diffuse_reflections == d (diffuse.py:34, 85), 0xFF = none
-    //   y: [0:8) the hit is stashed for its material's shading code while ray.depth < this, bit 8 untextured Emissive
-    //      (emissive.py:21-23, added on the spot), [9:12) 1 + stash bin (SP_BIN_*), [16:24) collider type
-    // and where the collider sits in the staged chunk (the ray's own collider is skipped there by position).
-    std::vector<uint2> dcls((size_t)n_col);
-    std::vector<float2> dsrc((size_t)n_col);
-    bool bin_used[SP_N_BINS] = {false, false, false, false, false};
-    {
-        std::vector<int> tag_of((size_t)n_col, -1);
-        if (all.chunk_off.size() == 2) {                  // one staged chunk: positions in its id array
-            GeomChunkHeader h0;
-            memcpy(&h0, all.data.data(), sizeof h0);
-            const int n_items = h0.n_sphere + h0.n_plane + h0.n_cuboid + h0.n_tri + h0.n_aax + h0.n_aay + h0.n_aaz;
-            const int* ids0 = reinterpret_cast<const int*>(all.data.data() + h0.off_ids);
-            for (int k = 0; k < n_items; ++k) tag_of[(size_t)ids0[k]] = k;
-        }
-        for (int i = 0; i < n_col; ++i) {
-            const sp_primitive& pr = s->prims[s->cols[i].primitive];
-            const sp_material& m = s->mats[pr.material];
-            const bool textured = m.color_tex >= 0 || m.normalmap_tex >= 0;
-            uint32_t fan = 0xFFFFFFFFu, misc = (uint32_t)s->cols[i].type << 16, limit = 255u;
-            int bin = -1;
-            switch (m.kind) {
-            case SP_MAT_DIFFUSE:
-                if (textured) { bin = SP_BIN_GENERIC; break; }
-                fan = 0u;
-                for (int dr = 0; dr < 4; ++dr) {
-                    uint32_t c = 0xFFu;
-                    if (dr < 1) c = (uint32_t)dm[pr.material].fan_class;
-                    else if (dr < m.max_diffuse_reflections) c = 0u;
-                    fan |= c << (8 * dr);
-                }
-                break;
-            case SP_MAT_EMISSIVE: if (m.color_tex >= 0) bin = SP_BIN_GENERIC; else misc |= 0x100u; break;
-            case SP_MAT_REFRACTIVE: bin = SP_BIN_REFR; limit = (uint32_t)std::min(std::max(pr.max_ray_depth, 0), 255); break;
-            case SP_MAT_THINFILM: bin = SP_BIN_THIN; limit = (uint32_t)std::min(std::max(pr.max_ray_depth, 0), 255); break;
-            case SP_MAT_GLOSSY: bin = SP_BIN_GLOSSY; break;
-            default: bin = SP_BIN_SKY; break;
-            }
-            if (bin >= 0) { misc |= ((uint32_t)(bin + 1) << 9) | limit; bin_used[bin] = true; }
-            dcls[(size_t)i] = make_uint2(fan, misc);
-            float2 src;
-            memcpy(&src.x, &tag_of[(size_t)i], sizeof(int));
-            src.y = (float)m.ambient_weight;
-            dsrc[(size_t)i] = src;
-        }
-    }
-    CUDA_TRY(s->d_colcls.upload(dcls));
-    CUDA_TRY(s->d_colsrc.upload(dsrc));
-    d.col_cls = s->d_colcls.p; d.col_src = s->d_colsrc.p;
-    d.n_stash_bins = 0;
-    for (int b = 0; b < 8; ++b) d.stash_slot[b] = -1;
-    for (int b = 0; b < SP_N_BINS; ++b) if (bin_used[b]) d.stash_slot[b] = d.n_stash_bins++;
     CUDA_TRY(s->geom_all.upload(all.data));
     CUDA_TRY(s->off_all.upload(all.chunk_off));
     CUDA_TRY(s->geom_shadow.upload(shadow.data));
@@ -1097,12 +1072,16 @@ int sp_scene_commit(sp_scene* s) {
         default: break;
         }
     }
-    if (d.bvh.n_nodes > 0 || n_col > SP_SMALL_COLLIDERS) needed |= SP_F_BVH;     // large scenes: per-collider tables stay in global memory
+    if (d.bvh.n_nodes > 0) needed |= SP_F_BVH;
     s->material_set = sp_pick_material_set(needed);
     s->d.use_warp_kernel = s->opt_warp ? 1 : 0;
     if (int rc = pick_kernels(s)) return rc;
-    s->use_ray = s->use_fan = 0.0;
-    s->chunk_limit = 0;
+    const uint64_t sig = shape_signature(s);
+    if (sig != s->shape_sig) {                   // a different scene: measure the queue occupancy afresh
+        s->use_ray = s->use_fan = 0.0;
+        s->chunk_limit = 0;
+        s->shape_sig = sig;
+    }
     s->committed = true;
     return 0;
 }
@@ -1110,26 +1089,19 @@ int sp_scene_commit(sp_scene* s) {
 // =================================================================================================
 // wavefront driver
 // =================================================================================================
-// Primaries per chunk and records per queue when the caller sets neither.
-//   sp_path_kernel: a Diffuse bounce stays in registers / shared memory, only specular children and the fans behind
-//   them are queued (Cornell box: ~3 records per primary), so queues of 32 Mi records (1.5 GB per queue side; 9 GB in
-//   all for a scene with one fan class > 1) carry chunks of tens of millions of primaries.
-//   sp_level_kernel (option "warp_kernel" = 0, multi-chunk exhaustive walks): every bounce goes through the queues,
-//   24 records per primary of a chunk: 192 Mi records each (54 GB with two fan classes) for a full 8 Mi-primary
-//   chunk, proportionally less for small jobs.
-// A chunk that overflows a queue all the same is rendered again at half the size (see render loop below).
-#define SP_DEFAULT_CHUNK_LEVEL ((int64_t)8 << 20)
-#define SP_DEFAULT_CHUNK_PATH ((int64_t)64 << 20)
-#define SP_DEFAULT_CAP_PATH ((int64_t)32 << 20)
+// Primaries per chunk and records per queue when the caller sets neither: queues hold 24 records per primary of a
+// chunk (a diffuse first bounce turns 1 primary into diffuse_rays secondary hits): 192 Mi records each (54 GB with two
+// fan classes) for a full 8 Mi-primary chunk, proportionally less for small jobs; options "chunk_primaries",
+// "ray_queue_capacity" and "fan_queue_capacity" trade memory for launch size (4 Mi-primary chunks: 27 GB, -1 % on the
+// headline frame).  The driver measures the real occupancy on a first chunk and sizes later chunks to fit; a chunk
+// that overflows a queue all the same is rendered again at half the size (see the render loop below).
+#define SP_DEFAULT_CHUNK ((int64_t)8 << 20)      /* measured 4 Mi -> 35.3, 8 Mi -> 35.7, 16 Mi -> 35.8 Grays/s */
 
-static int64_t default_chunk(const sp_scene* s) {
-    return s->opt_chunk > 0 ? s->opt_chunk : (s->use_path ? SP_DEFAULT_CHUNK_PATH : SP_DEFAULT_CHUNK_LEVEL);
-}
+static int64_t default_chunk(const sp_scene* s) { return s->opt_chunk > 0 ? s->opt_chunk : SP_DEFAULT_CHUNK; }
 
 static int ensure_queues(sp_scene* s, uint64_t primaries) {
     const int64_t chunk = default_chunk(s);
     int64_t auto_cap = 24 * (int64_t)std::min<uint64_t>(std::max<uint64_t>(primaries, 1), (uint64_t)chunk);
-    if (s->use_path) auto_cap = std::min<int64_t>(auto_cap, SP_DEFAULT_CAP_PATH);
     auto_cap = std::max<int64_t>((auto_cap + 0xFFFFF) & ~(int64_t)0xFFFFF, (int64_t)1 << 20);
     uint32_t want_ray = (uint32_t)std::min<int64_t>(s->opt_ray_cap > 0 ? s->opt_ray_cap : auto_cap, 0x7FFFFFF0ll);
     uint32_t want_fan = (uint32_t)std::min<int64_t>(s->opt_fan_cap > 0 ? s->opt_fan_cap : auto_cap, 0x7FFFFFF0ll);
@@ -1151,8 +1123,9 @@ static int ensure_queues(sp_scene* s, uint64_t primaries) {
 struct ChunkJob {
     int source, run;
     uint32_t pix_begin, n_pix, sample_begin, n_items, user_base;
+    const uint32_t* tiles; uint32_t tile_shift, tiles_x;
     const float* user_o; const float* user_d;
-    float4* accum; int32_t* out_hit; float* out_t; float* out_o; float* out_d;
+    float4* accum; int32_t* out_hit; float* out_t; float* out_o; float* out_d; float* out_n;
 };
 
 // Enqueue all levels of one chunk, wait, fold its counters into `st`.  `overflow` comes back true when a queue was
@@ -1162,7 +1135,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
     int n_levels = (job.run == SP_RUN_FULL) ? s->n_levels : 1;
     if (s->opt_max_levels > 0) n_levels = std::min<int>(n_levels, (int)s->opt_max_levels);   // debugging aid
     const int ncl = SP_COUNTS_PER_LEVEL;
-    const bool path = s->use_path && job.run == SP_RUN_FULL;
+    const bool warp = job.run == SP_RUN_FULL && sp_use_warp_kernel(s->d, s->material_set);
     CUDA_TRY(cudaMemsetAsync(s->counts.p, 0, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
     for (int L = 0; L < n_levels; ++L) {
@@ -1172,6 +1145,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         a.source = (L == 0) ? job.source : SP_SRC_QUEUES;
         a.pix_begin = job.pix_begin; a.n_pix = job.n_pix; a.sample_begin = job.sample_begin;
         a.n_items0 = job.n_items; a.user_base = job.user_base; a.user_o = job.user_o; a.user_d = job.user_d;
+        a.tiles = job.tiles; a.tile_shift = job.tile_shift; a.tiles_x = job.tiles_x;
         a.in_rays = s->ray_q[L & 1].view(s->ray_cap);
         a.in_fans = s->fan_q[L & 1].view(s->fan_cap * s->d.n_fan_classes);
         a.out.rays = s->ray_q[(L + 1) & 1].view(s->ray_cap);
@@ -1184,11 +1158,10 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         a.out.counts = s->counts.p + (size_t)(L + 1) * ncl;
         a.out.stats = s->d_stats.p;
         a.accum = job.accum;
-        a.out_hit = job.out_hit; a.out_t = job.out_t; a.out_o = job.out_o; a.out_d = job.out_d;
+        a.out_hit = job.out_hit; a.out_t = job.out_t; a.out_o = job.out_o; a.out_d = job.out_d; a.out_n = job.out_n;
         a.shadow_slot = s->slot_shadow.p;
         CUDA_TRY(cudaEventRecord(s->events[L], s->stream));
-        const int grid = path ? (L == 0 ? s->pgrid0 : s->pgrid_q) : (L == 0 ? s->grid0 : s->grid_q);
-        CUDA_TRY(sp_launch_level(s->d, a, s->material_set, grid, path, s->stream));
+        CUDA_TRY(sp_launch_level(s->d, a, s->material_set, L == 0 ? s->grid0 : s->grid_q, s->stream));
     }
     CUDA_TRY(cudaEventRecord(s->events[n_levels], s->stream));
     std::vector<uint32_t> counts((size_t)(n_levels + 1) * ncl);
@@ -1223,7 +1196,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         st->chunks += 1;
         st->kernel_launches += (uint64_t)n_levels;
         st->level_kernel_launches += (uint64_t)n_levels;
-        if (path) st->warp_kernel_launches += (uint64_t)n_levels;
+        if (warp) st->warp_kernel_launches += (uint64_t)(n_levels - 1);
         st->peak_ray_records = std::max<uint64_t>(st->peak_ray_records, peak_r);
         st->peak_fan_records = std::max<uint64_t>(st->peak_fan_records, peak_f);
         for (int L = 0; L < n_levels; ++L) {
@@ -1304,18 +1277,12 @@ static int shrink_after_overflow(sp_scene* s, uint32_t n_items, sp_stats* st) {
     return 0;
 }
 
-int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample_begin, int sample_end, uint64_t seed,
-                     int clear, sp_stats* st) {
-    SP_LOCK;
-    if (s && s->committed && !s->has_camera) return fail("sp_render_region: the scene has no camera");
-    const uint64_t region = (s && s->committed && pix_end > pix_begin) ? (uint64_t)(pix_end - pix_begin) : 0;
-    int rc = begin_call(s, seed, st, "sp_render_region", (uint64_t)std::max(sample_end - sample_begin, 0) * region);
-    if (rc) return rc;
-    const uint32_t n_pix_total = (uint32_t)s->d.cam.W * (uint32_t)s->d.cam.H;
-    if (sample_begin < 0 || sample_end < sample_begin) return fail("sp_render_region: invalid sample range");
-    if (pix_begin < 0 || pix_end < pix_begin || pix_end > (int64_t)n_pix_total) return fail("sp_render_region: invalid pixel range");
+// Render samples [sample_begin, sample_end) of a region of n_region "pixels" starting at first_pix — plain pixel
+// indices, or (tiles != nullptr) texels of a tile list — into the accumulation buffer, chunk by chunk.
+static int render_chunks(sp_scene* s, uint32_t first_pix, uint32_t n_region, const uint32_t* tiles, uint32_t tile_shift,
+                         uint32_t tiles_x, int sample_begin, int sample_end, int clear, sp_stats* st, const char* what) {
     ScopedEvent ev0, ev1;
-    if (!ev0.e || !ev1.e) return fail("sp_render_region: cudaEventCreate failed");
+    if (!ev0.e || !ev1.e) return fail("%s: cudaEventCreate failed", what);
     cudaEvent_t t0 = ev0.e, t1 = ev1.e;
     // Chunks add their radiance to a scratch frame that is folded into the accumulation buffer once the chunk is
     // known to be complete, so that a chunk whose queues overflowed can be rendered again in smaller pieces.
@@ -1325,12 +1292,13 @@ int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample
     }
     CUDA_TRY(cudaEventRecord(t0, s->stream));
     if (clear) CUDA_TRY(cudaMemsetAsync(s->accum.p, 0, s->accum.n * sizeof(float4), s->stream));
-    const uint32_t first_pix = (uint32_t)pix_begin, n_region = (uint32_t)(pix_end - pix_begin);
+    int rc = 0;
     uint32_t sample = (uint32_t)sample_begin, pix = 0;          // pix: offset inside the region
     while (n_region > 0 && sample < (uint32_t)sample_end && rc == 0) {
         const uint32_t P = pick_chunk(s, n_region);
         ChunkJob job{};
         job.source = SP_SRC_CAMERA; job.run = SP_RUN_FULL; job.accum = s->scratch.p;
+        job.tiles = tiles; job.tile_shift = tile_shift; job.tiles_x = tiles_x;
         uint32_t next_sample = sample, next_pix = pix;
         if (pix == 0 && P >= n_region) {                         // whole region x several samples
             const uint32_t ns = std::min<uint32_t>(P / n_region, (uint32_t)sample_end - sample);
@@ -1342,20 +1310,62 @@ int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample
             next_pix = pix + n;
             if (next_pix == n_region) { next_pix = 0; next_sample = sample + 1; }
         }
+        // the part of the frame the chunk can touch: its pixel range, or (tiles) anything
+        float4* const acc_lo = tiles ? s->accum.p : s->accum.p + job.pix_begin;
+        float4* const scr_lo = tiles ? s->scratch.p : s->scratch.p + job.pix_begin;
+        const uint32_t n_touch = tiles ? (uint32_t)s->accum.n : job.n_pix;
         bool overflow = false;
         rc = run_chunk(s, job, st, overflow);
         if (rc) break;
         if (overflow) {
-            CUDA_TRY(cudaMemsetAsync(s->scratch.p + job.pix_begin, 0, (size_t)job.n_pix * sizeof(float4), s->stream));
+            CUDA_TRY(cudaMemsetAsync(scr_lo, 0, (size_t)n_touch * sizeof(float4), s->stream));
             rc = shrink_after_overflow(s, job.n_items, st);
             continue;
         }
-        CUDA_TRY(sp_launch_fold(s->accum.p + job.pix_begin, s->scratch.p + job.pix_begin, job.n_pix, s->stream));
+        CUDA_TRY(sp_launch_fold(acc_lo, scr_lo, n_touch, s->stream));
         if (st) st->kernel_launches += 1;
         sample = next_sample; pix = next_pix;
     }
     int rc2 = end_call(s, st, t0, t1);
     return rc ? rc : rc2;
+}
+
+int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample_begin, int sample_end, uint64_t seed,
+                     int clear, sp_stats* st) {
+    SP_LOCK;
+    if (s && s->committed && !s->has_camera) return fail("sp_render_region: the scene has no camera");
+    const uint64_t region = (s && s->committed && pix_end > pix_begin) ? (uint64_t)(pix_end - pix_begin) : 0;
+    int rc = begin_call(s, seed, st, "sp_render_region", (uint64_t)std::max(sample_end - sample_begin, 0) * region);
+    if (rc) return rc;
+    const uint32_t n_pix_total = (uint32_t)s->d.cam.W * (uint32_t)s->d.cam.H;
+    if (sample_begin < 0 || sample_end < sample_begin) return fail("sp_render_region: invalid sample range");
+    if (pix_begin < 0 || pix_end < pix_begin || pix_end > (int64_t)n_pix_total) return fail("sp_render_region: invalid pixel range");
+    return render_chunks(s, (uint32_t)pix_begin, (uint32_t)(pix_end - pix_begin), nullptr, 0u, 0u, sample_begin, sample_end, clear, st,
+                         "sp_render_region");
+}
+
+int sp_render_tiles(sp_scene* s, const int32_t* tile_ids, int n_tiles, int tile_size, int sample_begin, int sample_end,
+                    uint64_t seed, int clear, sp_stats* st) {
+    SP_LOCK;
+    if (s && s->committed && !s->has_camera) return fail("sp_render_tiles: the scene has no camera");
+    if (n_tiles < 0 || (n_tiles > 0 && !tile_ids)) return fail("sp_render_tiles: invalid tile list");
+    int shift = 0;
+    while ((1 << shift) < tile_size) ++shift;
+    if (tile_size < 1 || tile_size > 1024 || (1 << shift) != tile_size) return fail("sp_render_tiles: tile_size must be a power of two in 1..1024");
+    const uint64_t region = (uint64_t)std::max(n_tiles, 0) * (uint64_t)tile_size * (uint64_t)tile_size;
+    if (region > 0x7FFFFFFFull) return fail("sp_render_tiles: too many tiles");
+    int rc = begin_call(s, seed, st, "sp_render_tiles", (uint64_t)std::max(sample_end - sample_begin, 0) * region);
+    if (rc) return rc;
+    if (sample_begin < 0 || sample_end < sample_begin) return fail("sp_render_tiles: invalid sample range");
+    const int tiles_x = (s->d.cam.W + tile_size - 1) / tile_size, tiles_y = (s->d.cam.H + tile_size - 1) / tile_size;
+    std::vector<uint32_t> ids((size_t)n_tiles);
+    for (int i = 0; i < n_tiles; ++i) {
+        if (tile_ids[i] < 0 || tile_ids[i] >= tiles_x * tiles_y) return fail("sp_render_tiles: tile %d out of range (frame has %d x %d tiles)", tile_ids[i], tiles_x, tiles_y);
+        ids[(size_t)i] = (uint32_t)tile_ids[i];
+    }
+    CUDA_TRY(s->d_tiles.upload(ids));
+    return render_chunks(s, 0u, (uint32_t)region, s->d_tiles.p, (uint32_t)shift, (uint32_t)tiles_x, sample_begin, sample_end, clear, st,
+                         "sp_render_tiles");
 }
 
 int sp_render_samples(sp_scene* s, int sample_begin, int sample_end, uint64_t seed, int clear, sp_stats* st) {
@@ -1459,27 +1469,35 @@ int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64
     return rc;
 }
 
-static int primary_pass(sp_scene* s, int run, int sample, uint64_t seed, float* out_o, float* out_d, float* out_t, const char* what) {
+static int primary_pass(sp_scene* s, int run, int sample, uint64_t seed, float* out_o, float* out_d, float* out_t,
+                        int32_t* out_hit, float* out_n, const char* what) {
     SP_LOCK;
     int rc = begin_call(s, seed, nullptr, what, s && s->committed ? s->accum.n : 0);
     if (rc) return rc;
     if (!s->has_camera) return fail("%s: the scene has no camera", what);
     const size_t n = s->accum.n;
-    DevBuf<float> d_o, d_d, d_t;
-    auto cleanup = [&]() { d_o.release(); d_d.release(); d_t.release(); };
+    DevBuf<float> d_o, d_d, d_t, d_n;
+    DevBuf<int32_t> d_hit;
+    auto cleanup = [&]() { d_o.release(); d_d.release(); d_t.release(); d_n.release(); d_hit.release(); };
     if (run == SP_RUN_DUMP_RAYS) { TRY_OR_CLEAN(d_o.alloc(3 * n)); TRY_OR_CLEAN(d_d.alloc(3 * n)); }
-    else TRY_OR_CLEAN(d_t.alloc(n));
+    else {
+        if (out_t) TRY_OR_CLEAN(d_t.alloc(n));
+        if (out_hit) TRY_OR_CLEAN(d_hit.alloc(n));
+        if (out_n) TRY_OR_CLEAN(d_n.alloc(3 * n));
+    }
     ChunkJob job{};
     job.source = SP_SRC_CAMERA; job.run = run; job.accum = s->accum.p;
     job.pix_begin = 0; job.n_pix = (uint32_t)n; job.sample_begin = (uint32_t)sample; job.n_items = (uint32_t)n;
-    job.out_o = d_o.p; job.out_d = d_d.p; job.out_t = d_t.p;
+    job.out_o = d_o.p; job.out_d = d_d.p; job.out_t = d_t.p; job.out_hit = d_hit.p; job.out_n = d_n.p;
     bool overflow = false;                                    // a level-0-only pass queues nothing
     rc = run_chunk(s, job, nullptr, overflow);
     if (rc == 0 && run == SP_RUN_DUMP_RAYS) {
         TRY_OR_CLEAN(cudaMemcpy(out_o, d_o.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
         TRY_OR_CLEAN(cudaMemcpy(out_d, d_d.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
     } else if (rc == 0) {
-        TRY_OR_CLEAN(cudaMemcpy(out_t, d_t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+        if (out_t) TRY_OR_CLEAN(cudaMemcpy(out_t, d_t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+        if (out_hit) TRY_OR_CLEAN(cudaMemcpy(out_hit, d_hit.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (out_n) TRY_OR_CLEAN(cudaMemcpy(out_n, d_n.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
     }
     cleanup();
     return rc;
@@ -1487,12 +1505,17 @@ static int primary_pass(sp_scene* s, int run, int sample, uint64_t seed, float* 
 
 int sp_camera_rays(sp_scene* s, int sample, uint64_t seed, float* out_origins, float* out_dirs) {
     if (!out_origins || !out_dirs || sample < 0) return fail("sp_camera_rays: invalid arguments");
-    return primary_pass(s, SP_RUN_DUMP_RAYS, sample, seed, out_origins, out_dirs, nullptr, "sp_camera_rays");
+    return primary_pass(s, SP_RUN_DUMP_RAYS, sample, seed, out_origins, out_dirs, nullptr, nullptr, nullptr, "sp_camera_rays");
 }
 
 int sp_distances(sp_scene* s, uint64_t seed, float* out_t) {
     if (!out_t) return fail("sp_distances: invalid arguments");
-    return primary_pass(s, SP_RUN_DISTANCES, 0, seed, nullptr, nullptr, out_t, "sp_distances");
+    return primary_pass(s, SP_RUN_DISTANCES, 0, seed, nullptr, nullptr, out_t, nullptr, nullptr, "sp_distances");
+}
+
+int sp_aovs(sp_scene* s, int sample, uint64_t seed, int32_t* out_hit_id, float* out_t, float* out_normal) {
+    if ((!out_hit_id && !out_t && !out_normal) || sample < 0) return fail("sp_aovs: invalid arguments");
+    return primary_pass(s, SP_RUN_DISTANCES, sample, seed, nullptr, nullptr, out_t, out_hit_id, out_normal, "sp_aovs");
 }
 
 int sp_set_option(sp_scene* s, const char* name, int64_t value) {

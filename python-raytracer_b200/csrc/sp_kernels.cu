@@ -92,7 +92,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     __shared__ IterShared sh;
 
     // a queue of an earlier level overflowed: its records are incomplete, the host discards the chunk
-    if (*reinterpret_cast<volatile const unsigned int*>(&a.out.stats->overflow)) return;
+    if (*reinterpret_cast<volatile const unsigned int*>(&a.out.stats->overflow) & 0xFFFFu) return;
 
     // ---- work items of this launch ---------------------------------------------------------
     uint32_t n_rays = 0, fan_n[SP_MAX_FAN_CLASSES];
@@ -169,10 +169,20 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 uint32_t i = (uint32_t)item;
                 uint32_t sample = a.sample_begin + i / a.n_pix;
                 r.pix = a.pix_begin + i % a.n_pix;
-                r.path = sp_root_path(sample);
-                sp_camera_ray(sc.cam, r.pix, sample, sc.seed_lo, sc.seed_hi, r.o, r.d);
-                r.thr = v3(1.f);
-                r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
+                if (a.tiles) {                                // texel of a tile list -> pixel of the frame
+                    const uint32_t ts = a.tile_shift, local = r.pix & ((1u << (2u * ts)) - 1u);
+                    const uint32_t tile = __ldg(a.tiles + (r.pix >> (2u * ts)));
+                    const uint32_t px = ((tile % a.tiles_x) << ts) + (local & ((1u << ts) - 1u));
+                    const uint32_t py = ((tile / a.tiles_x) << ts) + (local >> ts);
+                    active = px < (uint32_t)sc.cam.W && py < (uint32_t)sc.cam.H;
+                    r.pix = active ? py * (uint32_t)sc.cam.W + px : 0u;
+                }
+                if (active) {
+                    r.path = sp_root_path(sample);
+                    sp_camera_ray(sc.cam, r.pix, sample, sc.seed_lo, sc.seed_hi, r.o, r.d);
+                    r.thr = v3(1.f);
+                    r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
+                }
             } else if ((FEAT & SP_F_LEVEL0) && a.source == SP_SRC_USER) {
                 uint32_t i = a.user_base + (uint32_t)item;
                 r.pix = i;
@@ -281,6 +291,14 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 const size_t oi = (a.source == SP_SRC_USER) ? (size_t)a.user_base + (size_t)item : (size_t)item;
                 if (a.out_hit) a.out_hit[oi] = hit.id;
                 if (a.out_t) a.out_t[oi] = hit.t;
+                if (a.out_n) {                           // collider normal facing the ray (collider.get_Normal x orientation)
+                    float3 n = v3(0.f);
+                    if (hit.id >= 0) {
+                        const DCollider& c0 = sc.colliders[hit.id];
+                        n = to_f3(sp_collider_normal<float>(c0.type, c0.p, from_f3<float>(fma3(r.d, hit.t, r.o)))) * (float)hit.orient;
+                    }
+                    a.out_n[3 * oi] = n.x; a.out_n[3 * oi + 1] = n.y; a.out_n[3 * oi + 2] = n.z;
+                }
             }
         }
         if ((FEAT & SP_F_LEVEL0) && a.run == SP_RUN_DISTANCES) continue;
@@ -313,6 +331,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
             const int leader = __ffs(peers) - 1;
             if ((int)lane == leader) pos = atomicAdd(&cn.bin_cnt[bin], (uint32_t)__popc(peers));
             pos = __shfl_sync(peers, pos, leader) + __popc(peers & lt_mask);
+            SP_ASSERT(a.out.stats, pos < (uint32_t)SP_BATCH, SP_CHK_BIN);
             sh.list[bin][pos] = (uint16_t)slot;
         }
         {
@@ -355,7 +374,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
             uint32_t first = SP_SLOT_NONE;
             if (want > 0) {
                 first = atomicAdd(a.out.counts + lane, want);
-                if (first + want > cap) { first = SP_SLOT_NONE; a.out.stats->overflow = 1u; }
+                if (first + want > cap || first + want < first) { first = SP_SLOT_NONE; atomicOr(&a.out.stats->overflow, 1u); }
                 else if (lane > 0) first += a.out.fan_base[lane - 1];
             }
             cn.queue_base[lane] = first;
@@ -445,7 +464,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     }
 }
 
-#include "sp_path_kernel.cuh"
+#include "sp_warp_kernel.cuh"
 
 // ---- frame resolve: average, sRGB OETF, per-pixel max normalisation, truncation to uint8 ---------
 // scene.py:118-140 + colour_functions.py:4-18.  Double precision: the output is quantised by
@@ -542,47 +561,39 @@ static LevelKernel level_kernel(uint32_t material_set, bool level0) {
     }
 }
 
-// Full runs of scenes whose colliders fit one staged chunk (+ the BVH) go through sp_path_kernel (sp_path_kernel.cuh).
+// Queue-fed levels of small untextured Monte-Carlo scenes run the warp-autonomous kernel (sp_warp_kernel.cuh).
 // SIGHTPY_WARP_KERNEL=0 / option "warp_kernel" = 0 keeps them on sp_level_kernel (A/B measurements, parity tests).
-static LevelKernel path_kernel(uint32_t material_set, bool level0) {
-    switch (material_set) {
-    case SP_SET_MC: return level0 ? sp_path_kernel<SP_SET_MC | SP_F_LEVEL0> : sp_path_kernel<SP_SET_MC | SP_F_QUEUES>;
-    case SP_SET_WHITTED: return level0 ? sp_path_kernel<SP_SET_WHITTED | SP_F_LEVEL0> : sp_path_kernel<SP_SET_WHITTED | SP_F_QUEUES>;
-    case SP_SET_ALL_BVH: return level0 ? sp_path_kernel<SP_SET_ALL_BVH | SP_F_LEVEL0> : sp_path_kernel<SP_SET_ALL_BVH | SP_F_QUEUES>;
-    default: return level0 ? sp_path_kernel<SP_SET_ALL | SP_F_LEVEL0> : sp_path_kernel<SP_SET_ALL | SP_F_QUEUES>;
-    }
-}
-
-static size_t path_smem_bytes(const DScene& sc) {
-    return geom_smem_bytes(sc) + (size_t)sc.n_stash_bins * SPP_STASH_STRIDE * sizeof(uint32_t);
-}
-
-bool sp_use_path_kernel(const DScene& sc, uint32_t material_set) {
+bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set) {
     static const bool enabled = [] { const char* e = getenv("SIGHTPY_WARP_KERNEL"); return !(e && e[0] == '0'); }();
-    if (!enabled || !sc.use_warp_kernel) return false;
-    if (sc.all.n_chunks != 1) return false;                  // exhaustive multi-chunk walks stay on sp_level_kernel
-    if (!(material_set & SP_F_BVH) && sc.n_colliders > SP_SMALL_COLLIDERS) return false;
+    if (!enabled || !sc.use_warp_kernel || material_set != SP_SET_MC) return false;
+    if (sc.all.n_chunks != 1 || sc.bvh.n_nodes != 0 || sc.n_colliders > SPW_MAX_COLLIDERS) return false;
+    for (int c = 0; c < sc.n_fan_classes; ++c)
+        if (sc.fan_mult[c] > 1024) return false;
     return true;
 }
 
-int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0, bool path) {
+int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    LevelKernel k = path ? path_kernel(material_set, level0) : level_kernel(material_set, level0);
-    const size_t smem = path ? path_smem_bytes(sc) : geom_smem_bytes(sc);
-    const size_t opt_in = std::max<size_t>(smem, (size_t)SP_CHUNK_VEC4 * sizeof(float4));
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opt_in) != cudaSuccess) { cudaGetLastError(); return 0; }
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, path ? SPP_BLOCK : SP_BLOCK, smem) != cudaSuccess || per_sm < 1) {
-        cudaGetLastError();
-        return 0;                                             // does not fit (too many stash bins for the shared memory): caller falls back
+    if (!level0 && sp_use_warp_kernel(sc, material_set)) {
+        auto k = sp_warp_kernel<SP_SET_MC>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SPW_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        return sms * per_sm;
     }
+    LevelKernel k = level_kernel(material_set, level0);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SP_BLOCK, geom_smem_bytes(sc)) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
     return sms * per_sm;
 }
 
-cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, bool path, cudaStream_t st) {
-    if (path && a.run == SP_RUN_FULL) {
-        path_kernel(material_set, a.source != SP_SRC_QUEUES)<<<grid, SPP_BLOCK, path_smem_bytes(sc), st>>>(sc, a);
+cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st) {
+    if (a.source == SP_SRC_QUEUES && a.run == SP_RUN_FULL && sp_use_warp_kernel(sc, material_set)) {
+        sp_warp_kernel<SP_SET_MC><<<grid, SPW_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
         return cudaGetLastError();
     }
     level_kernel(material_set, a.source != SP_SRC_QUEUES)<<<grid, SP_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);

@@ -15,6 +15,10 @@ struct LevelArgs {
     // level 0, camera: item i -> pixel pix_begin + i % n_pix, sample sample_begin + i / n_pix
     // level 0, user rays: item i -> ray user_base + i (interleaved xyz), pixel id = ray index
     uint32_t pix_begin, n_pix, sample_begin, n_items0, user_base;
+    // tile-sharded frames (sp_render_tiles): the "pixel" index above runs over the texels of a list of square tiles,
+    // tile_size^2 per tile, row-major inside a tile; texels outside the frame (edge tiles) are skipped
+    const uint32_t* tiles;         // tile ids (row-major over the frame's tile grid), nullptr = plain pixel indices
+    uint32_t tile_shift, tiles_x;  // tile_size = 1 << tile_shift; tiles per row of the frame
     const float* user_o;
     const float* user_d;
     // level >= 1: records written by the previous level
@@ -25,6 +29,7 @@ struct LevelArgs {
     float4* accum;                 // per pixel (or per user ray): xyz = sum of radiance
     // optional per-item outputs of level 0
     int32_t* out_hit; float* out_t; float* out_o; float* out_d;
+    float* out_n;                  // oriented collider normal at the primary hit, 3 floats per item (sp_aovs)
     const int2* shadow_slot;
 };
 
@@ -37,10 +42,9 @@ struct ResolveArgs {
 };
 
 uint32_t sp_pick_material_set(uint32_t needed_features);          // smallest compiled kernel variant covering them
-bool sp_use_path_kernel(const DScene& sc, uint32_t material_set);      // full runs go through sp_path_kernel (sp_path_kernel.cuh)
-// CTAs of a persistent launch (0: the kernel does not fit the SM with this scene's shared-memory needs)
-int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0, bool path);
-cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, bool path, cudaStream_t st);
+bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set);      // queue-fed levels run sp_warp_kernel (sp_warp_kernel.cuh)
+int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0);   // CTAs of a persistent launch
+cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
 cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st);   // accum += scratch; scratch = 0
 cudaError_t sp_upload_decode_tables(const float* plain256, const float* linear256);

@@ -186,6 +186,7 @@ SP_DEV void sp_emit_ray(ShadeCtx& cx_, const Ray& r, float3 o, float3 d, float3 
     const uint32_t slot = cx_.ray_used == 0u ? cx_.ray_slot : cx_.ray_slot1;
     if (slot == SP_SLOT_NONE) return;       // the CTA's reservation overflowed the queue (reported to the host)
     uint32_t meta = sp_pack_meta(meta_depth(r.meta) + 1u, dr, medium, (uint32_t)src, mode);
+    SP_ASSERT(cx_.out->stats, slot < cx_.out->rays.capacity, SP_CHK_SLOT);
     sp_write_record(cx_.out->rays, slot, o, d, thr, r.pix, sp_child_path(r.path, k), meta);
     cx_.ray_used += 1u;
 }
@@ -247,6 +248,7 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
                 uint32_t mode = (planar || side_plus > 0.f) ? SP_SELF_SKIP : SP_SELF_FAR;
                 uint32_t meta = sp_pack_meta(depth + 1u, dr + 1u, medium, (uint32_t)h.id, mode);
                 if (cx_.fan_slot != SP_SLOT_NONE) {
+                    SP_ASSERT(cx_.out->stats, cx_.fan_slot < cx_.out->fans.capacity, SP_CHK_SLOT);
                     sp_write_record(cx_.out->fans, cx_.fan_slot, nudged, N, thr, r.pix, r.path, meta);
                     cx_.fan_slot = SP_SLOT_NONE;            // consumed
                 }

@@ -103,9 +103,6 @@ struct DCamera {
 };
 
 #define SP_MAX_FAN_CLASSES 4
-#define SP_SMALL_COLLIDERS 64      // scenes up to this size keep their per-collider tables in shared memory (sp_path_kernel.cuh)
-// stash bins of sp_path_kernel: hits that are shaded 32 at a time by the sp_shade instantiation of their material kind
-enum { SP_BIN_REFR = 0, SP_BIN_GLOSSY = 1, SP_BIN_THIN = 2, SP_BIN_SKY = 3, SP_BIN_GENERIC = 4, SP_N_BINS = 5 };
 #define SP_MAX_IMPORTANCE 16
 #define SP_MAX_LIGHTS 8
 
@@ -114,9 +111,7 @@ struct DScene {
     DBvh bvh;                          // n_nodes == 0: every collider is in the streams
     const DCollider* colliders;
     const DColInfo* col_info;
-    const float4* col_lite;        // per collider: its material's plain colour, 1 / diffuse_rays (inline shading, sp_path_kernel.cuh)
-    const uint2* col_cls;          // per collider: what a hit does (sp_hit_class, sp_api.cu), read by sp_path_kernel
-    const float2* col_src;         // per collider: position in the staged chunk's id array (int bits, -1: in the BVH), cosine-pdf weight
+    const float4* col_lite;        // per collider: its material's plain colour, 1 / diffuse_rays (inline shading, sp_warp_kernel.cuh)
     const double* colliders_d;     // [n][44] double payloads for the precise hit path
     const DPrimitive* prims;
     const DMaterial* mats;
@@ -132,8 +127,6 @@ struct DScene {
     unsigned long long fan_magic[SP_MAX_FAN_CLASSES];   // ceil(2^64 / fan_mult): n / mult == __umul64hi(n, magic) for n < 2^32
     int fan_mult[SP_MAX_FAN_CLASSES];     // rays per fan record of each class (class 0: 1)
     int use_warp_kernel;               // option "warp_kernel" (host side only)
-    int stash_slot[8];                 // sp_path_kernel: stash bin (SP_BIN_*) -> index of its shared-memory region, -1 = the scene has no such hits
-    int n_stash_bins;                  // regions in use
     uint32_t seed_lo, seed_hi;
     uint32_t philox_keys[20];          // the ten Philox round key pairs of (seed_lo, seed_hi), filled per call
 };
@@ -198,12 +191,22 @@ struct LevelOut {
     DeviceStats* stats;
 };
 
+// Development build (-DSP_CHECKED, `make checked`): the hand-rolled protocols of the level kernels (warp-private
+// stash and slabs, cp.async slot reuse, queue slot reservations) assert their invariants and report through bits
+// 16+ of DeviceStats::overflow, which the host turns into an error (compute-sanitizer is not available on the pool).
+#ifdef SP_CHECKED
+#define SP_ASSERT(stats, cond, code) do { if (!(cond)) atomicOr(&(stats)->overflow, 0x10000u << (code)); } while (0)
+#else
+#define SP_ASSERT(stats, cond, code) do { } while (0)
+#endif
+enum { SP_CHK_SLOT = 0, SP_CHK_STASH = 1, SP_CHK_SLAB = 2, SP_CHK_FETCH = 3, SP_CHK_BIN = 4 };
+
 struct DeviceStats {
     unsigned long long rays[SP_MAX_LEVELS];
     unsigned long long shadow_rays;
     // -DSP_PHASE_TIMING builds: warp-cycles spent in [0] ray generation, [1] intersection, [2] park + count,
     // [3] waiting at barrier A, [4] shading, [5] waiting at barrier C (summed over warps and launches)
     unsigned long long phase_cycles[6];
-    unsigned int overflow;
+    unsigned int overflow;             // bit 0: a queue was too small; bits 16+: SP_ASSERT failures (SP_CHK_*)
     unsigned int pad;
 };

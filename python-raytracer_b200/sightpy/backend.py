@@ -86,9 +86,12 @@ def load_library():
         "sp_scene_set_importance": (i32, [vp, vp, i32]),
         "sp_scene_set_shadow_colliders": (i32, [vp, vp, i32]),
         "sp_scene_commit": (i32, [vp]),
+        "sp_scene_clear_textures": (i32, [vp]),
+        "sp_scene_update_camera": (i32, [vp, vp]),
         "sp_render": (i32, [vp, i32, u64, vp, vp, C.POINTER(Stats)]),
         "sp_render_samples": (i32, [vp, i32, i32, u64, i32, C.POINTER(Stats)]),
         "sp_render_region": (i32, [vp, C.c_int64, C.c_int64, i32, i32, u64, i32, C.POINTER(Stats)]),
+        "sp_render_tiles": (i32, [vp, vp, i32, i32, i32, i32, u64, i32, C.POINTER(Stats)]),
         "sp_accum_device_ptr": (vp, [vp]),
         "sp_accum_bytes": (u64, [vp]),
         "sp_resolve": (i32, [vp, i32, vp, vp]),
@@ -96,6 +99,7 @@ def load_library():
         "sp_trace": (i32, [vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(Stats)]),
         "sp_camera_rays": (i32, [vp, i32, u64, vp, vp]),
         "sp_distances": (i32, [vp, u64, vp]),
+        "sp_aovs": (i32, [vp, i32, u64, vp, vp, vp]),
         "sp_set_option": (i32, [vp, C.c_char_p, C.c_int64]),
         "sp_measure_peaks": (i32, [f64p, f64p]),
     }
@@ -151,6 +155,7 @@ class NativeScene:
 
     def __init__(self, flat: FlatScene, device=None):
         self.lib = bind_device(device)
+        self.device_index = _BOUND_DEVICE        # the CUDA device all of this scene's memory and kernels live on
         self.flat = flat
         self.width = int(flat.camera["width"])
         self.height = int(flat.camera["height"])
@@ -162,7 +167,34 @@ class NativeScene:
             self.close()
             raise
 
-    def _upload(self, flat):
+    TABLES = ("materials", "primitives", "colliders", "lights", "importance", "shadow_colliders")
+
+    def update(self, flat):
+        """Re-describe this committed scene in place (animation frames, in-place edits of a Scene): only what changed
+        is handed over again.  A camera move alone needs no commit at all; anything else is re-committed on the same
+        handle, which keeps the wavefront queues, the frame buffers, keyed textures and — while the scene keeps its
+        shape — the queue-occupancy estimates of earlier frames.  Returns what was done."""
+        old, lib, h = self.flat, self.lib, self.handle
+        same_tex = len(old.textures) == len(flat.textures) and all(
+            getattr(a, "key", 0) == getattr(b, "key", 1) and a.decode == b.decode for a, b in zip(old.textures, flat.textures))
+        same_tables = (all(np.array_equal(getattr(old, k), getattr(flat, k)) for k in self.TABLES)
+                       and np.array_equal(old.media, flat.media) and np.array_equal(old.ambient, flat.ambient))
+        same_size = (int(old.camera["width"]), int(old.camera["height"])) == (int(flat.camera["width"]), int(flat.camera["height"]))
+        if same_tex and same_tables and same_size:
+            if old.camera.tobytes() == flat.camera.tobytes():
+                return "unchanged"
+            cam = np.ascontiguousarray(flat.camera.reshape(1))
+            _check(lib, lib.sp_scene_update_camera(h, _ptr(cam)), "sp_scene_update_camera")
+            self.flat = flat
+            return "camera"
+        if not same_tex:
+            _check(lib, lib.sp_scene_clear_textures(h), "sp_scene_clear_textures")
+        self._upload(flat, textures=not same_tex)
+        self.flat = flat
+        self.width, self.height = int(flat.camera["width"]), int(flat.camera["height"])
+        return "commit"
+
+    def _upload(self, flat, textures=True):
         lib, h = self.lib, self.handle
         amb = np.ascontiguousarray(flat.ambient, dtype=np.float64)
         mre = np.ascontiguousarray(flat.media.real, dtype=np.float64)
@@ -170,7 +202,7 @@ class NativeScene:
         _check(lib, lib.sp_scene_set_globals(h, _ptr(amb), _ptr(mre), _ptr(mim), len(flat.media)), "set_globals")
         cam = np.ascontiguousarray(flat.camera.reshape(1))
         _check(lib, lib.sp_scene_set_camera(h, _ptr(cam)), "set_camera")
-        for t in flat.textures:
+        for t in (flat.textures if textures else ()):
             tid = C.c_int(-1)
             u8 = np.ascontiguousarray(t.u8)
             _check(lib, lib.sp_scene_add_texture_keyed(h, int(getattr(t, "key", 0)), _ptr(u8), u8.shape[0], u8.shape[1],
@@ -217,6 +249,18 @@ class NativeScene:
                "sp_render_region")
         return st.as_dict()
 
+    def render_tiles(self, tile_ids, tile_size, sample_begin, sample_end, seed=0, clear=True):
+        """Accumulate samples [sample_begin, sample_end) of the listed square tiles (row-major tile ids)."""
+        ids = np.ascontiguousarray(tile_ids, dtype=np.int32)
+        st = Stats()
+        _check(self.lib, self.lib.sp_render_tiles(self.handle, _ptr(ids), len(ids), int(tile_size), int(sample_begin),
+                                                  int(sample_end), int(seed), int(bool(clear)), C.byref(st)),
+               "sp_render_tiles")
+        return st.as_dict()
+
+    def n_tiles(self, tile_size):
+        return -(-self.width // tile_size) * -(-self.height // tile_size)
+
     def accum_pointer(self):
         return int(self.lib.sp_accum_device_ptr(self.handle)), int(self.lib.sp_accum_bytes(self.handle))
 
@@ -226,9 +270,14 @@ class NativeScene:
                                                       int(cuda_stream is not None)), "sp_scene_set_stream")
 
     def use_current_stream(self):
-        """Enqueue on torch's current CUDA stream (so that a following NCCL collective is ordered)."""
+        """Enqueue on torch's current CUDA stream *of the library's device* (so that a following NCCL collective is
+        ordered after the kernels).  torch's current device must be that device: a collective issued on another
+        device's stream would not be ordered at all."""
         import torch
-        self.set_stream(torch.cuda.current_stream().cuda_stream)
+        if torch.cuda.current_device() != self.device_index:
+            raise RuntimeError(f"torch's current CUDA device is {torch.cuda.current_device()} but sightpy is bound to device "
+                               f"{self.device_index}: call torch.cuda.set_device({self.device_index}) (LOCAL_RANK) first")
+        self.set_stream(torch.cuda.current_stream(self.device_index).cuda_stream)
 
     def accum_tensor(self):
         """torch.float32 view (no copy) of the device accumulation buffer (float4 per pixel)."""
@@ -266,6 +315,16 @@ class NativeScene:
         _check(self.lib, self.lib.sp_camera_rays(self.handle, int(sample), int(seed), _ptr(o), _ptr(d)),
                "sp_camera_rays")
         return o, d
+
+    def aovs(self, sample=0, seed=0):
+        """Per-pixel nearest collider index, hit distance and ray-facing collider normal of one primary ray per pixel."""
+        n = self.width * self.height
+        hit = np.empty(n, dtype=np.int32)
+        t = np.empty(n, dtype=np.float32)
+        normal = np.empty((n, 3), dtype=np.float32)
+        _check(self.lib, self.lib.sp_aovs(self.handle, int(sample), int(seed), _ptr(hit), _ptr(t), _ptr(normal)), "sp_aovs")
+        return dict(hit_id=hit.reshape(self.height, self.width), t=t.reshape(self.height, self.width),
+                    normal=normal.reshape(self.height, self.width, 3))
 
     def distances(self, seed=0):
         t = np.empty(self.width * self.height, dtype=np.float32)

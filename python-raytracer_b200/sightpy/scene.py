@@ -29,9 +29,14 @@ class Scene:
         self.importance_sampled_list = []
         self.ambient_color = ambient_color
         self.n = n                      # refractive index of the ambient medium
-        self.seed = 0                   # frame seed of the counter-based RNG
+        # Frame seed of the counter-based RNG.  None (default): every render() of this Scene draws a fresh sample set
+        # (seed = number of frames rendered so far), as successive renders of the reference do with numpy's global
+        # stream, so averaging several renders reduces noise; an int pins it (the same frame every time).
+        self.seed = None
+        self.frames_rendered = 0
         self.last_stats = None
         self._native = None
+        self._stale = True
 
     # ---- description ---------------------------------------------------------------------
     def add_Camera(self, look_from, look_at, **kwargs):
@@ -64,21 +69,36 @@ class Scene:
         self._dirty()
 
     # ---- backend plumbing ------------------------------------------------------------------
+    # The reference deep-copies the scene on every render (scene.py:85), so whatever a script changed in place —
+    # primitive.rotate, camera attributes, material fields — is what gets rendered.  Here the committed device copy
+    # is kept between renders; scenes of up to AUTO_REFLATTEN colliders are flattened again on every render (tens of
+    # microseconds per collider) and only what differs is handed to the device (backend.NativeScene.update); larger
+    # scenes are re-described after add*() calls or an explicit invalidate().
+    AUTO_REFLATTEN = 512
+
     def _dirty(self):
-        if self._native is not None:
+        self._stale = True
+
+    def invalidate(self, full=False):
+        """Call after mutating primitives in place (e.g. in an animation's update_scene).  full=True also drops the
+        device copy, so that the next render describes and uploads the whole scene again."""
+        self._stale = True
+        if full and self._native is not None:
             self._native.close()
             self._native = None
 
-    def invalidate(self):
-        """Call after mutating primitives in place (e.g. in an animation's update_scene)."""
-        self._dirty()
-
     def _backend(self):
+        from .backend import NativeScene
+        from .flatten import flatten_scene
         if self._native is None:
-            from .backend import NativeScene
-            from .flatten import flatten_scene
             self._native = NativeScene(flatten_scene(self))
+        elif self._stale or len(self.collider_list) <= self.AUTO_REFLATTEN:
+            self._native.update(flatten_scene(self))
+        self._stale = False
         return self._native
+
+    def _frame_seed(self):
+        return self.frames_rendered if self.seed is None else int(self.seed)
 
     # ---- rendering -------------------------------------------------------------------------
     def render(self, samples_per_pixel, progress_bar=False, batch_size=None):
@@ -88,16 +108,22 @@ class Scene:
         print("Rendering...")
         t0 = time.time()
         from .parallel import render_frame
-        srgb8, stats = render_frame(self._backend(), int(samples_per_pixel), self.seed)
+        srgb8, stats = render_frame(self._backend(), int(samples_per_pixel), self._frame_seed())
+        self.frames_rendered += 1
         self.last_stats = stats
         print("Render Took", time.time() - t0)
         return Image.fromarray(srgb8, "RGB")
+
+    def get_aovs(self, sample=0):
+        """Debug buffers of one primary ray per pixel: dict(hit_id H x W int32 (index into collider_list, -1 = none),
+        t H x W float32 (inf = none), normal H x W x 3 float32 (collider normal facing the ray))."""
+        return self._backend().aovs(sample, self._frame_seed())
 
     def get_distances(self):
         """Debug depth map (scene.py:142-166)."""
         print("Rendering...")
         t0 = time.time()
-        t = self._backend().distances(self.seed).astype(np.float64)
+        t = self._backend().distances(self._frame_seed()).astype(np.float64)
         g = np.where(t <= 10, t, 10) / 10
         print("Render Took", time.time() - t0)
         h, w = self.camera.screen_height, self.camera.screen_width

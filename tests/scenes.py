@@ -354,4 +354,4 @@ def fuzzmc(ns, width=32, height=24, seed=0):
 
 
 BUILDERS = {"example1": example1, "example2": example2, "example3": example3, "example4": example4,
-            "cornell": cornell, "triangles": triangles, "fuzz": fuzz, "fuzzmc": fuzzmc}
+            "cornell": cornell, "triangles": triangles, "stress": stress, "fuzz": fuzz, "fuzzmc": fuzzmc}

@@ -26,7 +26,31 @@ WHITTED += sorted((k for k in REPORT if k.startswith("fuzz_")), key=lambda k: in
 MONTE_CARLO = ["example2_mc", "cornell", "cornell_mc"]
 MONTE_CARLO += sorted((k for k in REPORT if k.startswith("fuzzmc_")), key=lambda k: int(k[7:]))
 RGB_TOL = 1e-3
-TEXEL_TIE_BUDGET = 0.005      # fraction of rays allowed to exceed RGB_TOL (survey: 0.001-3 % from float32 rays alone)
+# Whitted scenes: every ray outside the reference's own tie mask (tests/tiemask.py: rays whose reference radiance or
+# nearest collider moves when the direction is perturbed by 1 float32 ulp) must be within RGB_TOL.  Measured on B200
+# (profiles/r2_parity_measured.json): 0 unmasked rays over tolerance on all 18 scenes, at most 5 of 12 288 rays masked.
+MASK_ULPS = 1
+MAX_MASKED_FRACTION = 0.002   # survey: float32 rounding of the primary rays alone moves 0.001-3.1 % of the pixels
+
+# Counts measured on B200 by an earlier run of this suite (tests/golden/gpu_measured.json); a test that allows
+# "grazing ties" allows the measured count + 1, not a flat percentage.  Every run writes what it saw to
+# gpurun_out/parity_measured.json.
+_MEASURED_FILE = GOLDEN / "gpu_measured.json"
+MEASURED = json.loads(_MEASURED_FILE.read_text()) if _MEASURED_FILE.exists() else {}
+_SEEN = {}
+
+
+def check_count(key, count, n, fallback_fraction):
+    """assert count <= measured + 1 (or, before anything was measured, count / n < fallback_fraction)"""
+    _SEEN[key] = {"count": int(count), "of": int(n)}
+    out = GOLDEN.parent.parent / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "parity_measured.json").write_text(json.dumps(_SEEN, indent=1))
+    if key in MEASURED:
+        allowed = MEASURED[key]["count"] + 1
+        assert count <= allowed, f"{key}: {count} of {n} (measured {MEASURED[key]['count']}, allowed {allowed})"
+    else:
+        assert count / max(n, 1) < fallback_fraction, f"{key}: {count} of {n}"
 
 
 def native_for(name):
@@ -39,7 +63,7 @@ def native_for(name):
 @pytest.mark.parametrize("name", WHITTED)
 def test_whitted_matches_reference(name):
     g = load_golden(name)
-    nat, _ = native_for(name)
+    nat, flat = native_for(name)
     out = nat.trace(g["origins"], g["dirs"], seed=0)
     nat.close()
     assert np.array_equal(out["hit_id"], g["hit_id"].astype(np.int32)), "nearest-collider ids differ from the reference"
@@ -47,8 +71,13 @@ def test_whitted_matches_reference(name):
     assert np.array_equal(np.isfinite(out["t"]), fin)
     np.testing.assert_allclose(out["t"][fin], g["t"][fin], rtol=2e-5, atol=1e-5)
     err = np.abs(out["rgb"].astype(np.float64) - g["rgb"]).max(axis=1)
-    frac = float(np.mean(err > RGB_TOL))
-    assert frac <= TEXEL_TIE_BUDGET, f"{frac:.4%} of rays off by > {RGB_TOL} (budget {TEXEL_TIE_BUDGET:.2%})"
+    from tiemask import sensitivity_mask
+    mask, _ = sensitivity_mask(flat, g["origins"], g["dirs"], tol=RGB_TOL, ulps=MASK_ULPS, seed=0)
+    bad = (err > RGB_TOL) & ~mask
+    print(f"{name}: {int(mask.sum())} of {len(mask)} rays masked ({mask.mean():.4%}), {int((err > RGB_TOL).sum())} over "
+          f"{RGB_TOL} in all, {int(bad.sum())} of them unmasked")
+    assert mask.mean() <= MAX_MASKED_FRACTION, f"{mask.mean():.4%} of the rays sit on a tie of the reference itself"
+    assert not bad.any(), f"{int(bad.sum())} unmasked rays off by > {RGB_TOL}: {np.flatnonzero(bad)[:8]}"
     assert np.median(err) < 1e-6
     assert abs(out["rgb"].mean() - g["rgb"].mean()) < 2e-3 * g["rgb"].mean()
 
@@ -66,8 +95,8 @@ def test_monte_carlo_matches_oracle_ray_by_ray(name):
     assert np.array_equal(out["hit_id"], want["hit_id"])
     err = np.abs(out["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)
     scale = 1.0 + np.abs(want["rgb"]).max(axis=1)
-    frac = float(np.mean(err > RGB_TOL * scale))
-    assert frac < 0.03, f"{frac:.3%} of rays differ from the oracle"
+    # measured on B200: not one ray of the 11 Monte-Carlo fixtures is off by more than RGB_TOL (largest 8e-4)
+    check_count(f"mc_rays_over_tol/{name}", int(np.sum(err > RGB_TOL * scale)), len(err), 0.03)
     assert np.median(err) < 1e-5
     assert abs(out["rgb"].mean() - want["rgb"].mean()) < 0.01 * want["rgb"].mean()
     # and statistically against the reference's own (numpy-stream) estimate of the same rays
@@ -186,7 +215,7 @@ def test_cornell_frame_equals_oracle_frame_pixel_by_pixel():
     orc = Oracle(flat, rng="philox", seed=21)
     want = sum(orc.trace(o, d, sample=s)["rgb"] for s, (o, d) in enumerate(rays)) / spp
     err = np.abs(gpu.reshape(3, -1).T - want).max(axis=1)
-    assert float(np.mean(err > RGB_TOL * (1.0 + np.abs(want).max(axis=1)))) < 0.01
+    check_count("rays_over_tol/cornell_frame", int(np.sum(err > RGB_TOL * (1.0 + np.abs(want).max(axis=1)))), len(err), 0.01)
     assert abs(gpu.mean() - want.mean()) < 0.005 * want.mean()
 
 
@@ -260,11 +289,11 @@ def test_stress_scene_multi_chunk_matches_oracle():
     out = nat.trace(o, d, seed=3)
     nat.close()
     want = Oracle(flat, rng="philox", seed=3).trace(o, d)
-    assert np.mean(out["hit_id"] != want["hit_id"]) < 0.003          # grazing ties
+    check_count("hit_mismatch/stress_multi_chunk", int(np.sum(out["hit_id"] != want["hit_id"])), len(want["hit_id"]), 0.003)   # grazing ties
     same = out["hit_id"] == want["hit_id"]
     err = np.abs(out["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[same]
     scale = 1.0 + np.abs(want["rgb"]).max(axis=1)[same]
-    assert float(np.mean(err > RGB_TOL * scale)) < 0.03
+    check_count("rays_over_tol/stress_multi_chunk", int(np.sum(err > RGB_TOL * scale)), len(err), 0.03)
     assert np.median(err) < 1e-5
     assert abs(out["rgb"].mean() - want["rgb"].mean()) < 0.02 * want["rgb"].mean()
     assert out["stats"]["shadow_rays"] > 0
@@ -289,7 +318,7 @@ def test_full_resolution_frame_matches_oracle_on_sampled_pixels(name, size, spp)
     want = Oracle(flat, rng="philox", seed=6).trace(o[pick], d[pick], pix=pick.astype(np.uint32))
     got = lin.reshape(3, -1).T[pick]
     err = np.abs(got.astype(np.float64) - want["rgb"]).max(axis=1)
-    assert float(np.mean(err > RGB_TOL)) <= 0.02, f"{np.mean(err > RGB_TOL):.3%} of sampled pixels off by > {RGB_TOL}"
+    check_count(f"rays_over_tol/full_resolution_{name}", int(np.sum(err > RGB_TOL)), len(err), 0.02)
     assert np.median(err) < 1e-6
 
 
@@ -384,11 +413,11 @@ def test_mixed_fan_classes_point_light_textured_diffuse_match_oracle(importance)
     out = nat.trace(o, d, seed=8)
     nat.close()
     want = Oracle(flat, rng="philox", seed=8).trace(o, d)
-    assert np.mean(out["hit_id"] != want["hit_id"]) < 0.002
+    check_count(f"hit_mismatch/mixed_fans_{importance}", int(np.sum(out["hit_id"] != want["hit_id"])), len(want["hit_id"]), 0.002)
     same = out["hit_id"] == want["hit_id"]
     err = np.abs(out["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[same]
     scale = 1.0 + np.abs(want["rgb"]).max(axis=1)[same]
-    assert float(np.mean(err > RGB_TOL * scale)) < 0.03, float(np.mean(err > RGB_TOL * scale))
+    check_count(f"rays_over_tol/mixed_fans_{importance}", int(np.sum(err > RGB_TOL * scale)), len(err), 0.03)
     assert abs(out["rgb"].mean() - want["rgb"].mean()) < 0.02 * want["rgb"].mean()
 
 
@@ -422,10 +451,11 @@ def test_textures_stay_resident_across_scene_rebuilds():
     but its images are found in the device-resident texture cache by key: same frame, far cheaper upload."""
     import time
     scene = build_scene("example1", (64, 48))
+    scene.seed = 0                                    # the same sample set every frame
     first = np.asarray(scene.render(2))
     t = []
     for _ in range(3):
-        scene.invalidate()
+        scene.invalidate(full=True)
         t0 = time.perf_counter()
         again = np.asarray(scene.render(2))
         t.append(time.perf_counter() - t0)
@@ -493,11 +523,11 @@ def test_bvh_and_exhaustive_loop_agree():
     nat.set_option("bvh", 0)
     brute = nat.trace(o, d, seed=3)
     nat.close()
-    assert np.mean(with_bvh["hit_id"] != brute["hit_id"]) < 0.002
+    check_count("hit_mismatch/bvh_vs_exhaustive", int(np.sum(with_bvh["hit_id"] != brute["hit_id"])), len(brute["hit_id"]), 0.002)
     same = with_bvh["hit_id"] == brute["hit_id"]
     np.testing.assert_allclose(with_bvh["t"][same], brute["t"][same], rtol=1e-5, atol=1e-5)
     err = np.abs(with_bvh["rgb"] - brute["rgb"]).max(axis=1)[same]
-    assert np.mean(err > 1e-3) < 0.01
+    check_count("rays_over_tol/bvh_vs_exhaustive", int(np.sum(err > 1e-3)), len(err), 0.01)
     assert abs(with_bvh["stats"]["rays_total"] - brute["stats"]["rays_total"]) <= 0.001 * brute["stats"]["rays_total"]
     want = Oracle(flat, rng="philox", seed=3).trace(o, d)
     ok = brute["hit_id"] == want["hit_id"]
@@ -549,10 +579,11 @@ def test_triangle_mesh_from_obj_matches_oracle(tmp_path):
     out = nat.trace(o, d, seed=4)
     nat.close()
     want = Oracle(flat, rng="philox", seed=4).trace(o, d)
-    assert np.mean(out["hit_id"] != want["hit_id"]) < 0.01          # shared edges of a closed mesh are exact ties
+    # shared edges of a closed mesh are exact ties (test_exact_distance_ties_are_pinned)
+    check_count("hit_mismatch/obj_mesh", int(np.sum(out["hit_id"] != want["hit_id"])), len(want["hit_id"]), 0.01)
     same = out["hit_id"] == want["hit_id"]
     err = np.abs(out["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[same]
-    assert float(np.mean(err > RGB_TOL * (1.0 + np.abs(want["rgb"]).max(axis=1)[same]))) < 0.03
+    check_count("rays_over_tol/obj_mesh", int(np.sum(err > RGB_TOL * (1.0 + np.abs(want["rgb"]).max(axis=1)[same]))), len(err), 0.03)
     assert abs(out["rgb"].mean() - want["rgb"].mean()) < 0.03 * want["rgb"].mean()
 
 
@@ -646,11 +677,11 @@ def test_warp_autonomous_and_cooperative_kernels_agree(seed):
     np.testing.assert_allclose(warp["rgb"], coop["rgb"], rtol=2e-4, atol=1e-5)
     np.testing.assert_allclose(frame_w, frame_c, rtol=2e-4, atol=1e-5)
     want = Oracle(flat, rng="philox", seed=11).trace(o, d)
-    assert np.mean(warp["hit_id"] != want["hit_id"]) < 0.002
+    check_count(f"hit_mismatch/plain_mc_{seed}", int(np.sum(warp["hit_id"] != want["hit_id"])), len(want["hit_id"]), 0.002)
     same = warp["hit_id"] == want["hit_id"]
     err = np.abs(warp["rgb"].astype(np.float64) - want["rgb"]).max(axis=1)[same]
     scale = 1.0 + np.abs(want["rgb"]).max(axis=1)[same]
-    assert float(np.mean(err > RGB_TOL * scale)) < 0.03, float(np.mean(err > RGB_TOL * scale))
+    check_count(f"rays_over_tol/plain_mc_{seed}", int(np.sum(err > RGB_TOL * scale)), len(err), 0.03)
     assert abs(warp["rgb"].mean() - want["rgb"].mean()) < 0.02 * want["rgb"].mean()
 
 
@@ -670,3 +701,161 @@ def test_warp_kernel_slabs_survive_tiny_chunks_and_report_overflow():
     with pytest.raises(RuntimeError, match="overflow"):
         nat.render(2, seed=0)
     nat.close()
+
+
+def test_interleaved_tile_shards_add_up_to_the_full_frame():
+    """Tile sharding (parallel.py `tiles`, sp_render_tiles): the interleaved 64x64-tile lists of four ranks rendered
+    into one accumulator reproduce the full frame (same Philox keys per pixel and sample: equal up to the order of
+    the float additions), also when the frame size is not a multiple of the tile size, and equal the sample-sharded
+    frame."""
+    from sightpy.backend import NativeScene
+    from sightpy.parallel import tile_ids
+    import scenes
+    import sightpy
+    nat = NativeScene(flatten_scene(scenes.cornell(sightpy, width=150, height=100)))     # 3 x 2 tiles, ragged edges
+    _, full, sf = nat.render(3, seed=9)
+    rays = 0
+    for r in range(4):
+        st = nat.render_tiles(tile_ids(150, 100, r, 4), 64, 0, 3, seed=9, clear=(r == 0))
+        rays += st["rays_total"]
+    _, tiles = nat.resolve(3)
+    assert rays == sf["rays_total"] and sf["rays_per_depth"][0] == 3 * 150 * 100
+    np.testing.assert_allclose(tiles, full, rtol=1e-4, atol=1e-6)
+    for r in range(3):                                       # sample shards of the same frame
+        nat.render_samples(r, r + 1, seed=9, clear=(r == 0))
+    _, samples = nat.resolve(3)
+    np.testing.assert_allclose(tiles, samples, rtol=1e-4, atol=1e-6)
+    # a 16-pixel tile size and a tile list in arbitrary order
+    ids = np.random.default_rng(0).permutation(nat.n_tiles(16)).astype(np.int32)
+    nat.render_tiles(ids, 16, 0, 3, seed=9, clear=True)
+    _, small = nat.resolve(3)
+    nat.close()
+    np.testing.assert_allclose(small, full, rtol=1e-4, atol=1e-6)
+    with pytest.raises(RuntimeError, match="tile"):
+        NativeScene(flatten_scene(scenes.cornell(sightpy, width=32, height=32))).render_tiles([7], 64, 0, 1)
+
+
+def test_exact_distance_ties_are_pinned():
+    """ray.py:131-146: every collider whose distance EQUALS the nearest one shades the ray and the colours add.  The
+    survey found no such tie in 2.4 M rays of the example scenes (jittered rays never land exactly on an edge), and
+    the CUDA path keeps ONE winner per ray — the tied collider that comes first in collider_list — instead of
+    shading all of them (documented in INTEGRATION.md).  This test constructs exact ties and pins both sides:
+      * two coincident emissive rectangles: the oracle (= the reference) returns the SUM of both colours, the device
+        the colour of the first;
+      * rays through the shared edge of two emissive triangles: same;
+    and the reported hit id is the lowest tied index on both sides."""
+    import sightpy as sp
+    from sightpy.backend import NativeScene
+    v, rgb = sp.vec3, sp.rgb
+    sc = sp.Scene(ambient_color=rgb(0.0, 0.0, 0.0))
+    sc.add_Camera(look_from=v(0.0, 0.0, 5.0), look_at=v(0.0, 0.0, 0.0), screen_width=8, screen_height=8)
+    a_col, b_col = (1.0, 0.25, 0.0), (0.0, 0.5, 2.0)
+    for col in (a_col, b_col):                               # coincident rectangles at z = 0 (colliders 0, 1)
+        sc.add(sp.Plane(material=sp.Emissive(color=rgb(*col)), center=v(-2.0, 0.0, 0.0), width=1.0, height=1.0,
+                        u_axis=v(1.0, 0, 0), v_axis=v(0, 1.0, 0)))
+    tri = sp.Primitive(center=v(2.0, 0.0, 0.0), material=sp.Emissive(color=rgb(*a_col)), max_ray_depth=1, shadow=False)
+    tri.collider_list.append(sp.Triangle_Collider(assigned_surface=tri, p1=v(1.0, -1.0, 0.0), p2=v(3.0, -1.0, 0.0), p3=v(1.0, 1.0, 0.0)))
+    tri2 = sp.Primitive(center=v(2.0, 0.0, 0.0), material=sp.Emissive(color=rgb(*b_col)), max_ray_depth=1, shadow=False)
+    tri2.collider_list.append(sp.Triangle_Collider(assigned_surface=tri2, p1=v(3.0, 1.0, 0.0), p2=v(1.0, 1.0, 0.0), p3=v(3.0, -1.0, 0.0)))
+    sc.add(tri); sc.add(tri2)                                # colliders 2, 3 share the edge (3,-1,0)-(1,1,0)
+    flat = flatten_scene(sc)
+    # axis-parallel rays: every quantity of both intersection routines is exact in float32 and float64
+    O = np.array([[-2.0, 0.0, 4.0], [-2.5, 0.25, 4.0], [2.0, 0.0, 4.0], [2.5, -0.5, 4.0], [1.5, 0.5, 4.0],
+                  [1.25, -0.5, 4.0], [2.75, 0.5, 4.0]], dtype=np.float32)
+    D = np.tile(np.array([[0.0, 0.0, -1.0]], dtype=np.float32), (len(O), 1))
+    nat = NativeScene(flat)
+    got = nat.trace(O, D, seed=0)
+    nat.close()
+    want = Oracle(flat, rng="philox", seed=0).trace(O, D)
+    both = np.add(a_col, b_col)
+    assert np.allclose(want["rgb"][:5], both)                # the reference semantics: tied colliders add
+    assert np.allclose(want["rgb"][5], a_col) and np.allclose(want["rgb"][6], b_col)
+    assert np.array_equal(want["hit_id"], [0, 0, 2, 2, 2, 2, 3])
+    assert np.array_equal(got["hit_id"], want["hit_id"])     # lowest tied index on both sides
+    assert np.allclose(got["t"], 4.0) and np.allclose(want["t"], 4.0)
+    assert np.allclose(got["rgb"][:5], a_col)                # the device shades the first tied collider only
+    assert np.allclose(got["rgb"][5], a_col) and np.allclose(got["rgb"][6], b_col)
+
+
+def test_frame_level_aovs_match_the_traced_primary_hits():
+    """per-pixel nearest collider, distance and ray-facing collider normal (the fields of the
+    reference's Hit record, ray.py:97-119) of the frame's primary rays — the same rays sp_camera_rays returns and the
+    same hits sp_trace reports for them."""
+    nat, flat = native_for("example3")
+    o, d = nat.camera_rays(sample=1, seed=3)
+    ref = nat.trace(o, d, seed=3, want_rgb=False)
+    aov = nat.aovs(sample=1, seed=3)
+    nat.close()
+    assert np.array_equal(aov["hit_id"].ravel(), ref["hit_id"])
+    assert np.array_equal(aov["t"].ravel(), ref["t"])
+    n, hit = aov["normal"].reshape(-1, 3).astype(np.float64), ref["hit_id"] >= 0
+    assert np.allclose(np.linalg.norm(n[hit], axis=1), 1.0, atol=1e-5) and not n[~hit].any()
+    assert ((n[hit] * d[hit]).sum(axis=1) <= 1e-6).all()              # turned towards the ray
+    want = Oracle(flat, rng="philox", seed=3).trace(o, d)
+    assert np.array_equal(aov["hit_id"].ravel(), want["hit_id"])
+
+
+def test_scene_edits_between_renders_are_picked_up_without_a_rebuild():
+    """The reference deep-copies the scene on every render (scene.py:85), so in-place edits are rendered.  Here the
+    committed device copy is updated in place: a camera move goes through sp_scene_update_camera (no commit), a
+    material / primitive edit re-commits the changed tables on the same handle; either way the frame equals the
+    one a freshly built scene gives, and the queue-occupancy estimates survive (no second probe chunk)."""
+    import scenes
+    import sightpy as sp
+    sc = scenes.cornell(sp, width=64, height=48)
+    sc.seed = 5
+    first = np.asarray(sc.render(2))
+    native = sc._backend()
+    assert native.update(flatten_scene(sc)) == "unchanged"
+    sc.camera.look_from = sp.vec3(250.0, 300.0, 790.0)               # moved camera: attributes the flattening reads
+    sc.camera.__init__(look_from=sc.camera.look_from, look_at=sp.vec3(278, 278, 0), screen_width=64, screen_height=48,
+                       field_of_view=40)
+    assert native.update(flatten_scene(sc)) == "camera"
+    moved = np.asarray(sc.render(2))
+    assert sc._backend() is native and not np.array_equal(moved, first)
+    fresh = scenes.cornell(sp, width=64, height=48)
+    fresh.camera.__init__(look_from=sp.vec3(250.0, 300.0, 790.0), look_at=sp.vec3(278, 278, 0), screen_width=64,
+                          screen_height=48, field_of_view=40)
+    fresh.seed = 5
+    assert np.abs(np.asarray(fresh.render(2)).astype(int) - moved.astype(int)).max() <= 1
+    sc.scene_primitives[2].material.diff_texture.color = sp.rgb(0.1, 0.2, 0.9)      # repaint a wall in place
+    assert native.update(flatten_scene(sc)) == "commit"
+    painted = np.asarray(sc.render(2))
+    assert sc._backend() is native and not np.array_equal(painted, moved)
+    assert sc.last_stats["chunks"] == 1                               # occupancy estimates kept: no probe + rest split
+    sc.seed = None                                                    # default: a new sample set per render
+    a, b = np.asarray(sc.render(2)), np.asarray(sc.render(2))
+    assert not np.array_equal(a, b)
+
+
+def test_full_stress_scene_bvh_agrees_with_exhaustive_loop_on_sampled_pixels():
+    """BASELINE.json config 5 at its full size (4096 spheres + 2048 triangles + ground = 6145 colliders, 3840x2160):
+    4096 randomly chosen camera rays traced through the BVH and through the exhaustive multi-chunk loop (option
+    "bvh" = 0) find the same hits and carry the same radiance (same Philox keys).  The float64 oracle needs minutes
+    per hundred pixels of this scene (6145 numpy intersect calls per recursion level), so it checks the *primary*
+    nearest-hit ids and distances only (Oracle.nearest); the oracle's full recursion is compared on the scaled-down
+    scene of test_bvh_and_exhaustive_loop_agree."""
+    import scenes
+    import sightpy
+    from sightpy.backend import NativeScene
+    flat = flatten_scene(scenes.stress(sightpy, width=3840, height=2160))
+    assert len(flat.colliders) == 6145
+    nat = NativeScene(flat)
+    o, d = nat.camera_rays(sample=0, seed=2)
+    pick = np.random.default_rng(1).choice(len(o), size=4096, replace=False)
+    o, d = o[pick], d[pick]
+    with_bvh = nat.trace(o, d, seed=2)
+    nat.set_option("bvh", 0)
+    brute = nat.trace(o, d, seed=2)
+    nat.close()
+    check_count("hit_mismatch/full_stress_bvh", int(np.sum(with_bvh["hit_id"] != brute["hit_id"])), len(pick), 0.002)
+    same = with_bvh["hit_id"] == brute["hit_id"]
+    np.testing.assert_allclose(with_bvh["t"][same], brute["t"][same], rtol=1e-5, atol=1e-5)
+    err = np.abs(with_bvh["rgb"] - brute["rgb"]).max(axis=1)[same]
+    check_count("rays_over_tol/full_stress_bvh", int(np.sum(err > 1e-3 * (1.0 + np.abs(brute["rgb"]).max(axis=1)[same]))), len(err), 0.02)
+    orc = Oracle(flat, rng="philox", seed=2)
+    sub = slice(0, 4096)
+    hit_id, t = orc.nearest(o[sub], d[sub])
+    check_count("hit_mismatch/full_stress_oracle_primary", int(np.sum(with_bvh["hit_id"][sub] != hit_id)), 4096, 0.01)
+    ok = (with_bvh["hit_id"][sub] == hit_id) & np.isfinite(t)
+    np.testing.assert_allclose(with_bvh["t"][sub][ok], t[ok], rtol=2e-5, atol=1e-4)

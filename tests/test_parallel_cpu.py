@@ -26,13 +26,23 @@ def test_sample_range_partitions_every_spp():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_interleaved_tiles_partition_the_frame():
+    from sightpy.parallel import tile_ids
+    for (w, h) in ((1920, 1080), (100, 100), (64, 64), (65, 1)):
+        n = -(-w // 64) * -(-h // 64)
+        for world in (1, 2, 3, 8):
+            parts = [tile_ids(w, h, r, world) for r in range(world)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, spp, out_dir):
+def _worker(rank, world, port, spp, shard, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     for p in (REPO, REPO / "python-raytracer_b200", REPO / "tests"):
         sys.path.insert(0, str(p))
@@ -74,6 +84,18 @@ def _worker(rank, world, port, spp, out_dir):
                 view[pix_begin:pix_end, :3] += torch.from_numpy(rgb.astype(np.float32))
             return dict(rays_total=orc.rays_total)
 
+        def render_tiles(self, tile_ids, tile_size, begin, end, seed=0, clear=True):
+            if clear:
+                self.acc.zero_()
+            tiles_x = -(-self.width // tile_size)
+            total = 0
+            for t in tile_ids:                       # a tile = rows of contiguous pixels clipped to the frame
+                ty, tx = divmod(int(t), tiles_x)
+                for y in range(ty * tile_size, min((ty + 1) * tile_size, self.height)):
+                    x0, x1 = tx * tile_size, min((tx + 1) * tile_size, self.width)
+                    total += self.render_region(y * self.width + x0, y * self.width + x1, begin, end, seed, clear=False)["rays_total"]
+            return dict(rays_total=total)
+
         def accum_tensor(self):
             return self.acc
 
@@ -81,19 +103,22 @@ def _worker(rank, world, port, spp, out_dir):
             lin = (self.acc.view(-1, 4)[:, :3].numpy().astype(np.float64) / spp_total).T
             return tonemap_u8(lin, self.height, self.width), lin.astype(np.float32).reshape(3, self.height, self.width)
 
+    import sightpy.parallel as par
+    par.TILE = 4                                     # a 12 x 10 frame has 3 x 3 tiles of 4 x 4 pixels
     scene = OracleScene()
-    srgb, lin, stats = render_frame(scene, spp, seed=4, want_linear=True)
+    srgb, lin, stats = render_frame(scene, spp, seed=4, want_linear=True, shard=shard)
     np.savez(Path(out_dir) / f"rank{rank}.npz", srgb=srgb, lin=lin, rays=stats["rays_total"])
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("spp", [3, 1])          # 3: sample-range shards; 1 (< world size): pixel-band shards
-def test_two_rank_gloo_frame_equals_single_process(tmp_path, spp):
+# auto: 3 spp -> sample-range shards, 1 spp (< world size) -> interleaved tiles; tiles can also be asked for
+@pytest.mark.parametrize("spp,shard", [(3, "auto"), (1, "auto"), (3, "tiles")])
+def test_two_rank_gloo_frame_equals_single_process(tmp_path, spp, shard):
     import torch.multiprocessing as mp
     world = 2
-    mp.start_processes(_worker, args=(world, _free_port(), spp, str(tmp_path)), nprocs=world, join=True,
+    mp.start_processes(_worker, args=(world, _free_port(), spp, shard, str(tmp_path)), nprocs=world, join=True,
                        start_method="spawn")
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
 
