@@ -419,7 +419,7 @@ def run_native(args, emit=print):
         e2e_s = allmax(e2e_s)
         h2d = sum(getattr(flat, k).nbytes for k in ("materials", "primitives", "colliders", "lights", "importance",
                                                       "shadow_colliders", "media", "ambient")) + flat.camera.nbytes \
-            + sum(t.u8.nbytes for t in flat.textures)
+            + sum(t.source_u8.nbytes for t in flat.textures)
         e2e = {"value": allsum(e2e_rays) / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(width * height * 3), "steps": n_e2e, "s_per_frame": e2e_s / n_e2e,
                "note": "textures named by a stable key stay resident on the device after their first upload"}

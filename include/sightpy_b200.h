@@ -128,11 +128,19 @@ int  sp_abi_version(void);
 /* sizeof() of the ABI structs, so that a binding can verify its own layout. */
 int  sp_abi_sizes(int32_t out[6]);  /* camera, material, primitive, collider, light, stats */
 int  sp_init(int device);           /* bind the calling process to a CUDA device (idempotent)     */
+/* Bind the process to several GPUs of one node.  device_ids[0] becomes the default device (new scenes; it gathers
+ * and resolves the frames of sp_render_group) and is given peer access to the others. */
+int  sp_init_devices(int n, const int* device_ids);
+int  sp_default_device(void);       /* -1 before sp_init                                           */
 int  sp_device_count(void);
 const char* sp_last_error(void);
 void sp_shutdown(void);
+/* Return idle pooled device memory (wavefront queues of destroyed or re-committed scenes, unreferenced cached
+ * textures) to the driver.  On its own the library keeps at most 64 GB of idle buffers per device. */
+void sp_trim(void);
 
-int  sp_scene_create(sp_scene** out);
+int  sp_scene_create(sp_scene** out);               /* on the default device                       */
+int  sp_scene_create_on(sp_scene** out, int device);  /* on one of the devices of sp_init_devices    */
 void sp_scene_destroy(sp_scene*);
 
 /* ---- scene description (Scene.__init__/add/add_*Light/add_Background, scene.py:29-69) ---------- */
@@ -145,6 +153,14 @@ int  sp_scene_add_texture(sp_scene*, const uint8_t* rgb_hw3, int H, int W, int d
  * re-describing a scene per animation frame (animation.py:27-31) uploads each image once. */
 int  sp_scene_add_texture_keyed(sp_scene*, uint64_t key, const uint8_t* rgb_hw3, int H, int W, int decode,
                                 int* tex_id);
+/* Same for a cross-layout cube map (3 x 4 blocks of square faces) that the scene wants blurred
+ * (Scene.add_Background(..., blur=...), skybox.py:46-49): the library blurs the texels on the device exactly as
+ * blur_skybox does with Pillow on the host (blur_background.py:17-132: per face a canvas with its four rotated
+ * neighbours, bytes re-quantised, three fixed-point box passes per axis), byte for byte. */
+int  sp_scene_add_texture_blurred(sp_scene*, uint64_t key, const uint8_t* rgb_hw3, int H, int W, int decode,
+                                  double cube_blur, int* tex_id);
+/* Texels of texture tex_id of a committed scene as the device holds them (after any blur), H*W*3 bytes. */
+int  sp_scene_read_texture(sp_scene*, int tex_id, uint8_t* out_rgb_hw3);
 int  sp_scene_set_materials(sp_scene*, const sp_material*, int n);
 int  sp_scene_set_primitives(sp_scene*, const sp_primitive*, int n);
 int  sp_scene_set_colliders(sp_scene*, const sp_collider*, int n);
@@ -193,6 +209,14 @@ int  sp_resolve(sp_scene*, int spp_total, float* out_linear_rgb, uint8_t* out_sr
 /* Enqueue this scene's work on a caller-owned CUDA stream (a cudaStream_t, e.g. the stream an NCCL
  * reduce of sp_accum_device_ptr is ordered on); use_it == 0 returns to the library's own stream. */
 int  sp_scene_set_stream(sp_scene*, void* cuda_stream, int use_it);
+
+/* One frame on several GPUs without a launcher — what the reference's render() does with its process pool
+ * (scene.py:98-116).  scenes[0..n) are committed replicas of one scene on n different devices; one host thread per
+ * device renders its shard (shard_mode 0: contiguous sample ranges; 1, and whenever spp < n: interleaved 64x64
+ * tiles), then scenes[0]'s device adds the other frames to its own — read over NVLink through peer access — and
+ * resolves as sp_render does.  stats are summed over the devices (times: the slowest). */
+int  sp_render_group(sp_scene** scenes, int n, int spp, uint64_t seed, int shard_mode,
+                     float* out_linear_rgb, uint8_t* out_srgb8, sp_stats* stats);
 
 /* sp_trace == get_raycolor(Ray(o, d, depth 0, scene.n), scene) (ray.py:122-148) on caller rays:
  * n rays, origins/directions as n x 3 interleaved floats.  Outputs (each nullable): linear

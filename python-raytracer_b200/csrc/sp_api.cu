@@ -15,7 +15,7 @@
 
 // ---- error handling -------------------------------------------------------------------------------
 static thread_local std::string g_error;
-static int g_device = -1;
+static int g_device = -1;          // default device of new scenes (sp_init / first of sp_init_devices)
 
 static int fail(const char* fmt, ...) {
     char buf[1024];
@@ -32,34 +32,81 @@ static int fail(const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail("%s: %s", #expr, cudaGetErrorString(e__));            \
     } while (0)
 
-// Device allocations are recycled through a process-wide free list keyed by size instead of going back
-// to the driver when a scene is destroyed: Scene.render after an edit builds a new sp_scene with the same
-// buffer sizes, and cudaMalloc / cudaFree of the multi-GB wavefront queues (plus the device-wide
-// synchronisation every cudaFree implies) would otherwise cost tens of milliseconds to seconds per frame.
-// sp_shutdown returns everything to the driver.
+// ---- per-device state ---------------------------------------------------------------------------------------------
+// A process may drive several GPUs (sp_init_devices + sp_render_group: one host thread per device).  Everything the
+// scenes of a device share lives in that device's context; the calling thread names the device it works on in
+// t_device (set by the SP_ENTER guard of every entry point, which also makes it the current CUDA device and takes the
+// device's lock, so scenes of different devices render concurrently while calls on one device serialise).
+//
+// Device allocations are recycled through a per-device free list keyed by size instead of going back to the driver when
+// a scene is destroyed: Scene.render after an edit re-commits with the same buffer sizes, and cudaMalloc / cudaFree of
+// the multi-GB wavefront queues (plus the device-wide synchronisation every cudaFree implies) would otherwise cost tens
+// of milliseconds to seconds per frame.  When a scene is destroyed, idle buffers beyond kPoolIdleLimit are returned
+// to the driver (largest first); sp_trim / sp_shutdown return everything.
 #include <map>
 #include <mutex>
-// One lock for everything the scenes of a process share (buffer / stream / event pools, texture cache):
-// every exported entry point that can touch them takes it, so scenes may be driven from different threads
-// (ctypes releases the GIL during a call); rendering calls of different scenes therefore serialise.
-static std::recursive_mutex g_lock;
-#define SP_LOCK std::lock_guard<std::recursive_mutex> lock__(g_lock)
-static std::multimap<size_t, void*> g_pool;
+#include <thread>
+#define SP_MAX_DEVICES 16
+struct CachedTexture { uint64_t key; int H, W, decode; uint32_t* d; size_t bytes; int refs; uint64_t last_use; };
+struct DeviceCtx {
+    std::recursive_mutex lock;
+    bool ready = false;
+    std::multimap<size_t, void*> pool;
+    size_t pool_bytes = 0;
+    // Device-resident textures shared between scenes.  A caller that re-describes a scene every frame
+    // (animation.py: update_scene + render) names each image with a stable non-zero key; the packed texels
+    // of a key are uploaded once and reused by every later scene of the process (SURVEY §8f "GPU-resident
+    // scene reuse": example1's 4096x3072 sky box costs 28 ms to pack and upload, the frame itself 0.6 ms).
+    std::vector<CachedTexture> tex_cache;
+    uint64_t tex_clock = 0;
+    std::vector<cudaStream_t> stream_pool;
+    std::vector<cudaEvent_t> event_pool;
+};
+static DeviceCtx g_ctx[SP_MAX_DEVICES];
+static thread_local int t_device = -1;
+static DeviceCtx& ctx() { return g_ctx[t_device >= 0 ? t_device : 0]; }
+static const size_t kPoolIdleLimit = (size_t)64 << 30;         // idle pooled bytes kept per device (one full-size queue set)
+static const size_t kTexCacheLimit = (size_t)8 << 30;          // bytes kept alive for idle (unreferenced) textures
+
+struct DeviceGuard {                     // SP_ENTER(device): this thread works on `device` for the rest of the scope
+    int prev;
+    std::unique_lock<std::recursive_mutex> lk;
+    explicit DeviceGuard(int device) : prev(t_device), lk(g_ctx[device >= 0 && device < SP_MAX_DEVICES ? device : 0].lock) {
+        t_device = device >= 0 && device < SP_MAX_DEVICES ? device : 0;
+        cudaSetDevice(t_device);
+    }
+    ~DeviceGuard() { t_device = prev; if (prev >= 0) cudaSetDevice(prev); }
+};
+#define SP_ENTER(device) DeviceGuard guard__(device)
 
 static void pool_flush() {
-    for (auto& b : g_pool) cudaFree(b.second);
-    g_pool.clear();
+    DeviceCtx& c = ctx();
+    for (auto& b : c.pool) cudaFree(b.second);
+    c.pool.clear();
+    c.pool_bytes = 0;
+}
+
+static void pool_trim(size_t keep) {     // return the largest idle buffers to the driver until at most `keep` bytes idle
+    DeviceCtx& c = ctx();
+    while (c.pool_bytes > keep && !c.pool.empty()) {
+        auto it = std::prev(c.pool.end());
+        cudaFree(it->second);
+        c.pool_bytes -= it->first;
+        c.pool.erase(it);
+    }
 }
 
 static cudaError_t pool_get(void** out, size_t bytes) {
-    auto it = g_pool.find(bytes);
-    if (it != g_pool.end()) {
+    DeviceCtx& c = ctx();
+    auto it = c.pool.find(bytes);
+    if (it != c.pool.end()) {
         *out = it->second;
-        g_pool.erase(it);
+        c.pool_bytes -= it->first;
+        c.pool.erase(it);
         return cudaSuccess;
     }
     cudaError_t e = cudaMalloc(out, bytes);
-    if (e != cudaSuccess && !g_pool.empty()) {          // make room and retry once
+    if (e != cudaSuccess && !c.pool.empty()) {          // make room and retry once
         cudaGetLastError();
         pool_flush();
         e = cudaMalloc(out, bytes);
@@ -70,10 +117,12 @@ static cudaError_t pool_get(void** out, size_t bytes) {
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    int dev = -1;                        // the device whose pool the buffer came from
     cudaError_t alloc(size_t count) {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
+        dev = t_device >= 0 ? t_device : 0;
         return pool_get(reinterpret_cast<void**>(&p), count * sizeof(T));
     }
     cudaError_t upload(const std::vector<T>& h) {
@@ -81,38 +130,38 @@ template <typename T> struct DevBuf {
         if (e != cudaSuccess || h.empty()) return e;
         return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
     }
-    void release() { if (p) g_pool.emplace(n * sizeof(T), p); p = nullptr; n = 0; }
+    void release() {
+        if (p) {
+            DeviceCtx& c = g_ctx[dev >= 0 ? dev : 0];
+            c.pool.emplace(n * sizeof(T), p);
+            c.pool_bytes += n * sizeof(T);
+        }
+        p = nullptr; n = 0;
+    }
 };
 
-struct HostTexture { int H, W, decode; uint64_t key; std::vector<uint32_t> texels; };
-
-// Device-resident textures shared between scenes.  A caller that re-describes a scene every frame
-// (animation.py: update_scene + render) names each image with a stable non-zero key; the packed texels
-// of a key are uploaded once and reused by every later scene of the process (SURVEY §8f "GPU-resident
-// scene reuse": example1's 4096x3072 sky box costs 28 ms to pack and upload, the frame itself 0.6 ms).
-struct CachedTexture { uint64_t key; int H, W, decode; uint32_t* d; size_t bytes; int refs; uint64_t last_use; };
-static std::vector<CachedTexture> g_tex_cache;
-static uint64_t g_tex_clock = 0;
-static const size_t kTexCacheLimit = (size_t)8 << 30;          // bytes kept alive for idle (unreferenced) textures
+struct HostTexture { int H, W, decode; uint64_t key; std::vector<uint32_t> texels; double cube_blur = 0.0; };
 
 static int tex_cache_find(uint64_t key, int H, int W, int decode) {
-    for (size_t i = 0; i < g_tex_cache.size(); ++i)
-        if (g_tex_cache[i].key == key && g_tex_cache[i].H == H && g_tex_cache[i].W == W && g_tex_cache[i].decode == decode)
+    auto& tc = ctx().tex_cache;
+    for (size_t i = 0; i < tc.size(); ++i)
+        if (tc[i].key == key && tc[i].H == H && tc[i].W == W && tc[i].decode == decode)
             return (int)i;
     return -1;
 }
 
 static void tex_cache_trim() {
+    auto& tc = ctx().tex_cache;
     size_t idle = 0;
-    for (auto& t : g_tex_cache) if (t.refs == 0) idle += t.bytes;
+    for (auto& t : tc) if (t.refs == 0) idle += t.bytes;
     while (idle > kTexCacheLimit) {
         int victim = -1;
-        for (size_t i = 0; i < g_tex_cache.size(); ++i)
-            if (g_tex_cache[i].refs == 0 && (victim < 0 || g_tex_cache[i].last_use < g_tex_cache[(size_t)victim].last_use)) victim = (int)i;
+        for (size_t i = 0; i < tc.size(); ++i)
+            if (tc[i].refs == 0 && (victim < 0 || tc[i].last_use < tc[(size_t)victim].last_use)) victim = (int)i;
         if (victim < 0) break;
-        idle -= g_tex_cache[(size_t)victim].bytes;
-        cudaFree(g_tex_cache[(size_t)victim].d);
-        g_tex_cache.erase(g_tex_cache.begin() + victim);
+        idle -= tc[(size_t)victim].bytes;
+        cudaFree(tc[(size_t)victim].d);
+        tc.erase(tc.begin() + victim);
     }
 }
 
@@ -130,20 +179,20 @@ struct QueueSet {
     void release() { q0.release(); q1.release(); q2.release(); n = 0; }
 };
 
-// streams and events are recycled the same way
-static std::vector<cudaStream_t> g_stream_pool;
-static std::vector<cudaEvent_t> g_event_pool;
-
+// streams and events are recycled the same way (per device)
 struct ScopedEvent {                     // a pooled event for the duration of one call
     cudaEvent_t e = nullptr;
-    ScopedEvent() {
-        if (!g_event_pool.empty()) { e = g_event_pool.back(); g_event_pool.pop_back(); }
+    int dev;
+    ScopedEvent() : dev(t_device >= 0 ? t_device : 0) {
+        auto& pool = g_ctx[dev].event_pool;
+        if (!pool.empty()) { e = pool.back(); pool.pop_back(); }
         else if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
     }
-    ~ScopedEvent() { if (e) g_event_pool.push_back(e); }
+    ~ScopedEvent() { if (e) g_ctx[dev].event_pool.push_back(e); }
 };
 
 struct sp_scene {
+    int device = 0;                     // the CUDA device this scene lives on
     // ---- host description ---------------------------------------------------------------------
     double ambient[3] = {0, 0, 0};
     std::vector<double> media_re, media_im;
@@ -195,10 +244,13 @@ struct sp_scene {
     int grid0 = 0, grid_q = 0;                   // CTAs of level-0 / queue-fed launches of sp_level_kernel
     uint32_t material_set = 0;                   // compiled kernel variant (sp_pick_material_set)
 
-    ~sp_scene() { release_device(); release_textures(); }
+    ~sp_scene() {
+        release_device(); release_textures();
+        pool_trim(kPoolIdleLimit);           // what a destroyed scene leaves idle beyond the limit goes back to the driver
+    }
     void release_textures() {                    // a scene holds one reference per shared texture for its whole life
         for (uint64_t k : cached_tex_keys)
-            for (auto& t : g_tex_cache) if (t.key == k && t.refs > 0) { t.refs--; break; }
+            for (auto& t : g_ctx[device].tex_cache) if (t.key == k && t.refs > 0) { t.refs--; break; }
         cached_tex_keys.clear();
         tex_cache_trim();
     }
@@ -213,9 +265,9 @@ struct sp_scene {
         slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
-        for (auto e : events) g_event_pool.push_back(e);
+        for (auto e : events) g_ctx[device].event_pool.push_back(e);
         events.clear();
-        if (own_stream) { cudaStreamSynchronize(own_stream); g_stream_pool.push_back(own_stream); }
+        if (own_stream) { cudaStreamSynchronize(own_stream); g_ctx[device].stream_pool.push_back(own_stream); }
         own_stream = nullptr;
         stream = nullptr;
         d_lin.release(); d_u8.release();
@@ -597,6 +649,23 @@ static BuiltBvh build_bvh(const std::vector<sp_collider>& cols, const std::vecto
     return out;
 }
 
+// Texels of a cross-layout cube map that the scene wants blurred (add_Background(..., blur=...), skybox.py:46-49): the
+// device copy `d` (H x W packed texels) is replaced by its blurred version (sp_imaging.cu).
+static int blur_texture_in_place(uint32_t* d, int H, int W, double blur) {
+    const int N = H / 3;
+    if (N < 1 || 4 * N > W) return fail("cube-map blur: a %dx%d image is not a 3 x 4 cross of square faces", W, H);
+    DevBuf<uint32_t> out, tmp0, tmp1;
+    cudaError_t e = out.alloc((size_t)H * W);
+    if (e == cudaSuccess) e = tmp0.alloc((size_t)9 * N * N);
+    if (e == cudaSuccess) e = tmp1.alloc((size_t)9 * N * N);
+    if (e == cudaSuccess) e = sp_blur_cube_cross(d, out.p, tmp0.p, tmp1.p, H, W, (float)blur, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, out.p, (size_t)H * W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    out.release(); tmp0.release(); tmp1.release();
+    if (e != cudaSuccess) return fail("cube-map blur: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // Fingerprint of everything that decides how many records a primary ray puts into the queues *structurally*: frame
 // size, table sizes, material kinds / fan sizes / depth limits, collider types.  A scene that is re-described with
 // the same shape (an animation frame: moved colliders, another camera pose) keeps the queue-occupancy estimates of
@@ -615,8 +684,8 @@ static uint64_t shape_signature(const sp_scene* s) {
 
 // Launch geometry of the level kernels for this scene.
 static int pick_kernels(sp_scene* s) {
-    s->grid0 = sp_level_grid(g_device, s->d, s->material_set, true);
-    s->grid_q = sp_level_grid(g_device, s->d, s->material_set, false);
+    s->grid0 = sp_level_grid(s->device, s->d, s->material_set, true);
+    s->grid_q = sp_level_grid(s->device, s->d, s->material_set, false);
     return 0;
 }
 
@@ -642,15 +711,15 @@ int sp_device_count(void) {
     return n;
 }
 
-int sp_init(int device) {
-    SP_LOCK;
+static int init_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
         return fail("no CUDA device available (%s); sightpy-b200 has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    if (device < 0 || device >= n) return fail("device %d out of range (0..%d)", device, n - 1);
-    CUDA_TRY(cudaSetDevice(device));
+    if (device < 0 || device >= n || device >= SP_MAX_DEVICES) return fail("device %d out of range (0..%d)", device, std::min(n, SP_MAX_DEVICES) - 1);
+    SP_ENTER(device);
+    if (g_ctx[device].ready) return 0;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -663,32 +732,91 @@ int sp_init(int device) {
         linear[b] = (float)(x <= 0.03928 ? x / 12.92 : std::pow((x + 0.055) / 1.055, 2.4));
     }
     CUDA_TRY(sp_upload_decode_tables(plain, linear));
-    g_device = device;
+    g_ctx[device].ready = true;
     return 0;
+}
+
+int sp_init(int device) {
+    if (int rc = init_device(device)) return rc;
+    g_device = device;
+    cudaSetDevice(device);
+    return 0;
+}
+
+// Bind the process to several GPUs of the node: device_ids[0] becomes the default device (new scenes, the one that
+// gathers and resolves group frames) and is given peer access to the others, so that it can read their frames over
+// NVLink (sp_render_group).
+int sp_init_devices(int n, const int* device_ids) {
+    if (n < 1 || !device_ids) return fail("sp_init_devices: need at least one device id");
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return fail("sp_init_devices: device %d listed twice", device_ids[i]);
+    for (int i = 0; i < n; ++i)
+        if (int rc = init_device(device_ids[i])) return rc;
+    g_device = device_ids[0];
+    SP_ENTER(g_device);
+    for (int i = 1; i < n; ++i) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, g_device, device_ids[i]) == cudaSuccess && can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[i], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess(%d): %s", device_ids[i], cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    return 0;
+}
+
+int sp_default_device(void) { return g_device; }
+
+static void release_device_ctx(int device) {
+    SP_ENTER(device);
+    DeviceCtx& c = g_ctx[device];
+    if (!c.ready) return;
+    cudaDeviceSynchronize();
+    for (auto& t : c.tex_cache) cudaFree(t.d);
+    c.tex_cache.clear();
+    pool_flush();
+    for (auto st : c.stream_pool) cudaStreamDestroy(st);
+    c.stream_pool.clear();
+    for (auto e : c.event_pool) cudaEventDestroy(e);
+    c.event_pool.clear();
+    c.ready = false;
 }
 
 void sp_shutdown(void) {
-    SP_LOCK;
-    if (g_device >= 0) cudaDeviceSynchronize();
-    for (auto& t : g_tex_cache) cudaFree(t.d);
-    g_tex_cache.clear();
-    pool_flush();
-    for (auto st : g_stream_pool) cudaStreamDestroy(st);
-    g_stream_pool.clear();
-    for (auto e : g_event_pool) cudaEventDestroy(e);
-    g_event_pool.clear();
+    for (int d = 0; d < SP_MAX_DEVICES; ++d) release_device_ctx(d);
     g_device = -1;
 }
 
-int sp_scene_create(sp_scene** out) {
+// Return idle pooled device memory (wavefront queues of destroyed / re-committed scenes, unreferenced cached
+// textures) to the driver, on every bound device.
+void sp_trim(void) {
+    for (int d = 0; d < SP_MAX_DEVICES; ++d) {
+        if (!g_ctx[d].ready) continue;
+        SP_ENTER(d);
+        pool_flush();
+        auto& tc = g_ctx[d].tex_cache;
+        for (size_t i = tc.size(); i-- > 0;)
+            if (tc[i].refs == 0) { cudaFree(tc[i].d); tc.erase(tc.begin() + (long)i); }
+    }
+}
+
+int sp_scene_create_on(sp_scene** out, int device) {
     if (!out) return fail("sp_scene_create: null output pointer");
-    if (g_device < 0) return fail("sp_scene_create: call sp_init first");
+    if (device < 0 || device >= SP_MAX_DEVICES || !g_ctx[device].ready) return fail("sp_scene_create: device %d is not initialised (sp_init / sp_init_devices)", device);
     *out = new sp_scene();
+    (*out)->device = device;
     return 0;
 }
 
+int sp_scene_create(sp_scene** out) {
+    if (g_device < 0) return fail("sp_scene_create: call sp_init first");
+    return sp_scene_create_on(out, g_device);
+}
+
 void sp_scene_destroy(sp_scene* s) {
-    SP_LOCK;
+    if (!s) return;
+    SP_ENTER(s->device);
     delete s;
 }
 
@@ -717,7 +845,7 @@ int sp_scene_set_camera(sp_scene* s, const sp_camera* cam) {
 }
 
 int sp_scene_update_camera(sp_scene* s, const sp_camera* cam) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     if (!s || !cam) return fail("sp_scene_update_camera: invalid arguments");
     if (!s->committed || !s->has_camera) return fail("sp_scene_update_camera: scene not committed with a camera");
     if (cam->width != s->cam.width || cam->height != s->cam.height)
@@ -732,22 +860,26 @@ int sp_scene_update_camera(sp_scene* s, const sp_camera* cam) {
 }
 
 int sp_scene_clear_textures(sp_scene* s) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     NEED_SCENE(s);
     s->textures.clear();
     return 0;
 }
 
-int sp_scene_add_texture_keyed(sp_scene* s, uint64_t key, const uint8_t* rgb, int H, int W, int decode, int* tex_id) {
-    SP_LOCK;
+int sp_scene_add_texture_blurred(sp_scene* s, uint64_t key, const uint8_t* rgb, int H, int W, int decode, double cube_blur,
+                                 int* tex_id) {
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     NEED_SCENE(s);
     if (!rgb || H < 1 || W < 1) return fail("sp_scene_add_texture: invalid image");
     if (decode != SP_DECODE_PLAIN && decode != SP_DECODE_LINEAR) return fail("sp_scene_add_texture: unknown decode %d", decode);
+    if (!(cube_blur >= 0.0)) return fail("sp_scene_add_texture_blurred: blur must be >= 0");
+    if (cube_blur > 0.0 && (H / 3 < 1 || 4 * (H / 3) > W))
+        return fail("sp_scene_add_texture_blurred: a %dx%d image is not a 3 x 4 cross of square faces", W, H);
     HostTexture t;
-    t.H = H; t.W = W; t.decode = decode; t.key = key;
+    t.H = H; t.W = W; t.decode = decode; t.key = key; t.cube_blur = cube_blur;
     const int cached = key != 0 ? tex_cache_find(key, H, W, decode) : -1;
     if (cached >= 0 && !s->holds_texture(key)) {                       // resident: pin it for the life of this scene
-        g_tex_cache[(size_t)cached].refs++;
+        ctx().tex_cache[(size_t)cached].refs++;
         s->cached_tex_keys.push_back(key);
     }
     if (cached < 0) {                                                  // not resident yet: pack RGB8 -> one word per texel
@@ -760,8 +892,12 @@ int sp_scene_add_texture_keyed(sp_scene* s, uint64_t key, const uint8_t* rgb, in
     return 0;
 }
 
+int sp_scene_add_texture_keyed(sp_scene* s, uint64_t key, const uint8_t* rgb, int H, int W, int decode, int* tex_id) {
+    return sp_scene_add_texture_blurred(s, key, rgb, H, W, decode, 0.0, tex_id);
+}
+
 int sp_scene_add_texture(sp_scene* s, const uint8_t* rgb, int H, int W, int decode, int* tex_id) {
-    return sp_scene_add_texture_keyed(s, 0, rgb, H, W, decode, tex_id);
+    return sp_scene_add_texture_blurred(s, 0, rgb, H, W, decode, 0.0, tex_id);
 }
 
 int sp_scene_set_materials(sp_scene* s, const sp_material* m, int n) {
@@ -810,9 +946,9 @@ int sp_scene_set_shadow_colliders(sp_scene* s, const int32_t* ids, int n) {
 }
 
 int sp_scene_commit(sp_scene* s) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     if (!s) return fail("sp_scene_commit: null scene");
-    if (g_device < 0) return fail("sp_scene_commit: call sp_init first");
+    if (!g_ctx[s->device].ready) return fail("sp_scene_commit: call sp_init first");
     if (s->media_re.empty()) return fail("sp_scene_commit: sp_scene_set_globals was not called");
     const int n_tex = (int)s->textures.size(), n_mat = (int)s->mats.size(), n_prim = (int)s->prims.size();
     const int n_col = (int)s->cols.size(), n_media = (int)s->media_re.size() / 3;
@@ -852,8 +988,7 @@ int sp_scene_commit(sp_scene* s) {
     for (int id : s->shadow_ids) if (id < 0 || id >= n_col) return fail("shadow list: collider %d out of range", id);
 
     s->release_device();
-    CUDA_TRY(cudaSetDevice(g_device));
-    if (!g_stream_pool.empty()) { s->own_stream = g_stream_pool.back(); g_stream_pool.pop_back(); }
+    if (!ctx().stream_pool.empty()) { s->own_stream = ctx().stream_pool.back(); ctx().stream_pool.pop_back(); }
     else CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     s->stream = s->user_stream_set ? s->user_stream : s->own_stream;
     DScene& d = s->d;
@@ -959,16 +1094,26 @@ int sp_scene_commit(sp_scene* s) {
             if (ci < 0) {
                 if (ht.texels.empty()) return fail("texture %d: key %llu left the cache between description and commit", i, (unsigned long long)ht.key);
                 CachedTexture ct{ht.key, ht.H, ht.W, ht.decode, nullptr, ht.texels.size() * sizeof(uint32_t), 0, 0};
-                CUDA_TRY(cudaMalloc(&ct.d, ct.bytes));
+                cudaError_t em = cudaMalloc(&ct.d, ct.bytes);
+                if (em != cudaSuccess && !ctx().pool.empty()) {          // make room (idle pooled buffers) and retry once
+                    cudaGetLastError();
+                    pool_flush();
+                    em = cudaMalloc(&ct.d, ct.bytes);
+                }
+                CUDA_TRY(em);
                 CUDA_TRY(cudaMemcpy(ct.d, ht.texels.data(), ct.bytes, cudaMemcpyHostToDevice));
-                g_tex_cache.push_back(ct);
-                ci = (int)g_tex_cache.size() - 1;
+                if (ht.cube_blur > 0.0)
+                    if (int rcb = blur_texture_in_place(ct.d, ht.H, ht.W, ht.cube_blur)) { cudaFree(ct.d); return rcb; }
+                ctx().tex_cache.push_back(ct);
+                ci = (int)ctx().tex_cache.size() - 1;
             }
-            if (!s->holds_texture(ht.key)) { g_tex_cache[(size_t)ci].refs++; s->cached_tex_keys.push_back(ht.key); }
-            g_tex_cache[(size_t)ci].last_use = ++g_tex_clock;
-            td[i].texels = g_tex_cache[(size_t)ci].d;
+            if (!s->holds_texture(ht.key)) { ctx().tex_cache[(size_t)ci].refs++; s->cached_tex_keys.push_back(ht.key); }
+            ctx().tex_cache[(size_t)ci].last_use = ++ctx().tex_clock;
+            td[i].texels = ctx().tex_cache[(size_t)ci].d;
         } else {
             CUDA_TRY(s->d_texels[i].upload(ht.texels));
+            if (ht.cube_blur > 0.0)
+                if (int rcb = blur_texture_in_place(s->d_texels[i].p, ht.H, ht.W, ht.cube_blur)) return rcb;
             td[i].texels = s->d_texels[i].p;
         }
         td[i].H = ht.H; td[i].W = ht.W;
@@ -1056,7 +1201,7 @@ int sp_scene_commit(sp_scene* s) {
     CUDA_TRY(s->d_stats.alloc(1));
     s->events.resize((size_t)s->n_levels + 1);
     for (auto& e : s->events) {
-        if (!g_event_pool.empty()) { e = g_event_pool.back(); g_event_pool.pop_back(); }
+        if (!ctx().event_pool.empty()) { e = ctx().event_pool.back(); ctx().event_pool.pop_back(); }
         else CUDA_TRY(cudaEventCreate(&e));
     }
     uint32_t needed = 0;
@@ -1229,7 +1374,6 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
 static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what, uint64_t primaries) {
     if (!s) return fail("%s: null scene", what);
     if (!s->committed) return fail("%s: scene not committed (sp_scene_commit)", what);
-    CUDA_TRY(cudaSetDevice(g_device));
     s->d.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull);
     s->d.seed_hi = (uint32_t)(seed >> 32);
     for (uint32_t r = 0; r < 10; ++r) {
@@ -1332,7 +1476,7 @@ static int render_chunks(sp_scene* s, uint32_t first_pix, uint32_t n_region, con
 
 int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample_begin, int sample_end, uint64_t seed,
                      int clear, sp_stats* st) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     if (s && s->committed && !s->has_camera) return fail("sp_render_region: the scene has no camera");
     const uint64_t region = (s && s->committed && pix_end > pix_begin) ? (uint64_t)(pix_end - pix_begin) : 0;
     int rc = begin_call(s, seed, st, "sp_render_region", (uint64_t)std::max(sample_end - sample_begin, 0) * region);
@@ -1346,7 +1490,7 @@ int sp_render_region(sp_scene* s, int64_t pix_begin, int64_t pix_end, int sample
 
 int sp_render_tiles(sp_scene* s, const int32_t* tile_ids, int n_tiles, int tile_size, int sample_begin, int sample_end,
                     uint64_t seed, int clear, sp_stats* st) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     if (s && s->committed && !s->has_camera) return fail("sp_render_tiles: the scene has no camera");
     if (n_tiles < 0 || (n_tiles > 0 && !tile_ids)) return fail("sp_render_tiles: invalid tile list");
     int shift = 0;
@@ -1378,10 +1522,9 @@ void* sp_accum_device_ptr(sp_scene* s) { return s ? (void*)s->accum.p : nullptr;
 uint64_t sp_accum_bytes(sp_scene* s) { return s ? (uint64_t)(s->accum.n * sizeof(float4)) : 0; }
 
 int sp_resolve(sp_scene* s, int spp_total, float* out_linear, uint8_t* out_srgb8) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     if (!s || !s->committed || !s->has_camera) return fail("sp_resolve: scene not committed or has no camera");
     if (spp_total < 1) return fail("sp_resolve: spp_total must be >= 1");
-    CUDA_TRY(cudaSetDevice(g_device));
     const size_t n = s->accum.n;
     if (s->d_lin.n != 3 * n) CUDA_TRY(s->d_lin.alloc(3 * n));
     if (s->d_u8.n != 3 * n) CUDA_TRY(s->d_u8.alloc(3 * n));
@@ -1395,7 +1538,7 @@ int sp_resolve(sp_scene* s, int spp_total, float* out_linear, uint8_t* out_srgb8
 }
 
 int sp_scene_set_stream(sp_scene* s, void* cuda_stream, int use_it) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     if (!s) return fail("sp_scene_set_stream: null scene");
     s->user_stream_set = use_it != 0;
     s->user_stream = (cudaStream_t)cuda_stream;
@@ -1416,7 +1559,7 @@ int sp_render(sp_scene* s, int spp, uint64_t seed, float* out_linear, uint8_t* o
 
 int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64_t seed, float* out_rgb,
              int32_t* out_hit_id, float* out_t, sp_stats* st) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     int rc = begin_call(s, seed, st, "sp_trace", (uint64_t)std::max(n, 0));
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!origins || !dirs))) return fail("sp_trace: invalid arguments");
@@ -1471,7 +1614,7 @@ int sp_trace(sp_scene* s, const float* origins, const float* dirs, int n, uint64
 
 static int primary_pass(sp_scene* s, int run, int sample, uint64_t seed, float* out_o, float* out_d, float* out_t,
                         int32_t* out_hit, float* out_n, const char* what) {
-    SP_LOCK;
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     int rc = begin_call(s, seed, nullptr, what, s && s->committed ? s->accum.n : 0);
     if (rc) return rc;
     if (!s->has_camera) return fail("%s: the scene has no camera", what);
@@ -1518,6 +1661,23 @@ int sp_aovs(sp_scene* s, int sample, uint64_t seed, int32_t* out_hit_id, float* 
     return primary_pass(s, SP_RUN_DISTANCES, sample, seed, nullptr, nullptr, out_t, out_hit_id, out_normal, "sp_aovs");
 }
 
+int sp_scene_read_texture(sp_scene* s, int tex_id, uint8_t* out_rgb) {
+    SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
+    if (!s || !s->committed || !out_rgb) return fail("sp_scene_read_texture: scene not committed or null output");
+    if (tex_id < 0 || tex_id >= (int)s->textures.size()) return fail("sp_scene_read_texture: texture %d out of range", tex_id);
+    const HostTexture& ht = s->textures[(size_t)tex_id];
+    const size_t n = (size_t)ht.H * ht.W;
+    DTexture desc;
+    CUDA_TRY(cudaMemcpy(&desc, s->d_texdesc.p + tex_id, sizeof desc, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> texels(n);
+    CUDA_TRY(cudaMemcpy(texels.data(), desc.texels, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+        out_rgb[3 * i] = (uint8_t)(texels[i] & 255u); out_rgb[3 * i + 1] = (uint8_t)((texels[i] >> 8) & 255u);
+        out_rgb[3 * i + 2] = (uint8_t)((texels[i] >> 16) & 255u);
+    }
+    return 0;
+}
+
 int sp_set_option(sp_scene* s, const char* name, int64_t value) {
     if (!s || !name) return fail("sp_set_option: invalid arguments");
     if (value < 0) return fail("sp_set_option: %s must be >= 0", name);
@@ -1543,10 +1703,88 @@ int sp_set_option(sp_scene* s, const char* name, int64_t value) {
     return 0;
 }
 
+// ---- several GPUs of one node, driven by the library itself (the reference's process pool, scene.py:98-116) -----------
+// `scenes` are n committed replicas of one scene on n different devices (sp_scene_create_on).  One host thread per
+// device renders that device's shard of the frame — a contiguous sample range, or (shard_mode 1, and whenever spp < n)
+// the interleaved 64x64 tiles r, r + n, ... — then the first scene's device adds the other frames to its own, reading
+// them over NVLink (peer access, sp_init_devices; a staged peer copy otherwise), and resolves.
+int sp_render_group(sp_scene** scenes, int n, int spp, uint64_t seed, int shard_mode, float* out_linear, uint8_t* out_srgb8,
+                    sp_stats* st) {
+    if (!scenes || n < 1) return fail("sp_render_group: need at least one scene");
+    if (spp < 1) return fail("sp_render_group: samples_per_pixel must be >= 1");
+    for (int r = 0; r < n; ++r) {
+        if (!scenes[r] || !scenes[r]->committed || !scenes[r]->has_camera) return fail("sp_render_group: scene %d is not committed with a camera", r);
+        if (scenes[r]->accum.n != scenes[0]->accum.n) return fail("sp_render_group: scene %d has a different frame size", r);
+        for (int q = 0; q < r; ++q)
+            if (scenes[q]->device == scenes[r]->device) return fail("sp_render_group: scenes %d and %d share device %d", q, r, scenes[r]->device);
+    }
+    const bool tiles = shard_mode == 1 || spp < n;
+    const int W = scenes[0]->d.cam.W, H = scenes[0]->d.cam.H, T = 64;
+    const int n_tiles = ((W + T - 1) / T) * ((H + T - 1) / T);
+    std::vector<int> rcs((size_t)n, 0);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<sp_stats> sts((size_t)n);
+    auto work = [&](int r) {
+        if (tiles) {
+            std::vector<int32_t> ids;
+            for (int t = r; t < n_tiles; t += n) ids.push_back(t);
+            rcs[(size_t)r] = sp_render_tiles(scenes[r], ids.data(), (int)ids.size(), T, 0, spp, seed, 1, &sts[(size_t)r]);
+        } else {
+            const int base = spp / n, extra = spp % n;
+            const int begin = r * base + std::min(r, extra), end = begin + base + (r < extra ? 1 : 0);
+            rcs[(size_t)r] = sp_render_samples(scenes[r], begin, end, seed, 1, &sts[(size_t)r]);
+        }
+        if (rcs[(size_t)r]) errs[(size_t)r] = g_error;             // the message is thread-local
+    };
+    std::vector<std::thread> threads;
+    for (int r = 1; r < n; ++r) threads.emplace_back(work, r);
+    work(0);
+    for (auto& t : threads) t.join();
+    for (int r = 0; r < n; ++r)
+        if (rcs[(size_t)r]) return fail("sp_render_group: device %d: %s", scenes[r]->device, errs[(size_t)r].c_str());
+    sp_scene* s0 = scenes[0];
+    {
+        SP_ENTER(s0->device);
+        for (int r = 1; r < n; ++r) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, s0->device, scenes[r]->device);
+            const float4* src = scenes[r]->accum.p;
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(scenes[r]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+                cudaGetLastError();
+            }
+            if (!can) {                                          // no direct access: stage the peer's frame in the scratch frame
+                CUDA_TRY(cudaMemcpyPeerAsync(s0->scratch.p, s0->device, scenes[r]->accum.p, scenes[r]->device,
+                                             s0->accum.n * sizeof(float4), s0->stream));
+                src = s0->scratch.p;
+            }
+            CUDA_TRY(sp_launch_add(s0->accum.p, src, (uint32_t)s0->accum.n, s0->stream));
+            if (!can) CUDA_TRY(cudaMemsetAsync(s0->scratch.p, 0, s0->accum.n * sizeof(float4), s0->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s0->stream));
+    }
+    if (st) {
+        *st = sts[0];
+        for (int r = 1; r < n; ++r) {
+            const sp_stats& o = sts[(size_t)r];
+            st->rays_total += o.rays_total; st->shadow_rays += o.shadow_rays; st->kernel_launches += o.kernel_launches;
+            st->chunks += o.chunks; st->level_kernel_launches += o.level_kernel_launches; st->queue_bytes += o.queue_bytes;
+            st->warp_kernel_launches += o.warp_kernel_launches; st->chunk_retries += o.chunk_retries;
+            st->device_ms = std::max(st->device_ms, o.device_ms);
+            st->level_kernel_ms = std::max(st->level_kernel_ms, o.level_kernel_ms);
+            st->peak_ray_records = std::max(st->peak_ray_records, o.peak_ray_records);
+            st->peak_fan_records = std::max(st->peak_fan_records, o.peak_fan_records);
+            for (int L = 0; L < SP_MAX_DEPTH_LEVELS; ++L) { st->rays_per_depth[L] += o.rays_per_depth[L]; st->level_ms[L] = std::max(st->level_ms[L], o.level_ms[L]); }
+        }
+        st->kernel_launches += (uint64_t)n;                      // the peer adds and the resolve
+    }
+    return sp_resolve(s0, spp, out_linear, out_srgb8);
+}
+
 int sp_measure_peaks(double* fp32_tflops, double* copy_gbs) {
-    SP_LOCK;
     if (g_device < 0) return fail("sp_measure_peaks: call sp_init first");
-    CUDA_TRY(cudaSetDevice(g_device));
+    SP_ENTER(g_device);
     double a = 0.0, b = 0.0;
     CUDA_TRY(sp_bench_ffma(&a, nullptr));
     CUDA_TRY(sp_bench_copy(&b, nullptr));

@@ -514,6 +514,17 @@ __global__ void __launch_bounds__(256) sp_fold_kernel(float4* __restrict__ accum
     scratch[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Frame of another GPU added to this one's (sp_render_group): `other` is read straight from the peer's memory over
+// NVLink when peer access is enabled — the gather and the sum are one pass, no staging copy.
+__global__ void __launch_bounds__(256) sp_add_kernel(float4* __restrict__ accum, const float4* __restrict__ other, uint32_t n) {
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+        const float4 o = other[i];
+        float4 a = accum[i];
+        a.x += o.x; a.y += o.y; a.z += o.z;
+        accum[i] = a;
+    }
+}
+
 // ---- roofline denominators ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sp_ffma_kernel(float* out, int iters, float a, float b) {
     float x[16];
@@ -609,6 +620,12 @@ cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st) {
 cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st) {
     if (n_pix == 0) return cudaSuccess;
     sp_fold_kernel<<<(n_pix + 255u) / 256u, 256, 0, st>>>(accum, scratch, n_pix);
+    return cudaGetLastError();
+}
+
+cudaError_t sp_launch_add(float4* accum, const float4* other, uint32_t n_pix, cudaStream_t st) {
+    if (n_pix == 0) return cudaSuccess;
+    sp_add_kernel<<<148 * 8, 256, 0, st>>>(accum, other, n_pix);
     return cudaGetLastError();
 }
 

@@ -47,6 +47,10 @@ int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool leve
 cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
 cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st);   // accum += scratch; scratch = 0
+cudaError_t sp_launch_add(float4* accum, const float4* other, uint32_t n_pix, cudaStream_t st);   // accum.xyz += other.xyz (other may be peer memory)
 cudaError_t sp_upload_decode_tables(const float* plain256, const float* linear256);
+// sky-box blur of a cross-layout cube map of packed texels (sp_imaging.cu); tmp0 / tmp1: two (3 * (H / 3))^2 canvases
+cudaError_t sp_blur_cube_cross(const uint32_t* cross, uint32_t* out, uint32_t* tmp0, uint32_t* tmp1, int H, int W, float blur,
+                               cudaStream_t st);
 cudaError_t sp_bench_ffma(double* tflops, cudaStream_t st);
 cudaError_t sp_bench_copy(double* gbs, cudaStream_t st);

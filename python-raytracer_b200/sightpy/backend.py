@@ -11,7 +11,8 @@ import numpy as np
 
 from .flatten import (CAMERA_DT, COLLIDER_DT, LIGHT_DT, MATERIAL_DT, PRIMITIVE_DT, FlatScene)
 
-__all__ = ["NativeScene", "load_library", "library_path", "Stats", "measure_peaks"]
+__all__ = ["NativeScene", "NativeGroup", "load_library", "library_path", "Stats", "measure_peaks", "visible_devices",
+           "configured_devices", "trim"]
 
 SP_MAX_DEPTH_LEVELS = 64
 _LIB = None
@@ -70,6 +71,11 @@ def load_library():
         "sp_abi_version": (i32, []),
         "sp_abi_sizes": (i32, [vp]),
         "sp_init": (i32, [i32]),
+        "sp_init_devices": (i32, [i32, vp]),
+        "sp_default_device": (i32, []),
+        "sp_trim": (None, []),
+        "sp_scene_create_on": (i32, [C.POINTER(vp), i32]),
+        "sp_render_group": (i32, [vp, i32, i32, u64, i32, vp, vp, C.POINTER(Stats)]),
         "sp_device_count": (i32, []),
         "sp_last_error": (C.c_char_p, []),
         "sp_shutdown": (None, []),
@@ -79,6 +85,8 @@ def load_library():
         "sp_scene_set_camera": (i32, [vp, vp]),
         "sp_scene_add_texture": (i32, [vp, vp, i32, i32, i32, C.POINTER(i32)]),
         "sp_scene_add_texture_keyed": (i32, [vp, u64, vp, i32, i32, i32, C.POINTER(i32)]),
+        "sp_scene_add_texture_blurred": (i32, [vp, u64, vp, i32, i32, i32, C.c_double, C.POINTER(i32)]),
+        "sp_scene_read_texture": (i32, [vp, i32, vp]),
         "sp_scene_set_materials": (i32, [vp, vp, i32]),
         "sp_scene_set_primitives": (i32, [vp, vp, i32]),
         "sp_scene_set_colliders": (i32, [vp, vp, i32]),
@@ -129,14 +137,47 @@ def default_device():
     return 0
 
 
+_BOUND = set()          # devices initialised so far
+
+
 def bind_device(device=None):
+    """Initialise one CUDA device (the first one bound becomes the library's default device)."""
     global _BOUND_DEVICE
     lib = load_library()
     device = default_device() if device is None else int(device)
-    if _BOUND_DEVICE != device:
-        _check(lib, lib.sp_init(device), f"sp_init({device})")
-        _BOUND_DEVICE = device
+    if device not in _BOUND:
+        if _BOUND_DEVICE is None:
+            _check(lib, lib.sp_init(device), f"sp_init({device})")
+            _BOUND_DEVICE = device
+            import atexit
+            atexit.register(lib.sp_shutdown)          # return pooled device memory, streams and events
+        else:                                         # a further device: keep the default, add this one
+            ids = (C.c_int * (len(_BOUND) + 1))(_BOUND_DEVICE, *sorted(_BOUND - {_BOUND_DEVICE}), device)
+            _check(lib, lib.sp_init_devices(len(ids), ids), f"sp_init_devices(+{device})")
+        _BOUND.add(device)
     return lib
+
+
+def visible_devices():
+    return list(range(load_library().sp_device_count()))
+
+
+def configured_devices():
+    """Devices a Scene renders on.  SIGHTPY_DEVICES = "all" | "0,1,2" | unset.  Unset: every visible GPU when the
+    process is not one rank of a torchrun job (WORLD_SIZE <= 1), as the reference's render() uses every core
+    (scene.py:80); under torchrun each rank drives the one GPU named by LOCAL_RANK."""
+    spec = os.environ.get("SIGHTPY_DEVICES", "").strip().lower()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("SIGHTPY_DEVICE", "") != "":
+        return [default_device()]
+    if spec in ("", "all"):
+        n = load_library().sp_device_count()
+        return list(range(n)) if n > 0 else [0]
+    return [int(x) for x in spec.split(",") if x.strip() != ""]
+
+
+def trim():
+    """Return idle pooled device memory to the driver (sp_trim)."""
+    load_library().sp_trim()
 
 
 def measure_peaks(device=None):
@@ -155,12 +196,13 @@ class NativeScene:
 
     def __init__(self, flat: FlatScene, device=None):
         self.lib = bind_device(device)
-        self.device_index = _BOUND_DEVICE        # the CUDA device all of this scene's memory and kernels live on
+        # the CUDA device all of this scene's memory and kernels live on
+        self.device_index = default_device() if device is None else int(device)
         self.flat = flat
         self.width = int(flat.camera["width"])
         self.height = int(flat.camera["height"])
         self.handle = C.c_void_p()
-        _check(self.lib, self.lib.sp_scene_create(C.byref(self.handle)), "sp_scene_create")
+        _check(self.lib, self.lib.sp_scene_create_on(C.byref(self.handle), self.device_index), "sp_scene_create")
         try:
             self._upload(flat)
         except Exception:
@@ -204,9 +246,11 @@ class NativeScene:
         _check(lib, lib.sp_scene_set_camera(h, _ptr(cam)), "set_camera")
         for t in (flat.textures if textures else ()):
             tid = C.c_int(-1)
-            u8 = np.ascontiguousarray(t.u8)
-            _check(lib, lib.sp_scene_add_texture_keyed(h, int(getattr(t, "key", 0)), _ptr(u8), u8.shape[0], u8.shape[1],
-                                                       t.decode, C.byref(tid)), "add_texture")
+            # a sky box that wants blurring hands over its raw texels: the device blurs them (sp_imaging.cu)
+            blur = float(getattr(t, "cube_blur", 0.0))
+            u8 = np.ascontiguousarray(t.source_u8 if blur else t.u8)
+            _check(lib, lib.sp_scene_add_texture_blurred(h, int(getattr(t, "key", 0)), _ptr(u8), u8.shape[0], u8.shape[1],
+                                                         t.decode, blur, C.byref(tid)), "add_texture")
         for name, fn in (("materials", lib.sp_scene_set_materials), ("primitives", lib.sp_scene_set_primitives),
                          ("colliders", lib.sp_scene_set_colliders), ("lights", lib.sp_scene_set_lights),
                          ("importance", lib.sp_scene_set_importance),
@@ -316,6 +360,14 @@ class NativeScene:
                "sp_camera_rays")
         return o, d
 
+    def read_texture(self, tex_id):
+        """Texels of one texture as the device holds them (after any sky-box blur) -> H x W x 3 uint8."""
+        t = self.flat.textures[tex_id]
+        src = t.source_u8 if getattr(t, "cube_blur", 0.0) else t.u8
+        out = np.empty(src.shape, dtype=np.uint8)
+        _check(self.lib, self.lib.sp_scene_read_texture(self.handle, int(tex_id), _ptr(out)), "sp_scene_read_texture")
+        return out
+
     def aovs(self, sample=0, seed=0):
         """Per-pixel nearest collider index, hit distance and ray-facing collider normal of one primary ray per pixel."""
         n = self.width * self.height
@@ -330,3 +382,45 @@ class NativeScene:
         t = np.empty(self.width * self.height, dtype=np.float32)
         _check(self.lib, self.lib.sp_distances(self.handle, int(seed), _ptr(t)), "sp_distances")
         return t
+
+
+class NativeGroup:
+    """Replicas of one scene on several GPUs of the node, rendered together by sp_render_group: one host thread per
+    device inside the library, frames gathered over NVLink peer access — no launcher, no torch (the reference's
+    render() fans out over a process pool the same way, scene.py:98-116).  Everything that is not a frame render
+    (trace, camera_rays, aovs, distances) goes to the first member."""
+    GROUP_MIN_PRIMARIES = 4 << 20        # smaller frames are rendered by the first member alone
+
+    def __init__(self, flat, devices):
+        self.members = [NativeScene(flat, device=d) for d in devices]
+        self.lib = self.members[0].lib
+
+    # what Scene / parallel.render_frame use
+    flat = property(lambda self: self.members[0].flat)
+    width = property(lambda self: self.members[0].width)
+    height = property(lambda self: self.members[0].height)
+    device_index = property(lambda self: self.members[0].device_index)
+
+    def update(self, flat):
+        return [m.update(flat) for m in self.members][0]
+
+    def close(self):
+        for m in self.members:
+            m.close()
+
+    def render(self, spp, seed=0, want_linear=True, shard="auto"):
+        first = self.members[0]
+        if len(self.members) == 1 or int(spp) * self.width * self.height < self.GROUP_MIN_PRIMARIES:
+            return first.render(spp, seed, want_linear)
+        srgb = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        lin = np.empty((3, self.height, self.width), dtype=np.float32) if want_linear else None
+        st = Stats()
+        handles = (C.c_void_p * len(self.members))(*[m.handle for m in self.members])
+        _check(self.lib, self.lib.sp_render_group(handles, len(self.members), int(spp), int(seed), 1 if shard == "tiles" else 0,
+                                                  _ptr(lin), _ptr(srgb), C.byref(st)), "sp_render_group")
+        out = st.as_dict()
+        out["devices"] = [m.device_index for m in self.members]
+        return srgb, lin, out
+
+    def __getattr__(self, name):         # trace, camera_rays, aovs, distances, set_option, ...
+        return getattr(self.members[0], name)

@@ -4,7 +4,7 @@ ordinary huge primitive with a self-emitting texture.
 Reference: sightpy/backgrounds/skybox.py:9-94, sightpy/backgrounds/panorama.py:10-26.
 """
 from .constants import SKYBOX_DISTANCE
-from .imaging import DECODE_LINEAR, DECODE_PLAIN, TextureImage, blur_skybox_u8, open_rgb8
+from .imaging import DECODE_LINEAR, DECODE_PLAIN, TextureImage, open_rgb8
 from .shading import Material
 from .shapes import Cuboid_Collider, Primitive, Sphere_Collider
 from .vec import vec3
@@ -25,7 +25,8 @@ class SkyBox_Material(Material):
             self.lightmap = TextureImage(open_rgb8("sightpy/backgrounds/lightmaps/" + cubemap), DECODE_PLAIN)
         self.blur_image = None
         if blur != 0.0:
-            self.blur_image = TextureImage(blur_skybox_u8(raw, blur, cubemap), DECODE_LINEAR)
+            print("blurring " + str(cubemap))
+            self.blur_image = TextureImage(raw, DECODE_LINEAR, cube_blur=blur, name=str(cubemap))
         self.blur = blur
         self.light_intensity = light_intensity
         self.repeat = 1.0

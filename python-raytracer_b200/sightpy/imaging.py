@@ -52,20 +52,34 @@ _NEXT_TEXTURE_KEY = [1]
 
 class TextureImage:
     """uint8 RGB image + decode-table kind. ``shape``/``as_float`` mimic the reference arrays.
-    Immutable by convention: ``key`` names its bytes for the backend's device-resident texture cache."""
+    Immutable by convention: ``key`` names its bytes for the backend's device-resident texture cache.
 
-    def __init__(self, u8, decode):
+    ``cube_blur`` > 0 marks a cross-layout cube map that is to be blurred (skybox.py:46-49).  The renderer hands the raw
+    texels (``source_u8``) and the radius to the library, which blurs them on the GPU; ``u8`` — what host-side
+    consumers such as the test oracle read — is then computed on demand with the reference's own Pillow pipeline
+    (``blur_skybox_u8``), so the two can be compared byte for byte."""
+
+    def __init__(self, u8, decode, cube_blur=0.0, name=""):
         self.key = _NEXT_TEXTURE_KEY[0]          # unique per object for the life of the process
         _NEXT_TEXTURE_KEY[0] += 1
         u8 = np.ascontiguousarray(u8, dtype=np.uint8)
         if u8.ndim != 3 or u8.shape[2] != 3:
             raise ValueError("TextureImage expects an H x W x 3 uint8 array")
-        self.u8 = u8
+        self.source_u8 = u8
         self.decode = int(decode)
+        self.cube_blur = float(cube_blur)
+        self.name = name
+        self._u8 = None if self.cube_blur else u8
+
+    @property
+    def u8(self):
+        if self._u8 is None:
+            self._u8 = blur_skybox_u8(self.source_u8, self.cube_blur, self.name)
+        return self._u8
 
     @property
     def shape(self):
-        return self.u8.shape
+        return self.source_u8.shape
 
     def as_float(self):
         return decode_table(self.decode)[self.u8]
@@ -137,7 +151,6 @@ def blur_skybox_u8(u8, blur, name=""):
     ``(255*x).astype(uint8)`` (blur_background.py:6-10), i.e. byte b becomes max(b-1, 0) before
     the Gaussian filter; the filtered bytes are then read back as ``byte/256`` and linearised.
     Returning the filtered bytes keeps that pipeline exact (decode with DECODE_LINEAR)."""
-    print("blurring " + name)
     n = int(u8.shape[0] / 3)
     requant = (255 * (u8.astype(np.float64) / 256.0)).astype(np.uint8)
     face = {k: requant[r * n:(r + 1) * n, c * n:(c + 1) * n] for k, (r, c) in _CROSS_SLOT.items()}

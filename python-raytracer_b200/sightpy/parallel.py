@@ -74,7 +74,9 @@ def render_frame(native, spp, seed=0, want_linear=False, shard=None):
     function with a gloo group and a stand-in scene)."""
     rank, size = world()
     if size == 1:
-        srgb, lin, stats = native.render(spp, seed, want_linear=want_linear)
+        # one process: a backend.NativeGroup spreads the frame over the node's GPUs inside the library
+        kw = {"shard": shard} if shard and hasattr(native, "members") else {}
+        srgb, lin, stats = native.render(spp, seed, want_linear=want_linear, **kw)
         return (srgb, stats) if not want_linear else (srgb, lin, stats)
     import torch.distributed as dist
     shard = shard or os.environ.get("SIGHTPY_SHARD", "auto")

@@ -88,10 +88,12 @@ class Scene:
             self._native = None
 
     def _backend(self):
-        from .backend import NativeScene
+        from .backend import NativeGroup, NativeScene, configured_devices
         from .flatten import flatten_scene
         if self._native is None:
-            self._native = NativeScene(flatten_scene(self))
+            devices = configured_devices()
+            flat = flatten_scene(self)
+            self._native = NativeGroup(flat, devices) if len(devices) > 1 else NativeScene(flat, device=devices[0])
         elif self._stale or len(self.collider_list) <= self.AUTO_REFLATTEN:
             self._native.update(flatten_scene(self))
         self._stale = False

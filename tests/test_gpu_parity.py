@@ -859,3 +859,37 @@ def test_full_stress_scene_bvh_agrees_with_exhaustive_loop_on_sampled_pixels():
     check_count("hit_mismatch/full_stress_oracle_primary", int(np.sum(with_bvh["hit_id"][sub] != hit_id)), 4096, 0.01)
     ok = (with_bvh["hit_id"][sub] == hit_id) & np.isfinite(t)
     np.testing.assert_allclose(with_bvh["t"][sub][ok], t[ok], rtol=2e-5, atol=1e-4)
+
+
+def test_device_skybox_blur_is_byte_identical_to_the_reference_blur():
+    """add_Background(..., blur=...) blurs the cube map on the GPU (sp_imaging.cu).  The texels the
+    device ends up with equal, byte for byte, what blur_skybox (blur_background.py:17-132, Pillow on the host)
+    produces — for the example4 sky box (sha256 of the reference's own output, recorded by make_golden.py) and for
+    random cross images at several radii, including box radii below one pixel."""
+    import hashlib
+    from sightpy.backend import NativeScene
+    from sightpy.imaging import DECODE_LINEAR, TextureImage, blur_skybox_u8, decode_table
+    scene = build_scene("example4", (64, 48))
+    flat = flatten_scene(scene)
+    blurred = [i for i, t in enumerate(flat.textures) if getattr(t, "cube_blur", 0.0)]
+    assert len(blurred) == 1 and flat.textures[blurred[0]].cube_blur == 10.0
+    nat = NativeScene(flat)
+    got = nat.read_texture(blurred[0])
+    nat.close()
+    arr = np.ascontiguousarray(decode_table(DECODE_LINEAR)[got])
+    assert list(arr.shape) == REPORT["blur_lake_shape"]
+    assert hashlib.sha256(arr.tobytes()).hexdigest() == REPORT["blur_lake_sha256"]
+    # random crosses, other radii: against the host pipeline (which the digest above pins to the reference)
+    import sightpy as sp
+    rng = np.random.default_rng(5)
+    for n, radius in ((16, 0.7), (40, 3.3), (33, 10.0), (24, 25.0)):
+        raw = rng.integers(0, 256, size=(3 * n, 4 * n, 3), dtype=np.uint8)
+        sc = sp.Scene()
+        sc.add_Camera(look_from=sp.vec3(0, 0, 1), look_at=sp.vec3(0, 0, 0), screen_width=8, screen_height=8)
+        f = flatten_scene(sc)
+        f.textures.append(TextureImage(raw, DECODE_LINEAR, cube_blur=radius, name="random"))
+        nat = NativeScene(f)
+        got = nat.read_texture(0)
+        nat.close()
+        want = blur_skybox_u8(raw, radius)
+        assert np.array_equal(got, want), (n, radius, int((got != want).sum()))
