@@ -79,6 +79,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the brief runs of the other configurations")
+    ap.add_argument("--in-process", action="store_true",
+                    help="drive --gpus N devices from this one process through sp_render_group (no torchrun)")
     return ap.parse_args()
 
 
@@ -345,6 +347,56 @@ def timed(torch, dist, world, runner, warmup, steps, clocks=None):
     return tot
 
 
+def run_group(args, emit=print):
+    """N GPUs driven by the library itself from one process (sp_init_devices + sp_render_group: host thread per device,
+    NVLink peer-access gather) — what a plain `python example.py` gets on a multi-GPU node."""
+    import scenes
+    import sightpy
+    from sightpy.backend import NativeGroup
+    from sightpy.flatten import flatten_scene
+    cfg = CONFIGS[args.config]
+    width, height, spp = args.width or cfg["width"], args.height or cfg["height"], args.spp or cfg["spp"]
+    shard = args.shard or cfg.get("shard", "samples")
+    flat = flatten_scene(scenes.BUILDERS[cfg["builder"]](sightpy, width=width, height=height, **cfg["kw"]))
+    group = NativeGroup(flat, list(range(args.gpus)))
+    with ClockSampler(0) as clocks:
+        for _ in range(args.warmup):
+            group.render_on_device(spp, 0, shard)
+        clocks.mark_begin()
+        t0 = time.perf_counter()
+        rays = launches = 0
+        dev_ms = 0.0
+        for _ in range(args.steps):
+            st = group.render_on_device(spp, 0, shard)
+            rays += st["rays_total"]; launches += st["kernel_launches"]; dev_ms += st["device_ms"]
+        wall = time.perf_counter() - t0
+        clocks.mark_end()
+    srgb, lin, st = group.render(spp, 0, want_linear=True, shard=shard)
+    # end to end: the frame copied out every step (the scene stays resident: sp_render_group has no re-upload to time)
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 2))
+    e2e_rays = 0
+    for _ in range(n_e2e):
+        _, _, se = group.render(spp, 0, want_linear=False, shard=shard)
+        e2e_rays += se["rays_total"]
+    e2e_s = time.perf_counter() - t0
+    group.close()
+    emit(json.dumps({
+        "metric": metric_name(args.config), "value": rays / wall / 1e6, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "s_per_frame": wall / args.steps,
+        "device_ms_per_step_slowest_gpu": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{cfg['builder']} scene, {width}x{height}, {spp} spp (BASELINE.json configs[{cfg['index']}])",
+                   "sharding": f"in-process: sp_render_group over {args.gpus} devices, {shard}, peer-access gather (no torchrun, no NCCL)",
+                   "timing": "host wall clock around the blocking sp_render_group calls (slowest device + gather + resolve)",
+                   "rays_per_frame": rays / args.steps},
+        "frame": frame_fingerprint(srgb, lin),
+        "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": int(width * height * 3), "steps": n_e2e, "s_per_frame": e2e_s / n_e2e},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+    }))
+
+
 def run_native(args, emit=print):
     import torch
     import torch.distributed as dist
@@ -543,6 +595,8 @@ def main():
     try:
         if args.impl == "reference":
             run_reference(args, emit)
+        elif args.in_process and args.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+            run_group(args, emit)
         else:
             run_native(args, emit)
     finally:

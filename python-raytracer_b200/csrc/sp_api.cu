@@ -498,8 +498,12 @@ static int bvh_build_rec(BuiltBvh& out, std::vector<int>& order, int first, int 
             bounds.lo[k] = std::min(bounds.lo[k], boxes[order[i]].lo[k]);
             bounds.hi[k] = std::max(bounds.hi[k], boxes[order[i]].hi[k]);
         }
-    if (count <= 4) {                    // leaf: its items become consecutive in the item array
+    if (count <= 4) {                    // leaf: its items become consecutive in the item array, by type, then by id
         const int at = (int)out.items.size();
+        std::sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {
+            const int ta = item_of[a] & 255, tb = item_of[b] & 255;
+            return ta != tb ? ta < tb : a < b;
+        });
         for (int i = first; i < first + count; ++i) out.items.push_back(make_int4(item_of[order[i]], 0, order[i], 0));
         return ~((at << 3) | (count - 1));
     }
@@ -639,13 +643,32 @@ static BuiltBvh build_bvh(const std::vector<sp_collider>& cols, const std::vecto
         memcpy(&kids.x, &code, 4); memcpy(&kids.y, &none, 4);
         out.nodes[3] = kids;
     }
-    for (auto& it : out.items) {        // packed collider data, in item order
-        const int st = it.x & 255;
-        it.y = (int)out.data.size();
-        std::vector<float> tmp((size_t)4 * type_vec4(st), 0.f);
+    // Leaf records, in item order: one header vector (stream type | casts shadow << 8, collider id, data vectors, -)
+    // followed by the collider's packed data, so that a leaf is one contiguous run the traversal walks with a single
+    // pointer (no item table between the node and the data).
+    std::vector<int> record_at(out.items.size());
+    for (size_t k = 0; k < out.items.size(); ++k) {
+        int4& it = out.items[k];
+        const int st = it.x & 255, nv = type_vec4(st);
+        record_at[k] = (int)out.data.size();
+        it.y = record_at[k] + 1;
+        float4 head; memset(&head, 0, sizeof head);
+        memcpy(&head.x, &it.x, 4); memcpy(&head.y, &it.z, 4); memcpy(&head.z, &nv, 4);
+        out.data.push_back(head);
+        std::vector<float> tmp((size_t)4 * nv, 0.f);
         pack_collider(cols[(size_t)it.z], st, tmp.data());
-        for (int v = 0; v < type_vec4(st); ++v) out.data.push_back(make_float4(tmp[4 * v], tmp[4 * v + 1], tmp[4 * v + 2], tmp[4 * v + 3]));
+        for (int v = 0; v < nv; ++v) out.data.push_back(make_float4(tmp[4 * v], tmp[4 * v + 1], tmp[4 * v + 2], tmp[4 * v + 3]));
     }
+    // leaf codes name the first item of the leaf: turn them into the offset of its record
+    for (size_t nd = 0; nd + 3 < out.nodes.size(); nd += 4)
+        for (int k = 0; k < 2; ++k) {
+            float* slot = k == 0 ? &out.nodes[nd + 3].x : &out.nodes[nd + 3].y;
+            int code; memcpy(&code, slot, 4);
+            if (code >= 0) continue;
+            const int c = ~code, first = c >> 3, cnt1 = c & 7;
+            const int recoded = ~((record_at[(size_t)first] << 3) | cnt1);
+            memcpy(slot, &recoded, 4);
+        }
     return out;
 }
 
@@ -1402,11 +1425,13 @@ static uint32_t pick_chunk(sp_scene* s, uint64_t region) {
     int64_t p = default_chunk(s);
     if (s->use_ray == 0.0 && s->use_fan == 0.0)
         p = std::min<int64_t>(p, region <= ((uint64_t)16 << 20) ? (int64_t)std::max<uint64_t>(region, 1) : (int64_t)1 << 16);
+    else if (s->opt_chunk == 0)
+        p *= 8;            // scenes that queue little (Whitted trees: 1-3 records per primary) take far larger chunks in the same queues
     const double slack = 1.3;
     if (s->use_ray > 0.0) p = std::min<int64_t>(p, (int64_t)(s->ray_cap / (s->use_ray * slack)));
     if (s->use_fan > 0.0) p = std::min<int64_t>(p, (int64_t)(s->fan_cap / (s->use_fan * slack)));
     if (s->chunk_limit > 0) p = std::min<int64_t>(p, s->chunk_limit);
-    return (uint32_t)std::max<int64_t>(p, 1024);
+    return (uint32_t)std::min<int64_t>(std::max<int64_t>(p, 1024), (int64_t)0x7FFFFFFF);
 }
 
 // A chunk overflowed a queue: what to do next.  Returns non-zero (with the overflow message) when the chunk cannot

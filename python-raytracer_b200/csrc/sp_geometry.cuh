@@ -313,8 +313,9 @@ SP_DEV void sp_intersect_lean(const float4* __restrict__ ch, float3 O, float3 D,
 // so hits are those of the exhaustive loop.  Colliders that span a large part of the scene (ground planes,
 // sky boxes) stay in the staged chunk and are tested by every ray.
 //   node  (4 float4): child 0 box (lo.xyz, hi.x | hi.yz) child 1 box (lo.xy | lo.z, hi.xyz), children (int, int)
-//                     child >= 0: node index; child < 0: leaf, ~child = first item << 3 | (count - 1)
-//   item  (int4)    : stream type | casts shadow << 8, float4 offset of its packed data, collider id, -
+//                     child >= 0: node index; child < 0: leaf (see below)
+//   leaf  : ~child = float4 offset of its first record in `data` << 3 | (count - 1); a record is one header vector
+//           (stream type | casts shadow << 8, collider id, number of data vectors, -) followed by the packed collider
 
 SP_DEV bool sp_box_hit(float3 lo, float3 hi, float3 O, float3 inv, float t_max, float& t_near) {
     const float tx1 = (lo.x - O.x) * inv.x, tx2 = (hi.x - O.x) * inv.x;
@@ -327,51 +328,63 @@ SP_DEV bool sp_box_hit(float3 lo, float3 hi, float3 O, float3 inv, float t_max, 
 
 // Nearest hit among the BVH's colliders closer than best.t.  casters_only: shadow rays (glossy.py:53-57) look at
 // shadow-casting colliders only and may stop at the first hit closer than t_any.
+//
+// "while-while" traversal (Aila & Laine, Understanding the efficiency of ray traversal on GPUs): an inner loop walks
+// box nodes until the lane holds a leaf, a second loop tests the leaf's colliders.  Lanes that reach their leaf early
+// wait at the end of the inner loop, so the leaves of a warp are tested side by side instead of one lane at a time
+// between the node steps of the others (round 1's single loop ran its collider tests with 2 of 32 lanes, ncu
+// profiles/r2_stress_bvh_binary.md).  The host sorts the colliders of a leaf by type, so the lanes of a warp mostly
+// agree on the test they run for item k of their leaves.
+#define SP_BVH_DONE 0x7FFFFFFF
 SP_DEV void sp_bvh_nearest(const DBvh& bvh, float3 O, float3 D, int src_id, uint32_t mode, bool casters_only, float t_any,
                            ChunkBest& best) {
     if (bvh.n_nodes == 0) return;
     const float3 inv = v3(fast_rcp(D.x), fast_rcp(D.y), fast_rcp(D.z));
     int stack[32];
-    int sp = 0, node = 0;
-    while (true) {
-        const float4 n0 = __ldg(bvh.nodes + 4 * node), n1 = __ldg(bvh.nodes + 4 * node + 1);
-        const float4 n2 = __ldg(bvh.nodes + 4 * node + 2), n3 = __ldg(bvh.nodes + 4 * node + 3);
-        float ta, tb;
-        const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), O, inv, best.t, ta);
-        const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), O, inv, best.t, tb);
-        int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
-        if (ha && hb && tb < ta) { const int c = ca; ca = cb; cb = c; }      // nearer child first
-        int next = -1;                                                      // inner node to descend into
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const bool h = k == 0 ? (ha || hb) : (ha && hb);
-            const int c = k == 0 ? (ha ? ca : cb) : cb;
-            if (!h) continue;
-            if (c >= 0) {
-                if (next < 0) next = c; else stack[sp++] = c;
-            } else {                                                        // leaf
-                const int code = ~c, first = code >> 3, count = (code & 7) + 1;
-                for (int i = first; i < first + count; ++i) {
-                    const int4 it = __ldg(bvh.items + i);
-                    if (casters_only && !(it.x & 256)) continue;
-                    const float4* d = bvh.data + it.y;
-                    const bool is_self = it.z == src_id;
-                    switch (it.x & 255) {
-                    case SP_ST_SPHERE: sp_item_sphere(__ldg(d), O, D, is_self, mode, it.z, best); break;
-                    case SP_ST_PLANE: sp_item_plane(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), O, D, is_self, it.z, best); break;
-                    case SP_ST_CUBOID: sp_item_cuboid(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), __ldg(d + 4), O, D, is_self, mode, it.z, best); break;
-                    case SP_ST_TRI: sp_item_triangle(__ldg(d), __ldg(d + 1), __ldg(d + 2), O, D, is_self, it.z, best); break;
-                    case SP_ST_AAX: sp_item_aa<0>(__ldg(d), __ldg(d + 1), O, D, inv.x, is_self, it.z, best); break;
-                    case SP_ST_AAY: sp_item_aa<1>(__ldg(d), __ldg(d + 1), O, D, inv.y, is_self, it.z, best); break;
-                    default: sp_item_aa<2>(__ldg(d), __ldg(d + 1), O, D, inv.z, is_self, it.z, best); break;
-                    }
-                }
-                if (best.t < t_any) return;
+    int sp = 0, node = 0;                                  // >= 0: box node, < 0: leaf code, SP_BVH_DONE: finished
+    while (node != SP_BVH_DONE) {
+        // ---- box nodes until a leaf (or nothing) is at hand ----------------------------------------------------
+        while (node >= 0 && node != SP_BVH_DONE) {
+            const float4 n0 = __ldg(bvh.nodes + 4 * node), n1 = __ldg(bvh.nodes + 4 * node + 1);
+            const float4 n2 = __ldg(bvh.nodes + 4 * node + 2), n3 = __ldg(bvh.nodes + 4 * node + 3);
+            float ta, tb;
+            const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), O, inv, best.t, ta);
+            const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), O, inv, best.t, tb);
+            int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
+            if (ha && hb) {
+                if (tb < ta) { const int c = ca; ca = cb; cb = c; }      // nearer child first
+                stack[sp++] = cb;
+                node = ca;
+            } else if (ha || hb) {
+                node = ha ? ca : cb;
+            } else {
+                node = sp ? stack[--sp] : SP_BVH_DONE;
             }
         }
-        if (next >= 0) { node = next; continue; }
-        if (sp == 0) return;
-        node = stack[--sp];
+        // ---- the leaf's colliders ------------------------------------------------------------------------------
+        if (node != SP_BVH_DONE) {
+            const int code = ~node, count = (code & 7) + 1;
+            const float4* rec = bvh.data + (code >> 3);        // leaf records: header vector + packed collider, back to back
+            for (int i = 0; i < count; ++i) {
+                const float4 head = __ldg(rec);
+                const int kind = __float_as_int(head.x), id = __float_as_int(head.y);
+                const float4* d = rec + 1;
+                rec = d + __float_as_int(head.z);
+                if (casters_only && !(kind & 256)) continue;
+                const bool is_self = id == src_id;
+                switch (kind & 255) {
+                case SP_ST_SPHERE: sp_item_sphere(__ldg(d), O, D, is_self, mode, id, best); break;
+                case SP_ST_PLANE: sp_item_plane(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), O, D, is_self, id, best); break;
+                case SP_ST_CUBOID: sp_item_cuboid(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), __ldg(d + 4), O, D, is_self, mode, id, best); break;
+                case SP_ST_TRI: sp_item_triangle(__ldg(d), __ldg(d + 1), __ldg(d + 2), O, D, is_self, id, best); break;
+                case SP_ST_AAX: sp_item_aa<0>(__ldg(d), __ldg(d + 1), O, D, inv.x, is_self, id, best); break;
+                case SP_ST_AAY: sp_item_aa<1>(__ldg(d), __ldg(d + 1), O, D, inv.y, is_self, id, best); break;
+                default: sp_item_aa<2>(__ldg(d), __ldg(d + 1), O, D, inv.z, is_self, id, best); break;
+                }
+            }
+            if (best.t < t_any) return;
+            node = sp ? stack[--sp] : SP_BVH_DONE;
+        }
     }
 }
 

@@ -422,5 +422,13 @@ class NativeGroup:
         out["devices"] = [m.device_index for m in self.members]
         return srgb, lin, out
 
+    def render_on_device(self, spp, seed=0, shard="samples"):
+        """The same without copying the frame out (bench.py): the resolved frame stays in the first member's buffers."""
+        st = Stats()
+        handles = (C.c_void_p * len(self.members))(*[m.handle for m in self.members])
+        _check(self.lib, self.lib.sp_render_group(handles, len(self.members), int(spp), int(seed), 1 if shard == "tiles" else 0,
+                                                  None, None, C.byref(st)), "sp_render_group")
+        return st.as_dict()
+
     def __getattr__(self, name):         # trace, camera_rays, aovs, distances, set_option, ...
         return getattr(self.members[0], name)
