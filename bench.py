@@ -51,7 +51,10 @@ CONFIGS = {
                      what="example4.py scene (thin-film bubble, blurred light-emitting sky box), 3840x2160, 16 spp"),
     "cornell": dict(index=3, builder="cornell", width=1920, height=1080, spp=256, kw={}, cpu=(160, 90),
                     what="example_cornellbox.py scene, 1920x1080, 256 spp"),
+    # the reference's cost grows with (colliders x distinct colliders hit per level): at 6145 colliders it does not finish
+    # a thumbnail in minutes, so its CPU sample uses a 385-collider version of the scene (and says so)
     "stress": dict(index=4, builder="stress", width=3840, height=2160, spp=64, kw={}, cpu=(24, 14), shard="tiles",
+                   cpu_kw=dict(n_spheres=256, n_triangles=64),
                    what="4096 random spheres + 2 x 1024 triangles over a checker ground, 3840x2160, 64 spp"),
 }
 # algorithmic flops of one ray-collider test (1 FMA = 2 flop; compares / min / max not counted)
@@ -211,7 +214,7 @@ def run_reference(args, emit=print):
     w, h = cfg["cpu"]
     if args.config == "cornell":
         w, h = 240, 135                   # 1/8-scale frame: ~1.9 M rays per sample (~6 s per core)
-    kw = dict(cfg["kw"], width=w, height=h)
+    kw = dict(cfg["kw"], width=w, height=h, **cfg.get("cpu_kw", {}))
     small = dict(kw, width=max(w // 4, 8), height=max(h // 4, 8))
     for _ in range(args.warmup):
         cpu_rate(cfg["builder"], small, cores, cores)
@@ -223,7 +226,7 @@ def run_reference(args, emit=print):
     value = rays / secs / 1e6
     what = ("get_raycolor of the unmodified reference (baseline/_ref copy of lmondada/Python-Raytracer, float64 numpy)"
             if kind == "reference" else "float64 numpy oracle port of the reference")
-    sample = f"{cfg['builder']} scene at {w}x{h}, {cores} spp per step (one sample per worker process), {what}"
+    sample = f"{cfg['builder']} scene{' ' + str(cfg['cpu_kw']) if cfg.get('cpu_kw') else ''} at {w}x{h}, {cores} spp per step (one sample per worker process), {what}"
     # Scene.render exactly as the example scripts call it: process pool, deep copies and pickling included
     shipped = None
     if kind == "reference" and args.config == "cornell":
@@ -554,10 +557,10 @@ def run_native(args, emit=print):
     if not args.no_cpu_baseline and world == 1:
         w, h = cfg["cpu"]
         n = 2 if args.config == "cornell" else 1
-        r, s, kind = cpu_rate(cfg["builder"], dict(cfg["kw"], width=w, height=h), n, 1)
+        r, s, kind = cpu_rate(cfg["builder"], dict(cfg["kw"], width=w, height=h, **cfg.get("cpu_kw", {})), n, 1)
         what = "unmodified reference (baseline/_ref), get_raycolor" if kind == "reference" else "float64 numpy oracle port"
         cpu = {"value": r / s / 1e6, "unit": "Mrays/s", "cores": 1, "kind": kind,
-               "sample": f"{cfg['builder']} scene at {w}x{h}, {n} spp, {what}, single process"}
+               "sample": f"{cfg['builder']} scene{' ' + str(cfg['cpu_kw']) if cfg.get('cpu_kw') else ''} at {w}x{h}, {n} spp, {what}, single process"}
 
     out = {
         "metric": metric_name(args.config), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
