@@ -117,7 +117,7 @@ typedef struct sp_stats {
     double   level_ms[SP_MAX_DEPTH_LEVELS];   /* level kernel time per recursion depth            */
     uint64_t peak_ray_records;      /* largest per-level queue occupancy seen (records)           */
     uint64_t peak_fan_records;
-    uint64_t warp_kernel_launches;  /* of level_kernel_launches: those that ran the warp-autonomous sp_path_kernel */
+    uint64_t warp_kernel_launches;  /* of level_kernel_launches: those that ran the warp-autonomous sp_warp_kernel */
     uint64_t chunk_retries;         /* chunks rendered again at half the size after a queue overflow  */
 } sp_stats;
 
@@ -239,15 +239,18 @@ int  sp_distances(sp_scene*, uint64_t seed, float* out_t);
 int  sp_aovs(sp_scene*, int sample, uint64_t seed, int32_t* out_hit_id, float* out_t, float* out_normal);
 
 /* ---- tuning / measurement ---------------------------------------------------------------------- */
-/* options: "ray_queue_capacity", "fan_queue_capacity" (records; 0 = auto: 32 Mi records = 1.5 GB per queue side with
- *        sp_path_kernel, 9 GB of queues in all for a scene with one fan class; 24 records per primary of a chunk with
- *        sp_level_kernel), "chunk_primaries" (0 = auto; a chunk that overflows a queue is rendered again at half the
- *        size unless "fixed_chunks" = 1),
+/* options: "ray_queue_capacity", "fan_queue_capacity" (records of 48 B; 0 = auto: 24 records per primary of a chunk,
+ *        i.e. 54 GB of queues for a full 8 Mi-primary chunk of a scene with two fan classes, proportionally less for
+ *        smaller frames), "chunk_primaries" (0 = auto: up to 8 Mi, more for scenes that queue little; a chunk that
+ *        overflows a queue is rendered again at half the size unless "fixed_chunks" = 1),
  * "max_levels" (debugging: trace only the first k recursion depths, 0 = all),
  * "bvh" (1 = scenes with >= 64 colliders put their small colliders into a bounding-volume hierarchy, the
  *        default; 0 = every ray tests every collider),
- * "warp_kernel" (1 = scenes whose colliders fit one staged chunk (+ BVH) run the warp-autonomous sp_path_kernel, the
- *        default; 0 = the CTA-cooperative sp_level_kernel everywhere; same rays, same results) */
+ * "pretrace" (1 = scenes behind a BVH find the nearest hits of every level with sp_trace_kernel ahead of the level
+ *        launch, the default; 0 = inside sp_level_kernel; same hits),
+ * "warp_kernel" (1 = queue-fed levels of small untextured Diffuse / Refractive / Emissive scenes run the
+ *        warp-autonomous sp_warp_kernel, the default; 0 = the CTA-cooperative sp_level_kernel everywhere; same rays,
+ *        same results) */
 int  sp_set_option(sp_scene*, const char* name, int64_t value);
 /* Roofline denominators measured on the bound device: dependent-free FFMA chains (TFLOP/s, 2 flop
  * per FFMA) and a float4 copy (GB/s, read + write bytes). */

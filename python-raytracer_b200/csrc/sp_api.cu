@@ -208,6 +208,7 @@ struct sp_scene {
     std::vector<int32_t> importance, shadow_ids;
     // ---- options ------------------------------------------------------------------------------------
     int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0, opt_bvh = 1, opt_warp = 1;
+    int64_t opt_pretrace = 1;                    // BVH scenes: sp_trace_kernel ahead of every level launch
     int64_t opt_chunk_fixed = 0;                 // 1: a chunk that overflows is an error instead of being retried smaller
     int64_t chunk_limit = 0;                     // learnt from overflows: no chunk larger than this
     uint64_t shape_sig = 0;                      // what the occupancy estimates below were measured on (shape_signature)
@@ -221,6 +222,7 @@ struct sp_scene {
     std::vector<cudaEvent_t> events;
     DevBuf<float4> geom_all, geom_shadow, accum, scratch;
     DevBuf<uint32_t> d_tiles;                    // tile list of the last sp_render_tiles call
+    DevBuf<float2> d_hits;                       // BVH scenes: per-item nearest hits of the level about to run (sp_trace_kernel)
     DevBuf<int> off_all, off_shadow;
     DevBuf<int2> slot_shadow;
     DevBuf<DCollider> d_cols;
@@ -261,7 +263,7 @@ struct sp_scene {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
 
-        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); d_tiles.release(); off_all.release(); off_shadow.release();
+        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); d_tiles.release(); d_hits.release(); off_all.release(); off_shadow.release();
         slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
@@ -1304,6 +1306,16 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
     if (s->opt_max_levels > 0) n_levels = std::min<int>(n_levels, (int)s->opt_max_levels);   // debugging aid
     const int ncl = SP_COUNTS_PER_LEVEL;
     const bool warp = job.run == SP_RUN_FULL && sp_use_warp_kernel(s->d, s->material_set);
+    // scenes behind a BVH: the nearest hits of every level are found by a kernel of their own ahead of the level launch
+    const bool pretrace = job.run == SP_RUN_FULL && s->opt_pretrace && sp_can_pretrace(s->d, s->material_set);
+    if (pretrace) {
+        // items of the widest level: primaries, or queued records times their fan size (from the occupancy seen so far)
+        double per_primary = 1.0 + s->use_ray;
+        for (int c = 0; c < s->d.n_fan_classes; ++c) per_primary = std::max(per_primary, s->use_ray + s->use_fan * s->d.fan_mult[c] * s->d.n_fan_classes);
+        if (s->use_ray == 0.0 && s->use_fan == 0.0) per_primary = 64.0;
+        const size_t want = (size_t)std::min<double>(std::max<double>(1.3 * per_primary * job.n_items, 1 << 20), (double)((size_t)1 << 30));
+        if (s->d_hits.n < want) CUDA_TRY(s->d_hits.alloc(want));
+    }
     CUDA_TRY(cudaMemsetAsync(s->counts.p, 0, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
     for (int L = 0; L < n_levels; ++L) {
@@ -1328,7 +1340,10 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         a.accum = job.accum;
         a.out_hit = job.out_hit; a.out_t = job.out_t; a.out_o = job.out_o; a.out_d = job.out_d; a.out_n = job.out_n;
         a.shadow_slot = s->slot_shadow.p;
+        a.hits = pretrace ? s->d_hits.p : nullptr;
+        a.hits_cap = pretrace ? (uint32_t)std::min<size_t>(s->d_hits.n, 0xFFFFFFFFull) : 0u;
         CUDA_TRY(cudaEventRecord(s->events[L], s->stream));
+        if (pretrace) CUDA_TRY(sp_launch_trace(s->d, a, s->material_set, s->device, s->stream));
         CUDA_TRY(sp_launch_level(s->d, a, s->material_set, L == 0 ? s->grid0 : s->grid_q, s->stream));
     }
     CUDA_TRY(cudaEventRecord(s->events[n_levels], s->stream));
@@ -1362,7 +1377,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
     }
     if (st) {
         st->chunks += 1;
-        st->kernel_launches += (uint64_t)n_levels;
+        st->kernel_launches += (uint64_t)n_levels * (pretrace ? 2u : 1u);
         st->level_kernel_launches += (uint64_t)n_levels;
         if (warp) st->warp_kernel_launches += (uint64_t)(n_levels - 1);
         st->peak_ray_records = std::max<uint64_t>(st->peak_ray_records, peak_r);
@@ -1710,6 +1725,7 @@ int sp_set_option(sp_scene* s, const char* name, int64_t value) {
     else if (!strcmp(name, "fan_queue_capacity")) s->opt_fan_cap = value;
     else if (!strcmp(name, "chunk_primaries")) s->opt_chunk = value;
     else if (!strcmp(name, "fixed_chunks")) s->opt_chunk_fixed = value;
+    else if (!strcmp(name, "pretrace")) s->opt_pretrace = value;
     else if (!strcmp(name, "max_levels")) s->opt_max_levels = value;
     else if (!strcmp(name, "bvh")) {
         s->opt_bvh = value;

@@ -85,6 +85,83 @@ struct IterShared {
 #define SP_TICK(k) do { } while (0)
 #endif
 
+// The ray of work item `item` of a level launch (camera / caller ray at level 0; a queued ray record, or child
+// `item % mult` of a queued fan record, afterwards).  Returns false for items that carry nothing (dead records,
+// zero-weight samples, texels of an edge tile outside the frame).  Deterministic in (scene, args, item): the trace
+// kernel of BVH scenes and the level kernel both call it and see the same ray.
+template <uint32_t FEAT>
+SP_DEV bool sp_item_ray(const DScene& sc, const LevelArgs& a, uint32_t item, uint32_t n_rays, const uint32_t* fan_n, Ray& r) {
+    bool active = true;
+    if ((FEAT & SP_F_LEVEL0) && a.source == SP_SRC_CAMERA) {
+        uint32_t i = (uint32_t)item;
+        uint32_t sample = a.sample_begin + i / a.n_pix;
+        r.pix = a.pix_begin + i % a.n_pix;
+        if (a.tiles) {                                // texel of a tile list -> pixel of the frame
+            const uint32_t ts = a.tile_shift, local = r.pix & ((1u << (2u * ts)) - 1u);
+            const uint32_t tile = __ldg(a.tiles + (r.pix >> (2u * ts)));
+            const uint32_t px = ((tile % a.tiles_x) << ts) + (local & ((1u << ts) - 1u));
+            const uint32_t py = ((tile / a.tiles_x) << ts) + (local >> ts);
+            active = px < (uint32_t)sc.cam.W && py < (uint32_t)sc.cam.H;
+            r.pix = active ? py * (uint32_t)sc.cam.W + px : 0u;
+        }
+        if (active) {
+            r.path = sp_root_path(sample);
+            sp_camera_ray(sc.cam, r.pix, sample, sc.seed_lo, sc.seed_hi, r.o, r.d);
+            r.thr = v3(1.f);
+            r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
+        }
+    } else if ((FEAT & SP_F_LEVEL0) && a.source == SP_SRC_USER) {
+        uint32_t i = a.user_base + (uint32_t)item;
+        r.pix = i;
+        r.path = sp_root_path(0u);
+        r.o = v3(__ldg(a.user_o + 3 * (size_t)i), __ldg(a.user_o + 3 * (size_t)i + 1), __ldg(a.user_o + 3 * (size_t)i + 2));
+        r.d = v3(__ldg(a.user_d + 3 * (size_t)i), __ldg(a.user_d + 3 * (size_t)i + 1), __ldg(a.user_d + 3 * (size_t)i + 2));
+        r.thr = v3(1.f);
+        r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
+    } else if (!(FEAT & SP_F_QUEUES)) {
+        active = false;
+    } else if (item < n_rays) {
+        const uint32_t s = (uint32_t)item;
+        // all three vectors at once: one memory round trip (a dead record's q0 / q1 are simply ignored)
+        const float4 q2 = a.in_rays.q2[s], q0 = a.in_rays.q0[s], q1 = a.in_rays.q1[s];
+        r.meta = __float_as_uint(q2.w);
+        if (r.meta == SP_META_DEAD) {
+            active = false;
+        } else {
+            r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
+            r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
+        }
+    } else if (!(FEAT & SP_F_DIFFUSE)) {
+        active = false;
+    } else {
+        uint32_t local = item - n_rays;
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < SP_MAX_FAN_CLASSES - 1; ++k) {
+            const uint32_t span = fan_n[k] * (uint32_t)sc.fan_mult[k];
+            if (c == k && local >= span) { local -= span; c = k + 1; }
+        }
+        const uint32_t m = (uint32_t)sc.fan_mult[c];
+        const uint32_t rec = (m == 1u) ? local : (uint32_t)__umul64hi((unsigned long long)local, sc.fan_magic[c]);
+        const uint32_t child = local - rec * m;
+        const uint32_t s = a.in_fan_base[c] + rec;
+        const float4 q2 = a.in_fans.q2[s], q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
+        r.meta = __float_as_uint(q2.w);
+        if (r.meta == SP_META_DEAD) {
+            active = false;
+        } else {
+            r.o = xyz(q0); r.thr = xyz(q2);
+            r.pix = __float_as_uint(q0.w);
+            r.path = sp_child_path(__float_as_uint(q1.w), child);
+            const float w_cos = __ldg(&sc.col_info[meta_src(r.meta)].w_cos);
+            const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), w_cos, r.pix, r.path, r.d);
+            r.thr = r.thr * weight;
+            active = weight > 0.f;          // zero-weight samples cannot contribute: not traced
+        }
+    }
+    return active;
+}
+
 template <uint32_t FEAT>
 __global__ void __launch_bounds__(SP_BLOCK, SP_CTAS_PER_SM(FEAT))
 sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
@@ -164,75 +241,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
         r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
 
         // ---- 1. the ray of this item ---------------------------------------------------------
-        if (active) {
-            if ((FEAT & SP_F_LEVEL0) && a.source == SP_SRC_CAMERA) {
-                uint32_t i = (uint32_t)item;
-                uint32_t sample = a.sample_begin + i / a.n_pix;
-                r.pix = a.pix_begin + i % a.n_pix;
-                if (a.tiles) {                                // texel of a tile list -> pixel of the frame
-                    const uint32_t ts = a.tile_shift, local = r.pix & ((1u << (2u * ts)) - 1u);
-                    const uint32_t tile = __ldg(a.tiles + (r.pix >> (2u * ts)));
-                    const uint32_t px = ((tile % a.tiles_x) << ts) + (local & ((1u << ts) - 1u));
-                    const uint32_t py = ((tile / a.tiles_x) << ts) + (local >> ts);
-                    active = px < (uint32_t)sc.cam.W && py < (uint32_t)sc.cam.H;
-                    r.pix = active ? py * (uint32_t)sc.cam.W + px : 0u;
-                }
-                if (active) {
-                    r.path = sp_root_path(sample);
-                    sp_camera_ray(sc.cam, r.pix, sample, sc.seed_lo, sc.seed_hi, r.o, r.d);
-                    r.thr = v3(1.f);
-                    r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
-                }
-            } else if ((FEAT & SP_F_LEVEL0) && a.source == SP_SRC_USER) {
-                uint32_t i = a.user_base + (uint32_t)item;
-                r.pix = i;
-                r.path = sp_root_path(0u);
-                r.o = v3(__ldg(a.user_o + 3 * (size_t)i), __ldg(a.user_o + 3 * (size_t)i + 1), __ldg(a.user_o + 3 * (size_t)i + 2));
-                r.d = v3(__ldg(a.user_d + 3 * (size_t)i), __ldg(a.user_d + 3 * (size_t)i + 1), __ldg(a.user_d + 3 * (size_t)i + 2));
-                r.thr = v3(1.f);
-                r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
-            } else if (!(FEAT & SP_F_QUEUES)) {
-                active = false;
-            } else if (item < n_rays) {
-                const uint32_t s = (uint32_t)item;
-                // all three vectors at once: one memory round trip (a dead record's q0 / q1 are simply ignored)
-                const float4 q2 = a.in_rays.q2[s], q0 = a.in_rays.q0[s], q1 = a.in_rays.q1[s];
-                r.meta = __float_as_uint(q2.w);
-                if (r.meta == SP_META_DEAD) {
-                    active = false;
-                } else {
-                    r.o = xyz(q0); r.d = xyz(q1); r.thr = xyz(q2);
-                    r.pix = __float_as_uint(q0.w); r.path = __float_as_uint(q1.w);
-                }
-            } else if (!(FEAT & SP_F_DIFFUSE)) {
-                active = false;
-            } else {
-                uint32_t local = item - n_rays;
-                int c = 0;
-#pragma unroll
-                for (int k = 0; k < SP_MAX_FAN_CLASSES - 1; ++k) {
-                    const uint32_t span = fan_n[k] * (uint32_t)sc.fan_mult[k];
-                    if (c == k && local >= span) { local -= span; c = k + 1; }
-                }
-                const uint32_t m = (uint32_t)sc.fan_mult[c];
-                const uint32_t rec = (m == 1u) ? local : (uint32_t)__umul64hi((unsigned long long)local, sc.fan_magic[c]);
-                const uint32_t child = local - rec * m;
-                const uint32_t s = a.in_fan_base[c] + rec;
-                const float4 q2 = a.in_fans.q2[s], q0 = a.in_fans.q0[s], q1 = a.in_fans.q1[s];
-                r.meta = __float_as_uint(q2.w);
-                if (r.meta == SP_META_DEAD) {
-                    active = false;
-                } else {
-                    r.o = xyz(q0); r.thr = xyz(q2);
-                    r.pix = __float_as_uint(q0.w);
-                    r.path = sp_child_path(__float_as_uint(q1.w), child);
-                    const float w_cos = __ldg(&sc.col_info[meta_src(r.meta)].w_cos);
-                    const float weight = sp_sample_diffuse(sc, r.o, xyz(q1), w_cos, r.pix, r.path, r.d);
-                    r.thr = r.thr * weight;
-                    active = weight > 0.f;          // zero-weight samples cannot contribute: not traced
-                }
-            }
-        }
+        if (active) active = sp_item_ray<FEAT>(sc, a, item, n_rays, fan_n, r);
         if ((FEAT & SP_F_LEVEL0) && a.run == SP_RUN_DUMP_RAYS) {
             if (active) {
                 const size_t i = (size_t)item;
@@ -260,6 +269,15 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 } else {
                     where = __ldg(&sc.col_info[src].slot);
                 }
+            }
+            if ((FEAT & SP_F_BVH) && need_test && a.hits && total <= a.hits_cap) {
+                // found ahead of this launch by sp_trace_kernel (full occupancy, no barrier behind the slowest traversal)
+                const float2 h = a.hits[item];
+                const uint32_t code = __float_as_uint(h.y);
+                hit.t = h.x;
+                hit.id = (code & 0x7FFFFFFFu) == 0x7FFFFFFFu ? -1 : (int)(code & 0x7FFFFFFFu);
+                hit.orient = (code & 0x80000000u) ? 1 : -1;
+                need_test = false;
             }
             for (int c = 0; c < n_chunks; ++c) {
                 if (n_chunks > 1) {
@@ -464,6 +482,202 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     }
 }
 
+// ---- nearest hits ahead of the level launch (scenes behind a BVH) -----------------------------------------------------
+// BVH traversal lengths differ wildly from ray to ray.  Inside sp_level_kernel every 512-ray batch waits at a barrier
+// for its slowest ray, and a warp that walks 32 rays in lock-step runs with the lanes of its longest ray only (ncu,
+// stress scene: 8 of 32 lanes per instruction).  This kernel does the level's "generate + intersect" half on its
+// own, with *persistent lanes* (Aila & Laine, Understanding the efficiency of ray traversal on GPUs):
+//   * a warp prepares 32 rays at a time with full lanes — sp_item_ray (camera ray / queue record / sampled fan child)
+//     and the walk over the staged chunk of scene-sized colliders, the same calls as the level kernel — and parks
+//     them in a warp-private shared-memory queue;
+//   * every lane traverses the BVH for one ray of its own; a lane whose ray is finished writes (t, id | orientation)
+//     for the work item and pops the next prepared ray, so the lanes stay busy however long their neighbours' rays take;
+//   * one round of the loop = box nodes until the lane holds a leaf, then that leaf's colliders ("while-while").
+// The level launch that follows reads the hits instead of intersecting, and only parks and shades.
+#define SPT_BLOCK 256
+#define SPT_WARPS (SPT_BLOCK / 32)
+#define SPT_BATCH 8                  // groups of 32 items a warp draws per atomic
+#ifndef SPT_CTAS
+#define SPT_CTAS 4                   // resident CTAs per SM the register allocation aims for
+#endif
+#define SPT_REC_WORDS 12             // o d t code src mode item -
+struct TraceShared { uint32_t q[SPT_WARPS][SPT_REC_WORDS][32]; };
+
+// Prepare the rays of items [first, first + 32) (those below `total`) and park the ones that need a BVH traversal in the
+// warp's queue; returns how many were parked.  Rays that carry nothing, and rays that re-hit their own surface at
+// t = 0, need no hit record: the level kernel answers them itself.
+template <uint32_t FEAT>
+__device__ __noinline__ uint32_t sp_trace_prepare(const DScene* scp, const LevelArgs* ap, const float4* s_geom, uint32_t* q,
+                                                  uint32_t first, uint32_t total, uint32_t n_rays, const uint32_t* fan_n_in) {
+    const DScene& sc = *scp;
+    const LevelArgs& a = *ap;
+    const uint32_t lane = threadIdx.x & 31u, item = first + lane;
+    uint32_t fan_n[SP_MAX_FAN_CLASSES];
+#pragma unroll
+    for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) fan_n[c] = fan_n_in[c];
+    Ray r;
+    r.o = r.d = r.thr = v3(0.f); r.pix = 0; r.path = 0; r.meta = 0;
+    bool active = item < total;
+    if (active) active = sp_item_ray<FEAT>(sc, a, item, n_rays, fan_n, r);
+    const uint32_t src = meta_src(r.meta), mode = meta_mode(r.meta);
+    if (src != SP_SRC_NONE && mode == SP_SELF_ZERO) active = false;
+    ChunkBest best; best.t = SP_INF; best.idx = -1; best.orient = 0;
+    int hit_id = -1;
+    if (active) {
+        SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = self.aa = -1; self.mode = mode;
+        if (src != SP_SRC_NONE) {
+            const uint32_t where = __ldg(&sc.col_info[src].slot);
+            if ((where >> 24) == 0u) {
+                const int ty = (int)((where >> 20) & 15u), li = (int)(where & 0xFFFFFu);
+                if (ty == 0) self.sphere = li; else if (ty == 1) self.plane = li;
+                else if (ty == 2) self.cuboid = li; else if (ty == 3) self.tri = li; else self.aa = li;
+            }
+        }
+        sp_intersect_chunk(s_geom, r.o, r.d, self, best);
+        if (best.idx >= 0) hit_id = sp_chunk_id(s_geom, best.idx);
+    }
+    const uint32_t keep = __ballot_sync(0xffffffffu, active);
+    if (active) {
+        const uint32_t j = __popc(keep & ((1u << lane) - 1u));
+        q[0 * 32 + j] = __float_as_uint(r.o.x); q[1 * 32 + j] = __float_as_uint(r.o.y); q[2 * 32 + j] = __float_as_uint(r.o.z);
+        q[3 * 32 + j] = __float_as_uint(r.d.x); q[4 * 32 + j] = __float_as_uint(r.d.y); q[5 * 32 + j] = __float_as_uint(r.d.z);
+        q[6 * 32 + j] = __float_as_uint(best.t);
+        q[7 * 32 + j] = (hit_id < 0 ? 0x7FFFFFFFu : (uint32_t)hit_id) | (best.orient > 0 ? 0x80000000u : 0u);
+        q[8 * 32 + j] = src == SP_SRC_NONE ? 0xFFFFFFFFu : src;
+        q[9 * 32 + j] = mode;
+        q[10 * 32 + j] = item;
+    }
+    __syncwarp();
+    return __popc(keep);
+}
+
+template <uint32_t FEAT>
+__global__ void __launch_bounds__(SPT_BLOCK, SPT_CTAS)
+sp_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
+    extern __shared__ float4 s_geom[];
+    __shared__ TraceShared sh;
+    if (*reinterpret_cast<volatile const unsigned int*>(&a.out.stats->overflow) & 0xFFFFu) return;
+    uint32_t n_rays = 0, fan_n[SP_MAX_FAN_CLASSES], total;
+#pragma unroll
+    for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c) fan_n[c] = 0;
+    if ((FEAT & SP_F_QUEUES) && a.source == SP_SRC_QUEUES) {
+        n_rays = min(__ldg(a.in_counts), a.in_rays.capacity);
+        total = n_rays;
+#pragma unroll
+        for (int c = 0; c < SP_MAX_FAN_CLASSES; ++c)
+            if (c < sc.n_fan_classes) {
+                fan_n[c] = min(__ldg(a.in_counts + 1 + c), a.in_fan_cap[c]);
+                total += fan_n[c] * (uint32_t)sc.fan_mult[c];
+            }
+    } else {
+        total = a.n_items0;
+    }
+    if (total == 0u || total > a.hits_cap) return;           // too many items for the hit array: the level kernel intersects itself
+    for (int i = threadIdx.x, n = __ldg(sc.all.chunk_off + 1) - __ldg(sc.all.chunk_off); i < n; i += SPT_BLOCK) s_geom[i] = __ldg(sc.all.data + i);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* const q = &sh.q[threadIdx.x >> 5][0][0];
+    uint32_t* const work = const_cast<uint32_t*>(a.in_counts) + SP_COUNTS_PER_LEVEL / 2 + 1;
+    const DBvh& bvh = sc.bvh;
+
+    uint32_t q_n = 0;                                        // prepared rays waiting in the warp's queue (warp-uniform)
+    uint32_t wb = 0, wend = 0;                               // the warp's current batch of items
+    bool drained = false;                                    // the launch has no more items for this warp
+    // the lane's ray and where its traversal stands
+    bool have = false;
+    float3 O = v3(0.f), D = v3(0.f), inv = v3(0.f);
+    ChunkBest best; best.t = SP_INF; best.idx = -1; best.orient = 0;
+    int src_id = -1, node = SP_BVH_DONE, sp = 0;
+    uint32_t mode = 0u, item = 0u;
+    int stack[32];
+
+    while (true) {
+        // ---- idle lanes pop prepared rays; the queue is refilled with full lanes when it runs dry -----------------------
+        uint32_t idle = __ballot_sync(0xffffffffu, !have);
+        while (idle && !(drained && q_n == 0u)) {
+            if (q_n == 0u) {
+                if (wb == wend) {
+                    uint32_t nb = 0;
+                    if (lane == 0) nb = atomicAdd(work, 32u * SPT_BATCH);
+                    nb = __shfl_sync(0xffffffffu, nb, 0);
+                    if (nb >= total) { drained = true; break; }
+                    wb = nb; wend = min(nb + 32u * SPT_BATCH, total);
+                }
+                q_n = sp_trace_prepare<FEAT>(&sc, &a, s_geom, q, wb, total, n_rays, fan_n);
+                wb = min(wb + 32u, wend);
+                continue;
+            }
+            const uint32_t take = min((uint32_t)__popc(idle), q_n), rank = __popc(idle & ((1u << lane) - 1u));
+            if (!have && rank < take) {
+                const uint32_t j = q_n - 1u - rank;
+                O = v3(__uint_as_float(q[0 * 32 + j]), __uint_as_float(q[1 * 32 + j]), __uint_as_float(q[2 * 32 + j]));
+                D = v3(__uint_as_float(q[3 * 32 + j]), __uint_as_float(q[4 * 32 + j]), __uint_as_float(q[5 * 32 + j]));
+                best.t = __uint_as_float(q[6 * 32 + j]);
+                const uint32_t code = q[7 * 32 + j];
+                best.idx = (code & 0x7FFFFFFFu) == 0x7FFFFFFFu ? -1 : (int)(code & 0x7FFFFFFFu);
+                best.orient = (code & 0x80000000u) ? 1 : -1;
+                src_id = (int)q[8 * 32 + j];
+                mode = q[9 * 32 + j];
+                item = q[10 * 32 + j];
+                inv = v3(fast_rcp(D.x), fast_rcp(D.y), fast_rcp(D.z));
+                node = 0; sp = 0;
+                have = true;
+            }
+            __syncwarp();
+            q_n -= take;
+            idle = __ballot_sync(0xffffffffu, !have);
+        }
+        if (__ballot_sync(0xffffffffu, have) == 0u) break;   // nothing in flight, nothing left to fetch
+
+        // ---- one round of the traversal (sp_bvh_nearest, resumable) -----------------------------------------------------
+        if (have) {
+            while (node >= 0 && node != SP_BVH_DONE) {       // box nodes until a leaf (or nothing) is at hand
+                const float4 n0 = __ldg(bvh.nodes + 4 * node), n1 = __ldg(bvh.nodes + 4 * node + 1);
+                const float4 n2 = __ldg(bvh.nodes + 4 * node + 2), n3 = __ldg(bvh.nodes + 4 * node + 3);
+                float ta, tb;
+                const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), O, inv, best.t, ta);
+                const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), O, inv, best.t, tb);
+                int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
+                if (ha && hb) {
+                    if (tb < ta) { const int c = ca; ca = cb; cb = c; }
+                    stack[sp++] = cb;
+                    node = ca;
+                } else if (ha || hb) {
+                    node = ha ? ca : cb;
+                } else {
+                    node = sp ? stack[--sp] : SP_BVH_DONE;
+                }
+            }
+            if (node != SP_BVH_DONE) {                       // the leaf's colliders
+                const int code = ~node, count = (code & 7) + 1;
+                const float4* rec = bvh.data + (code >> 3);
+                for (int i = 0; i < count; ++i) {
+                    const float4 head = __ldg(rec);
+                    const int kind = __float_as_int(head.x), id = __float_as_int(head.y);
+                    const float4* d = rec + 1;
+                    rec = d + __float_as_int(head.z);
+                    const bool is_self = id == src_id;
+                    switch (kind & 255) {
+                    case SP_ST_SPHERE: sp_item_sphere(__ldg(d), O, D, is_self, mode, id, best); break;
+                    case SP_ST_PLANE: sp_item_plane(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), O, D, is_self, id, best); break;
+                    case SP_ST_CUBOID: sp_item_cuboid(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), __ldg(d + 4), O, D, is_self, mode, id, best); break;
+                    case SP_ST_TRI: sp_item_triangle(__ldg(d), __ldg(d + 1), __ldg(d + 2), O, D, is_self, id, best); break;
+                    case SP_ST_AAX: sp_item_aa<0>(__ldg(d), __ldg(d + 1), O, D, inv.x, is_self, id, best); break;
+                    case SP_ST_AAY: sp_item_aa<1>(__ldg(d), __ldg(d + 1), O, D, inv.y, is_self, id, best); break;
+                    default: sp_item_aa<2>(__ldg(d), __ldg(d + 1), O, D, inv.z, is_self, id, best); break;
+                    }
+                }
+                node = sp ? stack[--sp] : SP_BVH_DONE;
+            }
+            if (node == SP_BVH_DONE) {                       // this ray is done: its hit for the level kernel
+                const uint32_t code = (best.idx < 0 ? 0x7FFFFFFFu : (uint32_t)best.idx) | (best.orient > 0 ? 0x80000000u : 0u);
+                a.hits[item] = make_float2(best.t, __uint_as_float(code));
+                have = false;
+            }
+        }
+    }
+}
+
 #include "sp_warp_kernel.cuh"
 
 // ---- frame resolve: average, sRGB OETF, per-pixel max normalisation, truncation to uint8 ---------
@@ -608,6 +822,29 @@ cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t mater
         return cudaGetLastError();
     }
     level_kernel(material_set, a.source != SP_SRC_QUEUES)<<<grid, SP_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
+    return cudaGetLastError();
+}
+
+bool sp_can_pretrace(const DScene& sc, uint32_t material_set) {
+    static const bool enabled = [] { const char* e = getenv("SIGHTPY_PRETRACE"); return !(e && e[0] == '0'); }();
+    return enabled && material_set == SP_SET_ALL_BVH && sc.bvh.n_nodes > 0 && sc.all.n_chunks == 1;
+}
+
+cudaError_t sp_launch_trace(const DScene& sc, const LevelArgs& a, uint32_t material_set, int device, cudaStream_t st) {
+    (void)material_set;
+    static int grid[16] = {0};
+    auto k0 = sp_trace_kernel<SP_SET_ALL_BVH | SP_F_LEVEL0>;
+    auto kq = sp_trace_kernel<SP_SET_ALL_BVH | SP_F_QUEUES>;
+    auto k = a.source != SP_SRC_QUEUES ? k0 : kq;
+    if (grid[device & 15] == 0) {
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
+        cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kq, SPT_BLOCK, (size_t)SP_CHUNK_VEC4 * sizeof(float4)) != cudaSuccess || per_sm < 1) per_sm = 1;
+        grid[device & 15] = sms * per_sm;
+    }
+    k<<<grid[device & 15], SPT_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
     return cudaGetLastError();
 }
 

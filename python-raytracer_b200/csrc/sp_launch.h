@@ -31,6 +31,10 @@ struct LevelArgs {
     int32_t* out_hit; float* out_t; float* out_o; float* out_d;
     float* out_n;                  // oriented collider normal at the primary hit, 3 floats per item (sp_aovs)
     const int2* shadow_slot;
+    // BVH scenes: nearest hits found ahead of the level launch by sp_trace_kernel, one per work item:
+    // (t, collider id | outer face << 31; id 0x7FFFFFFF = miss).  Used when the launch has at most hits_cap items.
+    float2* hits;
+    uint32_t hits_cap;
 };
 
 struct ResolveArgs {
@@ -45,6 +49,8 @@ uint32_t sp_pick_material_set(uint32_t needed_features);          // smallest co
 bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set);      // queue-fed levels run sp_warp_kernel (sp_warp_kernel.cuh)
 int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0);   // CTAs of a persistent launch
 cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st);
+bool sp_can_pretrace(const DScene& sc, uint32_t material_set);           // scene behind a BVH with one staged chunk
+cudaError_t sp_launch_trace(const DScene& sc, const LevelArgs& a, uint32_t material_set, int device, cudaStream_t st);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
 cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st);   // accum += scratch; scratch = 0
 cudaError_t sp_launch_add(float4* accum, const float4* other, uint32_t n_pix, cudaStream_t st);   // accum.xyz += other.xyz (other may be peer memory)

@@ -87,7 +87,8 @@ class FlatScene:
         budget, of which a path has at most max_diffuse_reflections."""
         d = int(self.primitives["max_ray_depth"].max()) if len(self.primitives) else 0
         dif = self.materials["kind"] == MAT_DIFFUSE
-        extra = int(self.materials["max_diffuse_reflections"][dif].max()) if dif.any() else 0
+        # a first Diffuse hit always fans out, whatever max_diffuse_reflections says (diffuse.py:34)
+        extra = max(int(self.materials["max_diffuse_reflections"][dif].max()), 1) if dif.any() else 0
         return d + extra + 1
 
 

@@ -893,3 +893,29 @@ def test_device_skybox_blur_is_byte_identical_to_the_reference_blur():
         nat.close()
         want = blur_skybox_u8(raw, radius)
         assert np.array_equal(got, want), (n, radius, int((got != want).sum()))
+
+
+def test_pretraced_hits_equal_inline_intersection():
+    """Scenes behind a BVH find the nearest hits of every level with sp_trace_kernel ahead of the level launch (option
+    "pretrace" = 1, the default); with 0 sp_level_kernel intersects inside its own loop.  Same sp_item_ray /
+    sp_intersect_chunk / sp_bvh_nearest calls either way: identical hit ids, distances, ray counts, and radiance up
+    to the order of the float additions — for caller rays, for a rendered frame, and when the hit array is too small
+    for a launch (tiny chunk after a large one is not needed: the capacity check is per launch)."""
+    import scenes
+    import sightpy
+    from sightpy.backend import NativeScene
+    flat = flatten_scene(scenes.stress(sightpy, width=96, height=64, n_spheres=500, n_triangles=150, n_collections=2))
+    nat = NativeScene(flat)
+    o, d = nat.camera_rays(sample=0, seed=4)
+    pre = nat.trace(o, d, seed=4)
+    _, frame_pre, st_pre = nat.render(2, seed=8)
+    nat.set_option("pretrace", 0)
+    inl = nat.trace(o, d, seed=4)
+    _, frame_inl, st_inl = nat.render(2, seed=8)
+    nat.close()
+    assert st_pre["kernel_launches"] > st_inl["kernel_launches"]          # the trace launches are there
+    assert np.array_equal(pre["hit_id"], inl["hit_id"]) and np.array_equal(pre["t"], inl["t"])
+    assert pre["stats"]["rays_per_depth"] == inl["stats"]["rays_per_depth"]
+    assert st_pre["rays_per_depth"] == st_inl["rays_per_depth"] and st_pre["shadow_rays"] == st_inl["shadow_rays"]
+    np.testing.assert_allclose(pre["rgb"], inl["rgb"], rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(frame_pre, frame_inl, rtol=2e-4, atol=1e-5)
