@@ -222,6 +222,8 @@ struct sp_scene {
     std::vector<cudaEvent_t> events;
     DevBuf<float4> geom_all, geom_shadow, accum, scratch;
     DevBuf<uint32_t> d_tiles;                    // tile list of the last sp_render_tiles call
+    DevBuf<float4> d_shq;                        // BVH scenes: shadow-ray requests of the level that just ran (sp_shadow_kernel)
+    DevBuf<uint32_t> d_shq_count;                // per level: requests queued, work counter
     DevBuf<float2> d_hits;                       // BVH scenes: per-item nearest hits of the level about to run (sp_trace_kernel)
     DevBuf<int> off_all, off_shadow;
     DevBuf<int2> slot_shadow;
@@ -263,7 +265,7 @@ struct sp_scene {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
 
-        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); d_tiles.release(); d_hits.release(); off_all.release(); off_shadow.release();
+        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); d_tiles.release(); d_hits.release(); d_shq.release(); d_shq_count.release(); off_all.release(); off_shadow.release();
         slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
@@ -500,7 +502,8 @@ static int bvh_build_rec(BuiltBvh& out, std::vector<int>& order, int first, int 
             bounds.lo[k] = std::min(bounds.lo[k], boxes[order[i]].lo[k]);
             bounds.hi[k] = std::max(bounds.hi[k], boxes[order[i]].hi[k]);
         }
-    if (count <= 4) {                    // leaf: its items become consecutive in the item array, by type, then by id
+    static const int leaf_max = [] { const char* e = getenv("SIGHTPY_BVH_LEAF"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+    if (count <= leaf_max) {             // leaf: its items become consecutive in the item array, by type, then by id
         const int at = (int)out.items.size();
         std::sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {
             const int ta = item_of[a] & 255, tb = item_of[b] & 255;
@@ -869,6 +872,15 @@ int sp_scene_set_camera(sp_scene* s, const sp_camera* cam) {
     return 0;
 }
 
+// what primary-ray generation would otherwise divide by, per ray (sp_camera_ray)
+static void derive_camera(DCamera& c) {
+    c.w_magic = c.W > 1 ? (~0ull) / (unsigned long long)c.W + 1ull : 0ull;     // W == 1 is special-cased on the device
+    c.step_x = c.W > 1 ? (float)((double)c.cam_w / (double)(c.W - 1)) : 0.f;
+    c.step_y = c.H > 1 ? (float)((double)c.cam_h / (double)(c.H - 1)) : 0.f;
+    c.jitter_x = (float)((double)c.cam_w / (double)c.W);
+    c.jitter_y = (float)((double)c.cam_h / (double)c.H);
+}
+
 int sp_scene_update_camera(sp_scene* s, const sp_camera* cam) {
     SP_ENTER(s ? s->device : (g_device >= 0 ? g_device : 0));
     if (!s || !cam) return fail("sp_scene_update_camera: invalid arguments");
@@ -881,6 +893,7 @@ int sp_scene_update_camera(sp_scene* s, const sp_camera* cam) {
     c.look_from = f3(cam->look_from); c.right = f3(cam->right); c.up = f3(cam->up); c.fwd = f3(cam->fwd);
     c.cam_w = (float)cam->cam_w; c.cam_h = (float)cam->cam_h; c.lens_radius = (float)cam->lens_radius;
     c.focal_distance = (float)cam->focal_distance;
+    derive_camera(c);
     return 0;
 }
 
@@ -1219,6 +1232,7 @@ int sp_scene_commit(sp_scene* s) {
         d.cam.look_from = f3(c.look_from); d.cam.right = f3(c.right); d.cam.up = f3(c.up); d.cam.fwd = f3(c.fwd);
         d.cam.cam_w = (float)c.cam_w; d.cam.cam_h = (float)c.cam_h; d.cam.lens_radius = (float)c.lens_radius;
         d.cam.focal_distance = (float)c.focal_distance; d.cam.W = c.width; d.cam.H = c.height;
+        derive_camera(d.cam);
         CUDA_TRY(s->accum.alloc((size_t)c.width * c.height));
         CUDA_TRY(cudaMemset(s->accum.p, 0, s->accum.n * sizeof(float4)));
     }
@@ -1315,7 +1329,16 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         if (s->use_ray == 0.0 && s->use_fan == 0.0) per_primary = 64.0;
         const size_t want = (size_t)std::min<double>(std::max<double>(1.3 * per_primary * job.n_items, 1 << 20), (double)((size_t)1 << 30));
         if (s->d_hits.n < want) CUDA_TRY(s->d_hits.alloc(want));
+        // shadow-ray requests of one level: at most one per item and light; a quarter of the items' worth is kept (a
+        // request that finds the queue full is traversed inside the level kernel instead)
+        if (s->d.n_lights > 0 && s->d.n_shadow_casters > 0) {
+            const size_t want_sh = std::min<size_t>(std::max<size_t>(want / 4, (size_t)1 << 20), (size_t)128 << 20);
+            if (s->d_shq.n < 3 * want_sh) CUDA_TRY(s->d_shq.alloc(3 * want_sh));
+            if (s->d_shq_count.n < 2 * (size_t)SP_MAX_LEVELS) CUDA_TRY(s->d_shq_count.alloc(2 * (size_t)SP_MAX_LEVELS));
+            CUDA_TRY(cudaMemsetAsync(s->d_shq_count.p, 0, s->d_shq_count.n * sizeof(uint32_t), s->stream));
+        }
     }
+    const bool defer_shadows = pretrace && s->d_shq.p && s->d.n_lights > 0 && s->d.n_shadow_casters > 0;
     CUDA_TRY(cudaMemsetAsync(s->counts.p, 0, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
     for (int L = 0; L < n_levels; ++L) {
@@ -1325,6 +1348,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         a.source = (L == 0) ? job.source : SP_SRC_QUEUES;
         a.pix_begin = job.pix_begin; a.n_pix = job.n_pix; a.sample_begin = job.sample_begin;
         a.n_items0 = job.n_items; a.user_base = job.user_base; a.user_o = job.user_o; a.user_d = job.user_d;
+        a.n_pix_magic = job.n_pix > 1u ? (~0ull) / (unsigned long long)job.n_pix + 1ull : 0ull;
         a.tiles = job.tiles; a.tile_shift = job.tile_shift; a.tiles_x = job.tiles_x;
         a.in_rays = s->ray_q[L & 1].view(s->ray_cap);
         a.in_fans = s->fan_q[L & 1].view(s->fan_cap * s->d.n_fan_classes);
@@ -1343,8 +1367,12 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         a.hits = pretrace ? s->d_hits.p : nullptr;
         a.hits_cap = pretrace ? (uint32_t)std::min<size_t>(s->d_hits.n, 0xFFFFFFFFull) : 0u;
         CUDA_TRY(cudaEventRecord(s->events[L], s->stream));
+        a.shq = defer_shadows ? s->d_shq.p : nullptr;
+        a.shq_cap = defer_shadows ? (uint32_t)std::min<size_t>(s->d_shq.n / 3, 0xFFFFFFFFull) : 0u;
+        a.shq_count = defer_shadows ? s->d_shq_count.p + 2 * (size_t)L : nullptr;
         if (pretrace) CUDA_TRY(sp_launch_trace(s->d, a, s->material_set, s->device, s->stream));
         CUDA_TRY(sp_launch_level(s->d, a, s->material_set, L == 0 ? s->grid0 : s->grid_q, s->stream));
+        if (defer_shadows) CUDA_TRY(sp_launch_shadow(s->d, a, s->device, s->stream));
     }
     CUDA_TRY(cudaEventRecord(s->events[n_levels], s->stream));
     std::vector<uint32_t> counts((size_t)(n_levels + 1) * ncl);
@@ -1377,7 +1405,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
     }
     if (st) {
         st->chunks += 1;
-        st->kernel_launches += (uint64_t)n_levels * (pretrace ? 2u : 1u);
+        st->kernel_launches += (uint64_t)n_levels * (pretrace ? (defer_shadows ? 3u : 2u) : 1u);
         st->level_kernel_launches += (uint64_t)n_levels;
         if (warp) st->warp_kernel_launches += (uint64_t)(n_levels - 1);
         st->peak_ray_records = std::max<uint64_t>(st->peak_ray_records, peak_r);

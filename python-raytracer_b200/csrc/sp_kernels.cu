@@ -93,9 +93,10 @@ template <uint32_t FEAT>
 SP_DEV bool sp_item_ray(const DScene& sc, const LevelArgs& a, uint32_t item, uint32_t n_rays, const uint32_t* fan_n, Ray& r) {
     bool active = true;
     if ((FEAT & SP_F_LEVEL0) && a.source == SP_SRC_CAMERA) {
-        uint32_t i = (uint32_t)item;
-        uint32_t sample = a.sample_begin + i / a.n_pix;
-        r.pix = a.pix_begin + i % a.n_pix;
+        const uint32_t i = (uint32_t)item;
+        const uint32_t si = a.n_pix > 1u ? (uint32_t)__umul64hi((unsigned long long)i, a.n_pix_magic) : i;   // i / n_pix
+        const uint32_t sample = a.sample_begin + si;
+        r.pix = a.pix_begin + (i - si * a.n_pix);
         if (a.tiles) {                                // texel of a tile list -> pixel of the frame
             const uint32_t ts = a.tile_shift, local = r.pix & ((1u << (2u * ts)) - 1u);
             const uint32_t tile = __ldg(a.tiles + (r.pix >> (2u * ts)));
@@ -106,7 +107,7 @@ SP_DEV bool sp_item_ray(const DScene& sc, const LevelArgs& a, uint32_t item, uin
         }
         if (active) {
             r.path = sp_root_path(sample);
-            sp_camera_ray(sc.cam, r.pix, sample, sc.seed_lo, sc.seed_hi, r.o, r.d);
+            sp_camera_ray(sc.cam, r.pix, sample, sc.philox_keys, r.o, r.d);
             r.thr = v3(1.f);
             r.meta = sp_pack_meta(0u, 0u, 0u, SP_SRC_NONE, SP_SELF_SKIP);
         }
@@ -201,6 +202,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     const uint32_t lt_mask = (1u << lane) - 1u;
     ShadeCtx ctx;
     ctx.sc = &sc; ctx.out = &a.out; ctx.shadow_slot = a.shadow_slot;
+    ctx.shq = a.shq; ctx.shq_cap = a.shq_cap; ctx.shq_count = a.shq_count;
     ctx.shadow_rays = 0;
     unsigned long long traced = 0;
 
@@ -678,6 +680,153 @@ sp_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     }
 }
 
+// ---- shadow rays of Glossy hits, after the level launch (scenes behind a BVH) -----------------------------------------
+// The requests the shading phase queued (LevelArgs::shq) are answered with the same persistent-lane scheme as
+// sp_trace_kernel: 32 requests at a time are loaded and walked over the shadow-caster stream with full lanes, then
+// every lane runs the any-hit BVH traversal of one request and takes the next when it is done; a light that is
+// visible adds the radiance the request carries to its pixel (glossy.py:53-57: nearest shadow-caster distance >= the
+// distance to the light).
+__global__ void __launch_bounds__(SPT_BLOCK, SPT_CTAS)
+sp_shadow_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelArgs a) {
+    __shared__ TraceShared sh;
+    const uint32_t total = min(a.shq_count[0], a.shq_cap);
+    if (total == 0u) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* const q = &sh.q[threadIdx.x >> 5][0][0];
+    uint32_t* const work = a.shq_count + 1;
+    const DBvh& bvh = sc.bvh;
+    uint32_t q_n = 0, wb = 0, wend = 0;
+    bool drained = false, have = false;
+    float3 O = v3(0.f), D = v3(0.f), inv = v3(0.f), contrib = v3(0.f);
+    float dist = 0.f;
+    ChunkBest best; best.t = SP_INF; best.idx = -1; best.orient = 0;
+    int src_id = -1, node = SP_BVH_DONE, sp = 0;
+    uint32_t mode = 0u, pix = 0u;
+    int stack[32];
+
+    while (true) {
+        uint32_t idle = __ballot_sync(0xffffffffu, !have);
+        while (idle && !(drained && q_n == 0u)) {
+            if (q_n == 0u) {
+                if (wb == wend) {
+                    uint32_t nb = 0;
+                    if (lane == 0) nb = atomicAdd(work, 32u * SPT_BATCH);
+                    nb = __shfl_sync(0xffffffffu, nb, 0);
+                    if (nb >= total) { drained = true; break; }
+                    wb = nb; wend = min(nb + 32u * SPT_BATCH, total);
+                }
+                // prepare: load 32 requests, walk the shadow-caster stream (colliders outside the BVH) with full lanes,
+                // park the ones whose light is not yet known to be hidden
+                const uint32_t i = wb + lane;
+                bool keep_it = false;
+                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+                float t_stream = SP_INF;
+                if (i < wend) {
+                    r0 = a.shq[3 * (size_t)i]; r1 = a.shq[3 * (size_t)i + 1]; r2 = a.shq[3 * (size_t)i + 2];
+                    const uint32_t code = __float_as_uint(r2.w);
+                    const int sid = (int)(code >> 2);
+                    ChunkBest b0; b0.t = SP_INF; b0.idx = -1; b0.orient = 0;
+                    const int2 where = a.shadow_slot ? __ldg(a.shadow_slot + sid) : make_int2(-1, -1);
+                    for (int c = 0; c < sc.shadow.n_chunks; ++c) {
+                        const float4* ch = sc.shadow.data + __ldg(sc.shadow.chunk_off + c);
+                        SelfSlot self; self.sphere = self.plane = self.cuboid = self.tri = self.aa = -1; self.mode = code & 3u;
+                        if (where.x == c) {
+                            const int ty = where.y >> 28, li = where.y & 0x0FFFFFFF;
+                            if (ty == 0) self.sphere = li; else if (ty == 1) self.plane = li;
+                            else if (ty == 2) self.cuboid = li; else if (ty == 3) self.tri = li; else self.aa = li;
+                        }
+                        sp_intersect_chunk(ch, xyz(r0), xyz(r1), self, b0);
+                    }
+                    t_stream = b0.t;
+                    keep_it = !(t_stream < r0.w);                 // already hidden by a collider of the stream: nothing to add
+                }
+                const uint32_t keep = __ballot_sync(0xffffffffu, keep_it);
+                if (keep_it) {
+                    const uint32_t j = __popc(keep & ((1u << lane) - 1u));
+                    q[0 * 32 + j] = __float_as_uint(r0.x); q[1 * 32 + j] = __float_as_uint(r0.y); q[2 * 32 + j] = __float_as_uint(r0.z);
+                    q[3 * 32 + j] = __float_as_uint(r1.x); q[4 * 32 + j] = __float_as_uint(r1.y); q[5 * 32 + j] = __float_as_uint(r1.z);
+                    q[6 * 32 + j] = __float_as_uint(r0.w); q[7 * 32 + j] = __float_as_uint(r1.w);
+                    q[8 * 32 + j] = __float_as_uint(r2.x); q[9 * 32 + j] = __float_as_uint(r2.y); q[10 * 32 + j] = __float_as_uint(r2.z);
+                    q[11 * 32 + j] = __float_as_uint(r2.w);
+                }
+                __syncwarp();
+                q_n = __popc(keep);
+                wb = min(wb + 32u, wend);
+                continue;
+            }
+            const uint32_t take = min((uint32_t)__popc(idle), q_n), rank = __popc(idle & ((1u << lane) - 1u));
+            if (!have && rank < take) {
+                const uint32_t j = q_n - 1u - rank;
+                O = v3(__uint_as_float(q[0 * 32 + j]), __uint_as_float(q[1 * 32 + j]), __uint_as_float(q[2 * 32 + j]));
+                D = v3(__uint_as_float(q[3 * 32 + j]), __uint_as_float(q[4 * 32 + j]), __uint_as_float(q[5 * 32 + j]));
+                dist = __uint_as_float(q[6 * 32 + j]); pix = q[7 * 32 + j];
+                contrib = v3(__uint_as_float(q[8 * 32 + j]), __uint_as_float(q[9 * 32 + j]), __uint_as_float(q[10 * 32 + j]));
+                const uint32_t code = q[11 * 32 + j];
+                src_id = (int)(code >> 2); mode = code & 3u;
+                inv = v3(fast_rcp(D.x), fast_rcp(D.y), fast_rcp(D.z));
+                best.t = dist; best.idx = -1; best.orient = 0;       // only casters nearer than the light matter
+                node = 0; sp = 0;
+                have = true;
+            }
+            __syncwarp();
+            q_n -= take;
+            idle = __ballot_sync(0xffffffffu, !have);
+        }
+        if (__ballot_sync(0xffffffffu, have) == 0u) break;
+
+        if (have) {                                              // one round of the any-hit traversal (sp_bvh_nearest, casters only)
+            while (node >= 0 && node != SP_BVH_DONE) {
+                const float4 n0 = __ldg(bvh.nodes + 4 * node), n1 = __ldg(bvh.nodes + 4 * node + 1);
+                const float4 n2 = __ldg(bvh.nodes + 4 * node + 2), n3 = __ldg(bvh.nodes + 4 * node + 3);
+                float ta, tb;
+                const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), O, inv, best.t, ta);
+                const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), O, inv, best.t, tb);
+                int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
+                if (ha && hb) {
+                    if (tb < ta) { const int c = ca; ca = cb; cb = c; }
+                    stack[sp++] = cb;
+                    node = ca;
+                } else if (ha || hb) {
+                    node = ha ? ca : cb;
+                } else {
+                    node = sp ? stack[--sp] : SP_BVH_DONE;
+                }
+            }
+            if (node != SP_BVH_DONE) {
+                const int code = ~node, count = (code & 7) + 1;
+                const float4* rec = bvh.data + (code >> 3);
+                for (int i = 0; i < count; ++i) {
+                    const float4 head = __ldg(rec);
+                    const int kind = __float_as_int(head.x), id = __float_as_int(head.y);
+                    const float4* d = rec + 1;
+                    rec = d + __float_as_int(head.z);
+                    if (!(kind & 256)) continue;                     // not a shadow caster
+                    const bool is_self = id == src_id;
+                    switch (kind & 255) {
+                    case SP_ST_SPHERE: sp_item_sphere(__ldg(d), O, D, is_self, mode, id, best); break;
+                    case SP_ST_PLANE: sp_item_plane(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), O, D, is_self, id, best); break;
+                    case SP_ST_CUBOID: sp_item_cuboid(__ldg(d), __ldg(d + 1), __ldg(d + 2), __ldg(d + 3), __ldg(d + 4), O, D, is_self, mode, id, best); break;
+                    case SP_ST_TRI: sp_item_triangle(__ldg(d), __ldg(d + 1), __ldg(d + 2), O, D, is_self, id, best); break;
+                    case SP_ST_AAX: sp_item_aa<0>(__ldg(d), __ldg(d + 1), O, D, inv.x, is_self, id, best); break;
+                    case SP_ST_AAY: sp_item_aa<1>(__ldg(d), __ldg(d + 1), O, D, inv.y, is_self, id, best); break;
+                    default: sp_item_aa<2>(__ldg(d), __ldg(d + 1), O, D, inv.z, is_self, id, best); break;
+                    }
+                }
+                node = (best.t < dist) ? SP_BVH_DONE : (sp ? stack[--sp] : SP_BVH_DONE);     // hidden: stop at once
+            }
+            if (node == SP_BVH_DONE) {
+                if (!(best.t < dist)) {                              // the light is visible from here
+                    float* px = reinterpret_cast<float*>(a.accum + pix);
+                    if (contrib.x != 0.f) atomicAdd(px, contrib.x);
+                    if (contrib.y != 0.f) atomicAdd(px + 1, contrib.y);
+                    if (contrib.z != 0.f) atomicAdd(px + 2, contrib.z);
+                }
+                have = false;
+            }
+        }
+    }
+}
+
 #include "sp_warp_kernel.cuh"
 
 // ---- frame resolve: average, sRGB OETF, per-pixel max normalisation, truncation to uint8 ---------
@@ -828,6 +977,18 @@ cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t mater
 bool sp_can_pretrace(const DScene& sc, uint32_t material_set) {
     static const bool enabled = [] { const char* e = getenv("SIGHTPY_PRETRACE"); return !(e && e[0] == '0'); }();
     return enabled && material_set == SP_SET_ALL_BVH && sc.bvh.n_nodes > 0 && sc.all.n_chunks == 1;
+}
+
+cudaError_t sp_launch_shadow(const DScene& sc, const LevelArgs& a, int device, cudaStream_t st) {
+    static int grid[16] = {0};
+    if (grid[device & 15] == 0) {
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sp_shadow_kernel, SPT_BLOCK, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        grid[device & 15] = sms * per_sm;
+    }
+    sp_shadow_kernel<<<grid[device & 15], SPT_BLOCK, 0, st>>>(sc, a);
+    return cudaGetLastError();
 }
 
 cudaError_t sp_launch_trace(const DScene& sc, const LevelArgs& a, uint32_t material_set, int device, cudaStream_t st) {

@@ -15,6 +15,7 @@ struct LevelArgs {
     // level 0, camera: item i -> pixel pix_begin + i % n_pix, sample sample_begin + i / n_pix
     // level 0, user rays: item i -> ray user_base + i (interleaved xyz), pixel id = ray index
     uint32_t pix_begin, n_pix, sample_begin, n_items0, user_base;
+    unsigned long long n_pix_magic;   // ceil(2^64 / n_pix): item / n_pix == __umul64hi(item, n_pix_magic)
     // tile-sharded frames (sp_render_tiles): the "pixel" index above runs over the texels of a list of square tiles,
     // tile_size^2 per tile, row-major inside a tile; texels outside the frame (edge tiles) are skipped
     const uint32_t* tiles;         // tile ids (row-major over the frame's tile grid), nullptr = plain pixel indices
@@ -35,6 +36,13 @@ struct LevelArgs {
     // (t, collider id | outer face << 31; id 0x7FFFFFFF = miss).  Used when the launch has at most hits_cap items.
     float2* hits;
     uint32_t hits_cap;
+    // BVH scenes: shadow rays of Glossy hits (glossy.py:53-57) are not traversed inside the shading phase but queued
+    // — origin | distance to the light, direction | pixel, radiance the light adds if it is visible | source collider
+    // and self mode — and answered by sp_shadow_kernel after the level launch.  shq_count[0]: requests queued,
+    // shq_count[1]: that kernel's work counter.  A request that finds the queue full is traversed on the spot.
+    float4* shq;
+    uint32_t shq_cap;
+    uint32_t* shq_count;
 };
 
 struct ResolveArgs {
@@ -50,6 +58,7 @@ bool sp_use_warp_kernel(const DScene& sc, uint32_t material_set);      // queue-
 int sp_level_grid(int device, const DScene& sc, uint32_t material_set, bool level0);   // CTAs of a persistent launch
 cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t material_set, int grid, cudaStream_t st);
 bool sp_can_pretrace(const DScene& sc, uint32_t material_set);           // scene behind a BVH with one staged chunk
+cudaError_t sp_launch_shadow(const DScene& sc, const LevelArgs& a, int device, cudaStream_t st);
 cudaError_t sp_launch_trace(const DScene& sc, const LevelArgs& a, uint32_t material_set, int device, cudaStream_t st);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
 cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st);   // accum += scratch; scratch = 0

@@ -16,22 +16,26 @@ SP_DEV void sp_onb(float3 w, float3& u, float3& v) {
     u = cross(w, v);
 }
 
-SP_DEV void sp_camera_ray(const DCamera& cam, uint32_t pixel, uint32_t sample, uint32_t k0, uint32_t k1,
+SP_DEV void sp_camera_ray(const DCamera& cam, uint32_t pixel, uint32_t sample, const uint32_t* __restrict__ keys,
                           float3& origin, float3& dir) {
     float u[4];
-    sp_draw4(pixel, sp_root_path(sample), SP_BLOCK_DIRECTION, k0, k1, u);
-    int px = (int)(pixel % (uint32_t)cam.W), py = (int)(pixel / (uint32_t)cam.W);
+    sp_draw4_keys(pixel, sp_root_path(sample), SP_BLOCK_DIRECTION, keys, u);
+    const uint32_t py = cam.W > 1 ? (uint32_t)__umul64hi((unsigned long long)pixel, cam.w_magic) : pixel;
+    const uint32_t px = pixel - py * (uint32_t)cam.W;
     // np.linspace(-w/2, w/2, W)[px] and np.linspace(h/2, -h/2, H)[py]
-    float gx = cam.W > 1 ? -0.5f * cam.cam_w + cam.cam_w * ((float)px / (float)(cam.W - 1)) : -0.5f * cam.cam_w;
-    float gy = cam.H > 1 ? 0.5f * cam.cam_h - cam.cam_h * ((float)py / (float)(cam.H - 1)) : 0.5f * cam.cam_h;
-    float x = gx + (u[0] - 0.5f) * cam.cam_w / (float)cam.W;
-    float y = gy + (u[1] - 0.5f) * cam.cam_h / (float)cam.H;
-    float rr = sqrtf(u[2]), sn, cs;
-    sincospif(2.f * u[3], &sn, &cs);
-    float rx = rr * cs * cam.lens_radius, ry = rr * sn * cam.lens_radius;
-    origin = cam.look_from + cam.right * rx + cam.up * ry;
-    float fd = cam.focal_distance;
-    float3 target = cam.look_from + cam.up * (y * fd) + cam.right * (x * fd) + cam.fwd * fd;
+    const float gx = fmaf((float)px, cam.step_x, -0.5f * cam.cam_w);
+    const float gy = fmaf(-(float)py, cam.step_y, 0.5f * cam.cam_h);
+    const float x = fmaf(u[0] - 0.5f, cam.jitter_x, gx);
+    const float y = fmaf(u[1] - 0.5f, cam.jitter_y, gy);
+    origin = cam.look_from;
+    if (cam.lens_radius != 0.f) {                          // thin lens: a point of the aperture disk (random_in_unit_disk)
+        float rr = sqrtf(u[2]), sn, cs;
+        sincospif(2.f * u[3], &sn, &cs);
+        const float rx = rr * cs * cam.lens_radius, ry = rr * sn * cam.lens_radius;
+        origin = cam.look_from + cam.right * rx + cam.up * ry;
+    }
+    const float fd = cam.focal_distance;
+    const float3 target = cam.look_from + cam.up * (y * fd) + cam.right * (x * fd) + cam.fwd * fd;
     dir = normalize0(target - origin);
 }
 

@@ -176,6 +176,7 @@ struct ShadeCtx {
     const int2* shadow_slot;    // collider id -> (chunk, type << 28 | local index) in the shadow-caster stream
     const float* lin_lut;       // shared-memory copy of the sRGB -> linear table
     unsigned long long shadow_rays;
+    float4* shq; uint32_t shq_cap; uint32_t* shq_count;      // deferred shadow rays (LevelArgs::shq), nullptr = traverse inline
     // slots reserved for the hit being shaded
     uint32_t ray_slot, ray_slot1, ray_used, fan_slot;   // ray_slot1: where a second child ray goes
 };
@@ -277,24 +278,43 @@ SP_DEV float3 sp_shade(ShadeCtx& cx_, const Ray& r, const HitRec& h) {
                 lv = lt.color * (NdotL / (dist * dist) * 100.f);
             }
             if (NdotL <= 0.f) continue;                // lv == 0: both light terms vanish
-            float see = 1.f;
+            // what the light adds if it is visible: Lambert + Cook-Torrance (glossy.py:59-84)
+            auto lit = [&]() {
+                float3 c = diff * lv;
+                if (m.roughness != 0.f) {
+                    float3 Hv = normalize0(L + V);
+                    float3 F = sp_schlick(sp_f0(med.re, med.im, m.n_re, m.n_im), clamp01(dot(V, Hv)));
+                    float a = 2.f / (m.roughness * m.roughness) - 2.f;
+                    // Phong lobe x^a: exp2(a log2 x) through the MUFU pipe (relative error ~ a * 2e-7; x^0 = 1 also at x = 0)
+                    float Dp = (a == 0.f ? 1.f : __powf(clamp01(dot(N, Hv)), a)) * (a + 2.f) * (0.5f / SP_PI);
+                    float denom = 4.f * fminf(fmaxf(dot(N, V) * NdotL, 0.001f), 1.f);
+                    c += F * lv * (Dp / denom * m.spec_coeff);
+                }
+                return c;
+            };
             if (sc.n_shadow_casters > 0) {
                 uint32_t mode = sp_self_mode(ctype, side_plus, dot(L, g.Nc), zo);
-                float nearest = (mode == SP_SELF_ZERO) ? 0.f
-                                : sp_shadow_nearest<FEAT>(sc, nudged, L, h.id, mode, dist, cx_.shadow_slot);
-                see = nearest >= dist ? 1.f : 0.f;
                 cx_.shadow_rays++;
+                if (mode == SP_SELF_ZERO) continue;        // the shadow ray starts inside its own surface: occluded
+                if ((FEAT & SP_F_BVH) && cx_.shq) {
+                    // queue the shadow ray for sp_shadow_kernel (one atomic per warp and light)
+                    const uint32_t peers = __activemask(), lane = threadIdx.x & 31u;
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t base = 0;
+                    if ((int)lane == leader) base = atomicAdd(cx_.shq_count, (uint32_t)__popc(peers));
+                    base = __shfl_sync(peers, base, leader) + __popc(peers & ((1u << lane) - 1u));
+                    if (base < cx_.shq_cap) {
+                        const float3 c = r.thr * lit();
+                        cx_.shq[3 * (size_t)base] = make_float4(nudged.x, nudged.y, nudged.z, dist);
+                        cx_.shq[3 * (size_t)base + 1] = make_float4(L.x, L.y, L.z, __uint_as_float(r.pix));
+                        cx_.shq[3 * (size_t)base + 2] = make_float4(c.x, c.y, c.z, __uint_as_float(((uint32_t)h.id << 2) | mode));
+                        continue;
+                    }
+                }
+                float nearest = sp_shadow_nearest<FEAT>(sc, nudged, L, h.id, mode, dist, cx_.shadow_slot);
+                if (nearest < dist) continue;
             }
-            if (see == 0.f) continue;
-            color += diff * lv;
-            if (m.roughness != 0.f) {
-                float3 Hv = normalize0(L + V);
-                float3 F = sp_schlick(sp_f0(med.re, med.im, m.n_re, m.n_im), clamp01(dot(V, Hv)));
-                float a = 2.f / (m.roughness * m.roughness) - 2.f;
-                float Dp = powf(clamp01(dot(N, Hv)), a) * (a + 2.f) / (2.f * SP_PI);
-                float denom = 4.f * fminf(fmaxf(dot(N, V) * NdotL, 0.001f), 1.f);
-                color += F * lv * (Dp / denom * m.spec_coeff);
-            }
+            color += lit();
         }
         add = r.thr * color;
         if ((int)depth < prim.max_ray_depth) {

@@ -100,6 +100,10 @@ struct DCamera {
     float3 look_from, right, up, fwd;
     float cam_w, cam_h, lens_radius, focal_distance;
     int W, H;
+    // derived by the host (divisions are the dearest instructions of primary-ray generation)
+    unsigned long long w_magic;        // ceil(2^64 / W): pixel / W == __umul64hi(pixel, w_magic) for 32-bit pixel indices
+    float step_x, step_y;              // cam_w / (W - 1), cam_h / (H - 1): np.linspace steps (0 for a single column / row)
+    float jitter_x, jitter_y;          // cam_w / W, cam_h / H
 };
 
 #define SP_MAX_FAN_CLASSES 4

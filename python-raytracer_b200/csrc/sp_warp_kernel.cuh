@@ -147,6 +147,7 @@ __device__ __noinline__ void sp_shade_stash(const DScene* scp, const LevelArgs* 
     const uint32_t tot = __popc(b0) + 2u * __popc(b1);
     ShadeCtx ctx;
     ctx.sc = scp; ctx.out = &a.out; ctx.shadow_slot = a.shadow_slot; ctx.lin_lut = nullptr; ctx.shadow_rays = 0;
+    ctx.shq = nullptr; ctx.shq_cap = 0u; ctx.shq_count = nullptr;
     ctx.ray_slot = ctx.ray_slot1 = SP_SLOT_NONE; ctx.ray_used = 0u; ctx.fan_slot = SP_SLOT_NONE;
     if (tot) {
         const SlabGrant g = sp_slab_alloc(slabs, tot, 0u, slab_size < 64u ? 64u : slab_size, a.out, lane);
