@@ -139,7 +139,7 @@ class ClockSampler:
         parsed = []
         for t, r in self.rows:
             try:
-                parsed.append((t, float(r[0]), float(r[1]), r[3:7]))
+                parsed.append((t, float(r[0]), float(r[1]), r[3:7], float(r[2]) if r[2].replace('.', '', 1).isdigit() else None))
             except (ValueError, IndexError):
                 continue
         inside = [p for p in parsed if lo <= p[0] <= hi]
@@ -151,12 +151,15 @@ class ClockSampler:
         if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         reasons = set()
-        for _, _, _, flags in inside:
+        for _, _, _, flags, _ in inside:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         out = {"sm_mhz": statistics.median(p[1] for p in inside), "sm_max_mhz": max(p[2] for p in inside),
                "reasons": sorted(reasons), "samples": len(inside)}
+        watts = [p[4] for p in inside if p[4] is not None]
+        if watts:
+            out["power_w_median"], out["power_w_max"] = statistics.median(watts), max(watts)
         if note:
             out["note"] = note
         return out

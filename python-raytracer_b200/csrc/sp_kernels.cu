@@ -223,6 +223,8 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
 #ifdef SP_PHASE_TIMING
     unsigned long long phase_acc[6] = {0, 0, 0, 0, 0, 0};
     long long tick__ = clock64();
+    unsigned long long gt0__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0__));
+    const long long ck0__ = tick__;
 #endif
     uint32_t parity = 0;
     for (unsigned long long base64 = dynamic ? (unsigned long long)s_work[0] : (unsigned long long)blockIdx.x * SP_BATCH;
@@ -477,6 +479,10 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
 #ifdef SP_PHASE_TIMING
     if (lane == 0)
         for (int k = 0; k < 6; ++k) atomicAdd(&a.out.stats->phase_cycles[k], phase_acc[k]);
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+        unsigned long long gt1__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1__));
+        printf("[pt] level %d cta %d start %llu dur_ns %llu cycles %lld\n", a.level, (int)blockIdx.x, gt0__, gt1__ - gt0__, clock64() - ck0__);
+    }
 #endif
     if (lane == 0) {
         if (traced) atomicAdd(&a.out.stats->rays[a.level], traced);
