@@ -203,6 +203,9 @@ SP_DEV void sp_lean_plane(float4 a, float4 c, float4 u4, float4 v4, float3 O, fl
     if (ok) { bt = t; bcode = nd < 0.f ? tag : (tag | 0x80000000u); }
 }
 
+// The winner's code also names the slab the ray crosses at the hit, bits [8:10): the face normal is then a column of
+// the inverse basis, oriented against the ray (sp_warp_kernel.cuh writes it into the fan record; locating the face from
+// the hit point, as sp_collider_normal does, cost 45 instructions with a sixth of the lanes).
 SP_DEV void sp_lean_cuboid(float4 r0, float4 r1, float4 r2, float4 c, float4 e, float3 O, float3 D, bool is_self,
                            uint32_t mode, uint32_t tag, float& bt, uint32_t& bcode) {
     float3 oc = O - xyz(c);
@@ -212,13 +215,18 @@ SP_DEV void sp_lean_cuboid(float4 r0, float4 r1, float4 r2, float4 c, float4 e, 
     float t1 = (r0.w - Ol.x) * ix, t2 = (c.w - Ol.x) * ix;
     float t3 = (r1.w - Ol.y) * iy, t4 = (e.x - Ol.y) * iy;
     float t5 = (r2.w - Ol.z) * iz, t6 = (e.y - Ol.z) * iz;
-    float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
-    float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+    const float nx = fminf(t1, t2), ny = fminf(t3, t4), nz = fminf(t5, t6);
+    const float fx = fmaxf(t1, t2), fy = fmaxf(t3, t4), fz = fmaxf(t5, t6);
+    float tmin = fmaxf(fmaxf(nx, ny), nz);
+    float tmax = fminf(fminf(fx, fy), fz);
     bool miss = (tmax < 0.f) || (tmin > tmax);
     bool inside = (tmin < 0.f) || is_self;                 // SP_SELF_FAR: exit point only
     float t = inside ? tmax : tmin;
     bool ok = !miss && !(is_self && mode != SP_SELF_FAR) && (t < bt);
-    if (ok) { bt = t; bcode = inside ? (tag | 0x80000000u) : tag; }
+    if (ok) {
+        const uint32_t axis = inside ? (tmax == fx ? 0u : (tmax == fy ? 1u : 2u)) : (tmin == nx ? 0u : (tmin == ny ? 1u : 2u));
+        bt = t; bcode = (inside ? (tag | 0x80000000u) : tag) | (axis << 8);
+    }
 }
 
 SP_DEV void sp_lean_triangle(float4 m0, float4 m1, float4 m2, float3 O, float3 D, bool is_self, uint32_t tag, float& bt,
@@ -317,13 +325,18 @@ SP_DEV void sp_intersect_lean(const float4* __restrict__ ch, float3 O, float3 D,
 //   leaf  : ~child = float4 offset of its first record in `data` << 3 | (count - 1); a record is one header vector
 //           (stream type | casts shadow << 8, collider id, number of data vectors, -) followed by the packed collider
 
-SP_DEV bool sp_box_hit(float3 lo, float3 hi, float3 O, float3 inv, float t_max, float& t_near) {
-    const float tx1 = (lo.x - O.x) * inv.x, tx2 = (hi.x - O.x) * inv.x;
-    const float ty1 = (lo.y - O.y) * inv.y, ty2 = (hi.y - O.y) * inv.y;
-    const float tz1 = (lo.z - O.z) * inv.z, tz2 = (hi.z - O.z) * inv.z;
+// Slab test with the ray's origin folded into the multiply-add:  (lo - O) / D  =  lo * inv + noi  with inv = 1 / D and
+// noi = -O * inv, six FFMA per box instead of six FADD + six FMUL.  inv comes from sp_safe_rcp (a zero direction component
+// becomes +-1e-30, so inv stays finite and the products never meet inf - inf); the rounding of the folded form, 2^-24 of
+// |lo * inv|, is far inside the boxes' relative padding of 1e-5 (sp_api.cu, collider_aabb).
+SP_DEV float sp_safe_rcp(float d) { return fast_rcp(fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); }
+SP_DEV bool sp_box_hit(float3 lo, float3 hi, float3 inv, float3 noi, float t_max, float& t_near) {
+    const float tx1 = fmaf(lo.x, inv.x, noi.x), tx2 = fmaf(hi.x, inv.x, noi.x);
+    const float ty1 = fmaf(lo.y, inv.y, noi.y), ty2 = fmaf(hi.y, inv.y, noi.y);
+    const float tz1 = fmaf(lo.z, inv.z, noi.z), tz2 = fmaf(hi.z, inv.z, noi.z);
     t_near = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fmaxf(fminf(tz1, tz2), 0.f));
     const float t_far = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fminf(fmaxf(tz1, tz2), t_max));
-    return t_near <= t_far;                    // NaN (0 * inf on a slab boundary) compares false: handled by the box inflation
+    return t_near <= t_far;
 }
 
 // Nearest hit among the BVH's colliders closer than best.t.  casters_only: shadow rays (glossy.py:53-57) look at
@@ -339,7 +352,8 @@ SP_DEV bool sp_box_hit(float3 lo, float3 hi, float3 O, float3 inv, float t_max, 
 SP_DEV void sp_bvh_nearest(const DBvh& bvh, float3 O, float3 D, int src_id, uint32_t mode, bool casters_only, float t_any,
                            ChunkBest& best) {
     if (bvh.n_nodes == 0) return;
-    const float3 inv = v3(fast_rcp(D.x), fast_rcp(D.y), fast_rcp(D.z));
+    const float3 inv = v3(sp_safe_rcp(D.x), sp_safe_rcp(D.y), sp_safe_rcp(D.z));
+    const float3 noi = v3(-O.x * inv.x, -O.y * inv.y, -O.z * inv.z);
     int stack[32];
     int sp = 0, node = 0;                                  // >= 0: box node, < 0: leaf code, SP_BVH_DONE: finished
     while (node != SP_BVH_DONE) {
@@ -348,8 +362,8 @@ SP_DEV void sp_bvh_nearest(const DBvh& bvh, float3 O, float3 D, int src_id, uint
             const float4 n0 = __ldg(bvh.nodes + 4 * node), n1 = __ldg(bvh.nodes + 4 * node + 1);
             const float4 n2 = __ldg(bvh.nodes + 4 * node + 2), n3 = __ldg(bvh.nodes + 4 * node + 3);
             float ta, tb;
-            const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), O, inv, best.t, ta);
-            const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), O, inv, best.t, tb);
+            const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), inv, noi, best.t, ta);
+            const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), inv, noi, best.t, tb);
             int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
             if (ha && hb) {
                 if (tb < ta) { const int c = ca; ca = cb; cb = c; }      // nearer child first

@@ -453,10 +453,7 @@ sp_level_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                     if (fbase != SP_SLOT_NONE) ctx.fan_slot = fbase + (fs & 0x0FFFFFFFu);
                 }
                 const float3 add = sp_shade<FEAT>(ctx, s, h);
-                float* px = reinterpret_cast<float*>(a.accum + s.pix);
-                if (add.x != 0.f) atomicAdd(px, add.x);
-                if (add.y != 0.f) atomicAdd(px + 1, add.y);
-                if (add.z != 0.f) atomicAdd(px + 2, add.z);
+                sp_accum_add(a.accum + s.pix, add);
                 // reserved but unused slots become dead records
                 if (ctx.ray_slot != SP_SLOT_NONE)
                     for (uint32_t q = ctx.ray_used; q < need_ray; ++q) sp_write_dead(a.out.rays, ctx.ray_slot + q);
@@ -593,7 +590,7 @@ sp_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
     bool drained = false;                                    // the launch has no more items for this warp
     // the lane's ray and where its traversal stands
     bool have = false;
-    float3 O = v3(0.f), D = v3(0.f), inv = v3(0.f);
+    float3 O = v3(0.f), D = v3(0.f), inv = v3(0.f), noi = v3(0.f);
     ChunkBest best; best.t = SP_INF; best.idx = -1; best.orient = 0;
     int src_id = -1, node = SP_BVH_DONE, sp = 0;
     uint32_t mode = 0u, item = 0u;
@@ -627,7 +624,8 @@ sp_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 src_id = (int)q[8 * 32 + j];
                 mode = q[9 * 32 + j];
                 item = q[10 * 32 + j];
-                inv = v3(fast_rcp(D.x), fast_rcp(D.y), fast_rcp(D.z));
+                inv = v3(sp_safe_rcp(D.x), sp_safe_rcp(D.y), sp_safe_rcp(D.z));
+                noi = v3(-O.x * inv.x, -O.y * inv.y, -O.z * inv.z);
                 node = 0; sp = 0;
                 have = true;
             }
@@ -643,8 +641,8 @@ sp_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Level
                 const float4 n0 = __ldg(bvh.nodes + 4 * node), n1 = __ldg(bvh.nodes + 4 * node + 1);
                 const float4 n2 = __ldg(bvh.nodes + 4 * node + 2), n3 = __ldg(bvh.nodes + 4 * node + 3);
                 float ta, tb;
-                const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), O, inv, best.t, ta);
-                const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), O, inv, best.t, tb);
+                const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), inv, noi, best.t, ta);
+                const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), inv, noi, best.t, tb);
                 int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
                 if (ha && hb) {
                     if (tb < ta) { const int c = ca; ca = cb; cb = c; }
@@ -703,7 +701,7 @@ sp_shadow_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Leve
     const DBvh& bvh = sc.bvh;
     uint32_t q_n = 0, wb = 0, wend = 0;
     bool drained = false, have = false;
-    float3 O = v3(0.f), D = v3(0.f), inv = v3(0.f), contrib = v3(0.f);
+    float3 O = v3(0.f), D = v3(0.f), inv = v3(0.f), noi = v3(0.f), contrib = v3(0.f);
     float dist = 0.f;
     ChunkBest best; best.t = SP_INF; best.idx = -1; best.orient = 0;
     int src_id = -1, node = SP_BVH_DONE, sp = 0;
@@ -769,7 +767,8 @@ sp_shadow_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Leve
                 contrib = v3(__uint_as_float(q[8 * 32 + j]), __uint_as_float(q[9 * 32 + j]), __uint_as_float(q[10 * 32 + j]));
                 const uint32_t code = q[11 * 32 + j];
                 src_id = (int)(code >> 2); mode = code & 3u;
-                inv = v3(fast_rcp(D.x), fast_rcp(D.y), fast_rcp(D.z));
+                inv = v3(sp_safe_rcp(D.x), sp_safe_rcp(D.y), sp_safe_rcp(D.z));
+                noi = v3(-O.x * inv.x, -O.y * inv.y, -O.z * inv.z);
                 best.t = dist; best.idx = -1; best.orient = 0;       // only casters nearer than the light matter
                 node = 0; sp = 0;
                 have = true;
@@ -785,8 +784,8 @@ sp_shadow_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Leve
                 const float4 n0 = __ldg(bvh.nodes + 4 * node), n1 = __ldg(bvh.nodes + 4 * node + 1);
                 const float4 n2 = __ldg(bvh.nodes + 4 * node + 2), n3 = __ldg(bvh.nodes + 4 * node + 3);
                 float ta, tb;
-                const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), O, inv, best.t, ta);
-                const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), O, inv, best.t, tb);
+                const bool ha = sp_box_hit(v3(n0.x, n0.y, n0.z), v3(n0.w, n1.x, n1.y), inv, noi, best.t, ta);
+                const bool hb = sp_box_hit(v3(n1.z, n1.w, n2.x), v3(n2.y, n2.z, n2.w), inv, noi, best.t, tb);
                 int ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
                 if (ha && hb) {
                     if (tb < ta) { const int c = ca; ca = cb; cb = c; }
@@ -822,10 +821,7 @@ sp_shadow_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Leve
             }
             if (node == SP_BVH_DONE) {
                 if (!(best.t < dist)) {                              // the light is visible from here
-                    float* px = reinterpret_cast<float*>(a.accum + pix);
-                    if (contrib.x != 0.f) atomicAdd(px, contrib.x);
-                    if (contrib.y != 0.f) atomicAdd(px + 1, contrib.y);
-                    if (contrib.z != 0.f) atomicAdd(px + 2, contrib.z);
+                    sp_accum_add(a.accum + pix, contrib);
                 }
                 have = false;
             }

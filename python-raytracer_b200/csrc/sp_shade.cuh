@@ -20,6 +20,23 @@ struct Ray {
     uint32_t pix, path, meta;
 };
 
+// Add a ray's radiance to its pixel of the accumulation frame: one 16-byte reduction (red.global.add.v4.f32, sm_90+)
+// instead of three scalar ones — a third of the L2 atomic traffic and of the instructions around it.
+#ifndef SP_VECTOR_RED
+#define SP_VECTOR_RED 1
+#endif
+SP_DEV void sp_accum_add(float4* px, float3 add) {
+#if SP_VECTOR_RED
+    if (any_nonzero(add))
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(px), "f"(add.x), "f"(add.y), "f"(add.z), "f"(0.f) : "memory");
+#else
+    float* f = reinterpret_cast<float*>(px);
+    if (add.x != 0.f) atomicAdd(f, add.x);
+    if (add.y != 0.f) atomicAdd(f + 1, add.y);
+    if (add.z != 0.f) atomicAdd(f + 2, add.z);
+#endif
+}
+
 
 // ---- queue records ---------------------------------------------------------------------------------
 // Slots are reserved per CTA *before* shading from an upper bound of what each hit can emit

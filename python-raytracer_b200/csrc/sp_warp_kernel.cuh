@@ -157,10 +157,7 @@ __device__ __noinline__ void sp_shade_stash(const DScene* scp, const LevelArgs* 
     }
     if (mine) {
         const float3 add = sp_shade<FEAT>(ctx, s, h);
-        float* px = reinterpret_cast<float*>(a.accum + s.pix);
-        if (add.x != 0.f) atomicAdd(px, add.x);
-        if (add.y != 0.f) atomicAdd(px + 1, add.y);
-        if (add.z != 0.f) atomicAdd(px + 2, add.z);
+        sp_accum_add(a.accum + s.pix, add);
         // reserved but unused slots become dead records
         if (ctx.ray_used < 1u && n_ray >= 1 && ctx.ray_slot != SP_SLOT_NONE) sp_write_dead(a.out.rays, ctx.ray_slot);
         if (ctx.ray_used < 2u && n_ray >= 2 && ctx.ray_slot1 != SP_SLOT_NONE) sp_write_dead(a.out.rays, ctx.ray_slot1);
@@ -340,6 +337,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
             float hit_t = SP_INF;
             int hit_id = -1;
             bool outer = true;                                 // hit.orient > 0
+            uint32_t face_axis = 3u;                           // cuboid hits of the chunk walk: the slab crossed (3: not known)
             if (active) {
                 const uint32_t mode = meta_mode(r.meta);
                 if (self_tag >= 0 && mode == SP_SELF_ZERO) {
@@ -352,8 +350,9 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                     uint32_t bcode = 0xFFFFFFFFu;
                     sp_intersect_lean(s_geom, r.o, r.d, self_tag, mode, hit_t, bcode);
                     if (hit_t < SP_INF) {
-                        hit_id = sh.ids[bcode & 0x7FFFFFFFu];
+                        hit_id = sh.ids[bcode & 0xFFu];
                         outer = (bcode & 0x80000000u) == 0u;
+                        face_axis = (bcode >> 8) & 3u;
                     }
                 }
             }
@@ -371,10 +370,7 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                 glass = meta_depth(r.meta) < (hc.y & 255u);
                 if (hc.y & 0x100u) {                              // emissive.py:21-23
                     const float3 add = r.thr * xyz(sh.lite[hit_id]);
-                    float* px = reinterpret_cast<float*>(a.accum + r.pix);
-                    if (add.x != 0.f) atomicAdd(px, add.x);
-                    if (add.y != 0.f) atomicAdd(px + 1, add.y);
-                    if (add.z != 0.f) atomicAdd(px + 2, add.z);
+                    sp_accum_add(a.accum + r.pix, add);
                 }
             }
 
@@ -401,8 +397,16 @@ sp_warp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelA
                     if (any_nonzero(thr)) {
                         const DCollider& col = sc.colliders[hit_id];
                         const float3 P = fma3(r.d, hit_t, r.o);
-                        const float3 Nc = to_f3(sp_collider_normal<float>((int)ctype, col.p, from_f3<float>(P)));
-                        const float3 N = outer ? Nc : -Nc;
+                        float3 N;
+                        if (ctype == SP_COLLIDER_CUBOID && face_axis < 3u) {
+                            // column `axis` of the inverse basis = outward normal of the +axis face; towards the ray's side
+                            const float* ib = col.p + SP_CB_INVB + face_axis;
+                            N = v3(ib[0], ib[3], ib[6]);
+                            if (dot(N, r.d) > 0.f) N = -N;
+                        } else {
+                            const float3 Nc = to_f3(sp_collider_normal<float>((int)ctype, col.p, from_f3<float>(P)));
+                            N = outer ? Nc : -Nc;
+                        }
                         // sampled directions lie in the hemisphere of N: they leave a planar / outer surface
                         // and cross the interior of a convex collider hit from inside (sp_shade.cuh)
                         const bool planar = (ctype == SP_COLLIDER_PLANE || ctype == SP_COLLIDER_TRIANGLE);
