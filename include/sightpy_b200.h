@@ -250,7 +250,10 @@ int  sp_aovs(sp_scene*, int sample, uint64_t seed, int32_t* out_hit_id, float* o
  *        launch, the default; 0 = inside sp_level_kernel; same hits),
  * "warp_kernel" (1 = queue-fed levels of small untextured Diffuse / Refractive / Emissive scenes run the
  *        warp-autonomous sp_warp_kernel, the default; 0 = the CTA-cooperative sp_level_kernel everywhere; same rays,
- *        same results) */
+ *        same results),
+ * "split_kernels" (Whitted scenes — textures, Glossy, Refractive, ThinFilm, sky boxes; no Diffuse, no BVH: a level as a
+ *        hit kernel plus one shade kernel per material kind instead of the fused level kernel; 0 = never, 1 = level 0
+ *        of launches of 256 Ki primaries or more, the default, 2 = every level; same rays, same results) */
 int  sp_set_option(sp_scene*, const char* name, int64_t value);
 /* Roofline denominators measured on the bound device: dependent-free FFMA chains (TFLOP/s, 2 flop
  * per FFMA) and a float4 copy (GB/s, read + write bytes). */

@@ -208,6 +208,9 @@ struct sp_scene {
     std::vector<int32_t> importance, shadow_ids;
     // ---- options ------------------------------------------------------------------------------------
     int64_t opt_ray_cap = 0, opt_fan_cap = 0, opt_chunk = 0, opt_max_levels = 0, opt_bvh = 1, opt_warp = 1;
+    int64_t opt_split = 1;                       // Whitted scenes: hit kernel + per-material shade kernels (sp_split_kernels.cuh)
+    uint32_t kind_mask = 0;                      // material kinds present (bit SP_MAT_*)
+    uint64_t call_primaries = 0;                 // primaries of the render call in progress (sizes per-item buffers once)
     int64_t opt_pretrace = 1;                    // BVH scenes: sp_trace_kernel ahead of every level launch
     int64_t opt_chunk_fixed = 0;                 // 1: a chunk that overflows is an error instead of being retried smaller
     int64_t chunk_limit = 0;                     // learnt from overflows: no chunk larger than this
@@ -225,6 +228,7 @@ struct sp_scene {
     DevBuf<float4> d_shq;                        // BVH scenes: shadow-ray requests of the level that just ran (sp_shadow_kernel)
     DevBuf<uint32_t> d_shq_count;                // per level: requests queued, work counter
     DevBuf<float2> d_hits;                       // BVH scenes: per-item nearest hits of the level about to run (sp_trace_kernel)
+    DevBuf<uint32_t> d_klist, d_kcount;          // Whitted scenes: per-kind item lists of the level being shaded and their counts
     DevBuf<int> off_all, off_shadow;
     DevBuf<int2> slot_shadow;
     DevBuf<DCollider> d_cols;
@@ -265,7 +269,7 @@ struct sp_scene {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
 
-        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); d_tiles.release(); d_hits.release(); d_shq.release(); d_shq_count.release(); off_all.release(); off_shadow.release();
+        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); d_tiles.release(); d_hits.release(); d_klist.release(); d_kcount.release(); d_shq.release(); d_shq_count.release(); off_all.release(); off_shadow.release();
         slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
         d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
@@ -1259,6 +1263,9 @@ int sp_scene_commit(sp_scene* s) {
     if (d.bvh.n_nodes > 0) needed |= SP_F_BVH;
     s->material_set = sp_pick_material_set(needed);
     s->d.use_warp_kernel = s->opt_warp ? 1 : 0;
+    s->d.use_split = s->opt_split ? 1 : 0;
+    s->kind_mask = 0;
+    for (const auto& m : s->mats) s->kind_mask |= 1u << (m.kind & 31);
     if (int rc = pick_kernels(s)) return rc;
     const uint64_t sig = shape_signature(s);
     if (sig != s->shape_sig) {                   // a different scene: measure the queue occupancy afresh
@@ -1304,6 +1311,7 @@ static int ensure_queues(sp_scene* s, uint64_t primaries) {
     return 0;
 }
 
+#define SPS_KINDS_HOST 6        // shading bins of the split kernels (sp_split_kernels.cuh: SPS_KINDS)
 struct ChunkJob {
     int source, run;
     uint32_t pix_begin, n_pix, sample_begin, n_items, user_base;
@@ -1339,6 +1347,24 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         }
     }
     const bool defer_shadows = pretrace && s->d_shq.p && s->d.n_lights > 0 && s->d.n_shadow_casters > 0;
+    // Whitted scenes: hit kernel + per-material shade kernels (option "split_kernels": 1 = level 0 of launches of at
+    // least 256 Ki primaries, 2 = every level); per-item hit records and per-kind item lists sized for the widest level
+    // that runs this way (the primaries, or every queued record)
+    static const int env_split = [] { const char* e = getenv("SIGHTPY_SPLIT"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1; }();
+    const int split_mode = (job.run == SP_RUN_FULL && sp_can_split(s->d, s->material_set)) ? (env_split >= 0 ? env_split : (int)s->opt_split) : 0;
+    const bool split = split_mode == 2 || (split_mode == 1 && job.n_items >= (1u << 18));
+    size_t split_cap = 0;
+    if (split) {
+        // level 0 only: the largest chunk this call can cut (so that the buffers are allocated by the first chunk of the
+        // first frame, not again whenever a later chunk is larger)
+        const size_t largest = (size_t)std::min<uint64_t>(std::max<uint64_t>(s->call_primaries, job.n_items), 8ull * (uint64_t)default_chunk(s));
+        split_cap = split_mode == 2 ? std::max<size_t>(largest, s->ray_cap) : largest;
+        if (s->d_hits.n < split_cap) CUDA_TRY(s->d_hits.alloc(split_cap));
+        if (s->d_klist.n < split_cap * SPS_KINDS_HOST) CUDA_TRY(s->d_klist.alloc(split_cap * SPS_KINDS_HOST));
+        if (s->d_kcount.n < 8 * (size_t)SP_MAX_LEVELS) CUDA_TRY(s->d_kcount.alloc(8 * (size_t)SP_MAX_LEVELS));
+        CUDA_TRY(cudaMemsetAsync(s->d_kcount.p, 0, s->d_kcount.n * sizeof(uint32_t), s->stream));
+    }
+    int split_launches = 0;
     CUDA_TRY(cudaMemsetAsync(s->counts.p, 0, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
     for (int L = 0; L < n_levels; ++L) {
@@ -1370,6 +1396,14 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         a.shq = defer_shadows ? s->d_shq.p : nullptr;
         a.shq_cap = defer_shadows ? (uint32_t)std::min<size_t>(s->d_shq.n / 3, 0xFFFFFFFFull) : 0u;
         a.shq_count = defer_shadows ? s->d_shq_count.p + 2 * (size_t)L : nullptr;
+        if (split && (split_mode == 2 || L == 0)) {
+            a.hits = s->d_hits.p; a.hits_cap = (uint32_t)std::min<size_t>(split_cap, 0xFFFFFFFFull);
+            a.kind_list = s->d_klist.p; a.kind_cap = a.hits_cap; a.kind_count = s->d_kcount.p + 8 * (size_t)L;
+            int n_k = 0;
+            CUDA_TRY(sp_launch_split_level(s->d, a, s->kind_mask, s->device, s->stream, &n_k));
+            split_launches += n_k;
+            continue;
+        }
         if (pretrace) CUDA_TRY(sp_launch_trace(s->d, a, s->material_set, s->device, s->stream));
         CUDA_TRY(sp_launch_level(s->d, a, s->material_set, L == 0 ? s->grid0 : s->grid_q, s->stream));
         if (defer_shadows) CUDA_TRY(sp_launch_shadow(s->d, a, s->device, s->stream));
@@ -1405,7 +1439,8 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
     }
     if (st) {
         st->chunks += 1;
-        st->kernel_launches += (uint64_t)n_levels * (pretrace ? (defer_shadows ? 3u : 2u) : 1u);
+        st->kernel_launches += split ? (uint64_t)split_launches + (split_mode == 2 ? 0u : (uint64_t)(n_levels - 1))
+                                     : (uint64_t)n_levels * (pretrace ? (defer_shadows ? 3u : 2u) : 1u);
         st->level_kernel_launches += (uint64_t)n_levels;
         if (warp) st->warp_kernel_launches += (uint64_t)(n_levels - 1);
         st->peak_ray_records = std::max<uint64_t>(st->peak_ray_records, peak_r);
@@ -1447,6 +1482,7 @@ static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what
         s->d.philox_keys[2 * r + 1] = s->d.seed_hi + r * 0xBB67AE85u;
     }
     if (st) memset(st, 0, sizeof *st);
+    s->call_primaries = primaries;
     return ensure_queues(s, primaries);
 }
 
@@ -1754,6 +1790,10 @@ int sp_set_option(sp_scene* s, const char* name, int64_t value) {
     else if (!strcmp(name, "chunk_primaries")) s->opt_chunk = value;
     else if (!strcmp(name, "fixed_chunks")) s->opt_chunk_fixed = value;
     else if (!strcmp(name, "pretrace")) s->opt_pretrace = value;
+    else if (!strcmp(name, "split_kernels")) {
+        if (value > 2) return fail("sp_set_option: split_kernels must be 0 (off), 1 (level 0) or 2 (every level)");
+        s->opt_split = value; s->d.use_split = value ? 1 : 0;
+    }
     else if (!strcmp(name, "max_levels")) s->opt_max_levels = value;
     else if (!strcmp(name, "bvh")) {
         s->opt_bvh = value;

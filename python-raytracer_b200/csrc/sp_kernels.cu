@@ -830,6 +830,7 @@ sp_shadow_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Leve
 }
 
 #include "sp_warp_kernel.cuh"
+#include "sp_split_kernels.cuh"
 
 // ---- frame resolve: average, sRGB OETF, per-pixel max normalisation, truncation to uint8 ---------
 // scene.py:118-140 + colour_functions.py:4-18.  Double precision: the output is quantised by
@@ -1009,6 +1010,45 @@ cudaError_t sp_launch_trace(const DScene& sc, const LevelArgs& a, uint32_t mater
     }
     k<<<grid[device & 15], SPT_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
     return cudaGetLastError();
+}
+
+// Whitted scenes (no Diffuse fans, no BVH, one staged chunk) run a level as hit kernel + per-material shade kernels.
+// SIGHTPY_SPLIT=0 / option "split_kernels" = 0 keeps them on the fused sp_level_kernel (A/B measurements, parity tests).
+bool sp_can_split(const DScene& sc, uint32_t material_set) {
+    static const bool enabled = [] { const char* e = getenv("SIGHTPY_SPLIT"); return !(e && e[0] == '0'); }();
+    return enabled && sc.use_split && material_set == SP_SET_WHITTED && sc.all.n_chunks == 1 && sc.bvh.n_nodes == 0;
+}
+
+template <uint32_t SRC>
+static cudaError_t launch_split(const DScene& sc, const LevelArgs& a, uint32_t kind_mask, int grid, cudaStream_t st, int* launched) {
+    auto kh = sp_hit_kernel<SP_SET_WHITTED | SRC>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sp_hit_kernel<SP_SET_WHITTED | SP_F_LEVEL0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
+        cudaFuncSetAttribute(sp_hit_kernel<SP_SET_WHITTED | SP_F_QUEUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_CHUNK_VEC4 * sizeof(float4)));
+        attr_set = true;
+    }
+    int n = 1;
+    kh<<<grid, SPS_BLOCK, geom_smem_bytes(sc), st>>>(sc, a);
+    if (kind_mask & (1u << SP_MAT_REFRACTIVE)) { sp_shade_kernel<SP_F_TEX | SP_F_REFR | SRC, 0><<<grid, SPS_BLOCK, 0, st>>>(sc, a); ++n; }
+    if (kind_mask & (1u << SP_MAT_GLOSSY)) { sp_shade_kernel<SP_F_TEX | SP_F_GLOSSY | SRC, 1><<<grid, SPS_BLOCK, 0, st>>>(sc, a); ++n; }
+    if (kind_mask & (1u << SP_MAT_THINFILM)) { sp_shade_kernel<SP_F_TEX | SP_F_THIN | SRC, 2><<<grid, SPS_BLOCK, 0, st>>>(sc, a); ++n; }
+    if (kind_mask & (1u << SP_MAT_SKYBOX)) { sp_shade_kernel<SP_F_TEX | SP_F_SKY | SRC, 4><<<grid, SPS_BLOCK, 0, st>>>(sc, a); ++n; }
+    if (kind_mask & (1u << SP_MAT_EMISSIVE)) { sp_shade_kernel<SP_F_TEX | SRC, 5><<<grid, SPS_BLOCK, 0, st>>>(sc, a); ++n; }
+    if (launched) *launched = n;
+    return cudaGetLastError();
+}
+
+cudaError_t sp_launch_split_level(const DScene& sc, const LevelArgs& a, uint32_t kind_mask, int device, cudaStream_t st, int* launched) {
+    static int sms[16] = {0};
+    if (sms[device & 15] == 0) {
+        int v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+        sms[device & 15] = v;
+    }
+    const int grid = sms[device & 15] * 8;              // 4 resident CTAs per SM, two waves: grid-stride over the items
+    return a.source != SP_SRC_QUEUES ? launch_split<SP_F_LEVEL0>(sc, a, kind_mask, grid, st, launched)
+                                     : launch_split<SP_F_QUEUES>(sc, a, kind_mask, grid, st, launched);
 }
 
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st) {

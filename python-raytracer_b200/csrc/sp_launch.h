@@ -43,6 +43,11 @@ struct LevelArgs {
     float4* shq;
     uint32_t shq_cap;
     uint32_t* shq_count;
+    // Whitted scenes, material-sorted wavefront (sp_split_kernels.cuh): per shading bin the items that hit that material
+    // kind (bin b at kind_list + b * kind_cap, kind_count[b] entries); hit records go to `hits` above.
+    uint32_t* kind_list;
+    uint32_t kind_cap;
+    uint32_t* kind_count;
 };
 
 struct ResolveArgs {
@@ -60,6 +65,10 @@ cudaError_t sp_launch_level(const DScene& sc, const LevelArgs& a, uint32_t mater
 bool sp_can_pretrace(const DScene& sc, uint32_t material_set);           // scene behind a BVH with one staged chunk
 cudaError_t sp_launch_shadow(const DScene& sc, const LevelArgs& a, int device, cudaStream_t st);
 cudaError_t sp_launch_trace(const DScene& sc, const LevelArgs& a, uint32_t material_set, int device, cudaStream_t st);
+// Whitted scenes without a BVH: a level as sp_hit_kernel + one sp_shade_kernel per material kind present (kind_mask: bit
+// SP_MAT_*), see sp_split_kernels.cuh.  Returns the number of kernels launched through *launched.
+bool sp_can_split(const DScene& sc, uint32_t material_set);
+cudaError_t sp_launch_split_level(const DScene& sc, const LevelArgs& a, uint32_t kind_mask, int device, cudaStream_t st, int* launched);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
 cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st);   // accum += scratch; scratch = 0
 cudaError_t sp_launch_add(float4* accum, const float4* other, uint32_t n_pix, cudaStream_t st);   // accum.xyz += other.xyz (other may be peer memory)

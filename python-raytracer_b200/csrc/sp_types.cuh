@@ -131,6 +131,7 @@ struct DScene {
     unsigned long long fan_magic[SP_MAX_FAN_CLASSES];   // ceil(2^64 / fan_mult): n / mult == __umul64hi(n, magic) for n < 2^32
     int fan_mult[SP_MAX_FAN_CLASSES];     // rays per fan record of each class (class 0: 1)
     int use_warp_kernel;               // option "warp_kernel" (host side only)
+    int use_split;                     // option "split_kernels" (host side only)
     uint32_t seed_lo, seed_hi;
     uint32_t philox_keys[20];          // the ten Philox round key pairs of (seed_lo, seed_hi), filled per call
 };

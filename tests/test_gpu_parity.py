@@ -685,6 +685,45 @@ def test_warp_autonomous_and_cooperative_kernels_agree(seed):
     assert abs(warp["rgb"].mean() - want["rgb"].mean()) < 0.02 * want["rgb"].mean()
 
 
+@pytest.mark.parametrize("name,kw", [("example2", dict(width=96, height=72)), ("example3", dict(width=96, height=72, normalmap=True)),
+                                      ("example4", dict(width=96, height=72)), ("fuzz", dict(seed=5))])
+def test_split_and_fused_level_kernels_agree(name, kw):
+    """Whitted scenes can run a level as sp_hit_kernel + one sp_shade_kernel per material kind (option "split_kernels":
+    2 = every level, 1 = level 0 of large launches, 0 = the fused sp_level_kernel).  The split kernels call the same
+    device functions on the same rays: identical hit ids, distances and ray counts per depth, radiance equal up to
+    the order of the float additions — for caller rays, whole frames, tiny chunks (most warps never open a slab) and a
+    ray queue too small for the children (reported, not dropped)."""
+    import scenes
+    import sightpy
+    from sightpy.backend import NativeScene
+    flat = flatten_scene(scenes.BUILDERS[name](sightpy, **kw))
+    nat = NativeScene(flat)
+    o, d = nat.camera_rays(sample=1, seed=3)
+    nat.set_option("split_kernels", 0)
+    fused = nat.trace(o, d, seed=3)
+    _, frame_f, st_f = nat.render(3, seed=5)
+    nat.set_option("split_kernels", 2)
+    split = nat.trace(o, d, seed=3)
+    _, frame_s, st_s = nat.render(3, seed=5)
+    assert st_s["kernel_launches"] > st_f["kernel_launches"], "the split kernels did not run"
+    nat.set_option("chunk_primaries", 1024)
+    _, frame_t, st_t = nat.render(3, seed=5)
+    nat.set_option("chunk_primaries", 0)
+    assert np.array_equal(split["hit_id"], fused["hit_id"])
+    assert np.array_equal(split["t"], fused["t"])
+    assert split["stats"]["rays_per_depth"] == fused["stats"]["rays_per_depth"]
+    assert st_s["rays_per_depth"] == st_f["rays_per_depth"] == st_t["rays_per_depth"]
+    assert st_s["shadow_rays"] == st_f["shadow_rays"]
+    np.testing.assert_allclose(split["rgb"], fused["rgb"], rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(frame_s, frame_f, rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(frame_t, frame_f, rtol=2e-4, atol=1e-5)
+    if st_f["peak_ray_records"] > 64:
+        nat.set_option("ray_queue_capacity", 32)
+        with pytest.raises(RuntimeError, match="overflow"):
+            nat.render(2, seed=0)
+    nat.close()
+
+
 def test_warp_kernel_slabs_survive_tiny_chunks_and_report_overflow():
     """Warp-private slabs: a frame cut into 1024-primary chunks (every launch smaller than the grid: most warps
     never open a slab, the others leave dead tails) equals the frame rendered in one chunk, and a ray queue that
