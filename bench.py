@@ -519,10 +519,14 @@ def run_native(args, emit=print):
     fpr = runner.flop_per_ray()
     bvh = len(runner.flat.colliders) >= 64
     flops = fpr * tot["rays"]
-    per_ray_file = REPO / "profiles" / "r2_per_ray.json"     # from the committed ncu launch list of this build (tools/ncu_per_ray.py)
+    per_ray_file = REPO / "profiles" / "r2b_per_ray.json"    # from the committed ncu launch list of this build (tools/ncu_per_ray.py)
+    if not per_ray_file.exists():
+        per_ray_file = REPO / "profiles" / "r2_per_ray.json"
     per_ray = json.loads(per_ray_file.read_text()).get(args.config) if per_ray_file.exists() else None
     traffic = per_ray["dram_bytes_per_ray"] * tot["rays"] / n_launch if per_ray else None
     kernel = ("sp_warp_kernel (levels >= 1: 98 % of the rays) + sp_level_kernel (level 0)" if args.config == "cornell"
+              else "sp_trace_kernel + sp_level_kernel + sp_shadow_kernel (every level)" if bvh
+              else "sp_hit_kernel + sp_shade_kernel (level 0) + sp_level_kernel (levels >= 1)" if width * height * spp >= (1 << 18)
               else "sp_level_kernel (all levels)")
     roofline = {
         "bound": "fp32", "kernel": kernel,
@@ -545,7 +549,7 @@ def run_native(args, emit=print):
         "frac": per_ray["thread_inst_per_ray"] * tot["rays"] / level_s / 1e12 / issue_peak if per_ray else None,
         "thread_inst_per_ray": per_ray["thread_inst_per_ray"] if per_ray else None,
         "warp_inst_per_ray": per_ray["warp_inst_per_ray"] if per_ray else None,
-        "source": "smsp__thread_inst_executed.sum / rays of the committed ncu launch list (profiles/r2_per_ray.json)" if per_ray else
+        "source": f"smsp__thread_inst_executed.sum / rays of the committed ncu launch list (profiles/{per_ray_file.name})" if per_ray else
                   "no ncu launch list committed for this configuration",
     }
     roofline_hbm = {

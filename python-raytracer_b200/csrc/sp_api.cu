@@ -506,7 +506,7 @@ static int bvh_build_rec(BuiltBvh& out, std::vector<int>& order, int first, int 
             bounds.lo[k] = std::min(bounds.lo[k], boxes[order[i]].lo[k]);
             bounds.hi[k] = std::max(bounds.hi[k], boxes[order[i]].hi[k]);
         }
-    static const int leaf_max = [] { const char* e = getenv("SIGHTPY_BVH_LEAF"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+    static const int leaf_max = [] { const char* e = getenv("SIGHTPY_BVH_LEAF"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
     if (count <= leaf_max) {             // leaf: its items become consecutive in the item array, by type, then by id
         const int at = (int)out.items.size();
         std::sort(order.begin() + first, order.begin() + first + count, [&](int a, int b) {

@@ -12,6 +12,7 @@ import scenes, sightpy
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 quiet = contextlib.redirect_stdout(io.StringIO())
 with quiet:
+    scenes.example1(sightpy, width=64, height=48).render(samples_per_pixel=1)      # CUDA context, library load
     t0 = time.perf_counter(); sc4 = scenes.example4(sightpy, width=3840, height=2160); t1 = time.perf_counter()
     img = sc4.render(samples_per_pixel=16); t2 = time.perf_counter()
     img = sc4.render(samples_per_pixel=16); t3 = time.perf_counter()

@@ -5,7 +5,7 @@
         --clock-control none --csv --log-file launches.csv python bench.py <args>
     python tools/ncu_per_ray.py launches.csv bench_line.json <config> [profiles/r2_per_ray.json]
 
-Sums the metrics over the level kernels of the run (all steps and warm-ups alike: every step traces the same rays)
+Sums the metrics over the wavefront kernels of the run (level / warp / hit / shade / trace / shadow kernels) (all steps and warm-ups alike: every step traces the same rays)
 and divides by the rays those launches traced: steps x rays_per_frame of the bench line (the ncu run executes the
 same command, so the same number of frames).  bench.py reads the result for `roofline_issue` / `roofline_hbm.traffic`.
 """
@@ -25,7 +25,7 @@ def main():
     tot, n = defaultdict(float), defaultdict(int)
     for r in rows[1:]:
         name = r[ki].replace("void ", "").split("(")[0].split("<")[0]
-        if not name.startswith(("sp_level", "sp_warp")):
+        if not name.startswith(("sp_level", "sp_warp", "sp_hit", "sp_shade", "sp_trace", "sp_shadow")):
             continue
         tot[r[mi]] += float(r[vi].replace(",", ""))
         if r[mi] == "gpu__time_duration.sum":

@@ -67,9 +67,14 @@ def main():
         rows = [r for r in csv.reader(open(args.launches)) if len(r) > 5]
         hdr = rows[0]
         ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+        mi = hdr.index("Metric Name") if "Metric Name" in hdr else None
         tot, cnt = defaultdict(float), defaultdict(int)
         for r in rows[1:]:
+            if mi is not None and r[mi] != "gpu__time_duration.sum":
+                continue                                    # launch lists that carry several metrics per launch
             name = r[ki].split("(")[0]
+            if name.startswith(("sp_ffma", "sp_copy")):
+                continue                                    # roofline micro-benchmarks of bench.py, not part of a frame
             tot[name] += fnum(r[vi]); cnt[name] += 1
         s = sum(tot.values())
         print(f"## Launch list (`{args.launches}`, gpu__time_duration.sum; cold-cache, serialised: compare shares)\n")
