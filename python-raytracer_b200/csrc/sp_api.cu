@@ -3,6 +3,7 @@
 // sp_kernels.cu.  Replaces the body of Scene.render (sightpy/scene.py:71-140) and the
 // multiprocessing fan-out underneath it.
 #include <algorithm>
+#include <deque>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -191,6 +192,35 @@ struct ScopedEvent {                     // a pooled event for the duration of o
     ~ScopedEvent() { if (e) g_ctx[dev].event_pool.push_back(e); }
 };
 
+#define SPS_KINDS_HOST 6        // shading bins of the split kernels (sp_split_kernels.cuh: SPS_KINDS)
+struct ChunkJob {
+    int source, run;
+    uint32_t pix_begin, n_pix, sample_begin, n_items, user_base;
+    const uint32_t* tiles; uint32_t tile_shift, tiles_x;
+    const float* user_o; const float* user_d;
+    float4* accum; int32_t* out_hit; float* out_t; float* out_o; float* out_d; float* out_n;
+};
+
+
+// What one wavefront chunk in flight owns.  Two slots: the host enqueues chunk k + 1 (all its levels, the copy of its
+// counters into pinned memory, its fold into the frame) before it waits for chunk k, so that the GPU never idles
+// between the chunks of a frame on a host round trip.
+struct ChunkSlot {
+    DevBuf<uint32_t> counts;            // per level: queue counts + work counters (SP_COUNTS_PER_LEVEL words)
+    DevBuf<DeviceStats> d_stats;
+    DevBuf<float4> scratch;             // the chunk's radiance until it is known to be complete (frame-sized)
+    std::vector<cudaEvent_t> events;    // level boundaries
+    cudaEvent_t done = nullptr;         // everything of the chunk, copies included
+    uint32_t* h_counts = nullptr;       // pinned host copies
+    DeviceStats* h_stats = nullptr;
+    // the chunk in flight
+    bool busy = false;
+    ChunkJob job{};
+    int n_levels = 0, split_mode = 0, split_launches = 0;
+    bool warp = false, pretrace = false, defer_shadows = false, split = false, folded = false;
+    uint32_t region_pix = 0, region_ns = 0;       // what to render again if it overflows (offset / samples of the job)
+};
+
 struct sp_scene {
     int device = 0;                     // the CUDA device this scene lives on
     // ---- host description ---------------------------------------------------------------------
@@ -222,8 +252,8 @@ struct sp_scene {
     cudaStream_t own_stream = nullptr;  // the library's default stream for it
     DevBuf<float> d_lin;                // resolve outputs (device copies, reused across frames)
     DevBuf<uint8_t> d_u8;
-    std::vector<cudaEvent_t> events;
-    DevBuf<float4> geom_all, geom_shadow, accum, scratch;
+    ChunkSlot slot[2];
+    DevBuf<float4> geom_all, geom_shadow, accum;
     DevBuf<uint32_t> d_tiles;                    // tile list of the last sp_render_tiles call
     DevBuf<float4> d_shq;                        // BVH scenes: shadow-ray requests of the level that just ran (sp_shadow_kernel)
     DevBuf<uint32_t> d_shq_count;                // per level: requests queued, work counter
@@ -243,8 +273,6 @@ struct sp_scene {
     std::vector<DevBuf<uint32_t>> d_texels;
     std::vector<uint64_t> cached_tex_keys;       // keys of the shared textures this scene holds a reference to
     DevBuf<DMedium> d_media;
-    DevBuf<uint32_t> counts;
-    DevBuf<DeviceStats> d_stats;
     QueueSet ray_q[2], fan_q[2];
     uint32_t ray_cap = 0, fan_cap = 0;
     uint32_t chunk_primaries = 0;
@@ -269,12 +297,19 @@ struct sp_scene {
         for (auto& b : d_texels) b.release();
         d_texels.clear();
 
-        geom_all.release(); geom_shadow.release(); accum.release(); scratch.release(); d_tiles.release(); d_hits.release(); d_klist.release(); d_kcount.release(); d_shq.release(); d_shq_count.release(); off_all.release(); off_shadow.release();
+        geom_all.release(); geom_shadow.release(); accum.release(); d_tiles.release(); d_hits.release(); d_klist.release(); d_kcount.release(); d_shq.release(); d_shq_count.release(); off_all.release(); off_shadow.release();
         slot_shadow.release(); d_cols.release(); d_colinfo.release(); d_collite.release(); bvh_nodes.release(); bvh_data.release(); bvh_items.release(); d_cols_d.release(); d_prims.release();
-        d_mats.release(); d_texdesc.release(); d_media.release(); counts.release(); d_stats.release();
+        d_mats.release(); d_texdesc.release(); d_media.release();
         for (int i = 0; i < 2; ++i) { ray_q[i].release(); fan_q[i].release(); }
-        for (auto e : events) g_ctx[device].event_pool.push_back(e);
-        events.clear();
+        for (auto& sl : slot) {
+            sl.counts.release(); sl.d_stats.release(); sl.scratch.release();
+            for (auto e : sl.events) g_ctx[device].event_pool.push_back(e);
+            sl.events.clear();
+            if (sl.done) { g_ctx[device].event_pool.push_back(sl.done); sl.done = nullptr; }
+            if (sl.h_counts) { cudaFreeHost(sl.h_counts); sl.h_counts = nullptr; }
+            if (sl.h_stats) { cudaFreeHost(sl.h_stats); sl.h_stats = nullptr; }
+            sl.busy = false;
+        }
         if (own_stream) { cudaStreamSynchronize(own_stream); g_ctx[device].stream_pool.push_back(own_stream); }
         own_stream = nullptr;
         stream = nullptr;
@@ -1240,12 +1275,19 @@ int sp_scene_commit(sp_scene* s) {
         CUDA_TRY(s->accum.alloc((size_t)c.width * c.height));
         CUDA_TRY(cudaMemset(s->accum.p, 0, s->accum.n * sizeof(float4)));
     }
-    CUDA_TRY(s->counts.alloc((size_t)(SP_MAX_LEVELS + 1) * SP_COUNTS_PER_LEVEL));
-    CUDA_TRY(s->d_stats.alloc(1));
-    s->events.resize((size_t)s->n_levels + 1);
-    for (auto& e : s->events) {
-        if (!ctx().event_pool.empty()) { e = ctx().event_pool.back(); ctx().event_pool.pop_back(); }
-        else CUDA_TRY(cudaEventCreate(&e));
+    for (auto& sl : s->slot) {
+        CUDA_TRY(sl.counts.alloc((size_t)(SP_MAX_LEVELS + 1) * SP_COUNTS_PER_LEVEL));
+        CUDA_TRY(sl.d_stats.alloc(1));
+        if (!sl.h_counts) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&sl.h_counts), (size_t)(SP_MAX_LEVELS + 1) * SP_COUNTS_PER_LEVEL * sizeof(uint32_t), cudaHostAllocDefault));
+        if (!sl.h_stats) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&sl.h_stats), sizeof(DeviceStats), cudaHostAllocDefault));
+        sl.events.resize((size_t)s->n_levels + 1);
+        auto take_event = [&](cudaEvent_t& e) -> cudaError_t {
+            if (!ctx().event_pool.empty()) { e = ctx().event_pool.back(); ctx().event_pool.pop_back(); return cudaSuccess; }
+            return cudaEventCreate(&e);
+        };
+        for (auto& e : sl.events) CUDA_TRY(take_event(e));
+        if (!sl.done) CUDA_TRY(take_event(sl.done));
+        sl.busy = false;
     }
     uint32_t needed = 0;
     for (int i = 0; i < n_col; ++i) {
@@ -1311,19 +1353,10 @@ static int ensure_queues(sp_scene* s, uint64_t primaries) {
     return 0;
 }
 
-#define SPS_KINDS_HOST 6        // shading bins of the split kernels (sp_split_kernels.cuh: SPS_KINDS)
-struct ChunkJob {
-    int source, run;
-    uint32_t pix_begin, n_pix, sample_begin, n_items, user_base;
-    const uint32_t* tiles; uint32_t tile_shift, tiles_x;
-    const float* user_o; const float* user_d;
-    float4* accum; int32_t* out_hit; float* out_t; float* out_o; float* out_d; float* out_n;
-};
-
-// Enqueue all levels of one chunk, wait, fold its counters into `st`.  `overflow` comes back true when a queue was
-// too small for the chunk: what the chunk added to job.accum is then incomplete and the caller discards it.
-static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overflow) {
-    overflow = false;
+// Enqueue all levels of one chunk into slot k: the level launches, then (render calls) the fold of the chunk's scratch
+// frame into the accumulation buffer, the copies of its counters into pinned host memory, and the slot's event.
+static int enqueue_chunk(sp_scene* s, const ChunkJob& job, int k, float4* fold_into, float4* fold_from, uint32_t fold_n) {
+    ChunkSlot& sl = s->slot[k];
     int n_levels = (job.run == SP_RUN_FULL) ? s->n_levels : 1;
     if (s->opt_max_levels > 0) n_levels = std::min<int>(n_levels, (int)s->opt_max_levels);   // debugging aid
     const int ncl = SP_COUNTS_PER_LEVEL;
@@ -1365,8 +1398,8 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         CUDA_TRY(cudaMemsetAsync(s->d_kcount.p, 0, s->d_kcount.n * sizeof(uint32_t), s->stream));
     }
     int split_launches = 0;
-    CUDA_TRY(cudaMemsetAsync(s->counts.p, 0, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), s->stream));
-    CUDA_TRY(cudaMemsetAsync(s->d_stats.p, 0, sizeof(DeviceStats), s->stream));
+    CUDA_TRY(cudaMemsetAsync(sl.counts.p, 0, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), s->stream));
+    CUDA_TRY(cudaMemsetAsync(sl.d_stats.p, 0, sizeof(DeviceStats), s->stream));
     for (int L = 0; L < n_levels; ++L) {
         LevelArgs a;
         memset(&a, 0, sizeof a);
@@ -1384,15 +1417,15 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
             a.in_fan_base[c] = a.out.fan_base[c] = (uint32_t)c * s->fan_cap;
             a.in_fan_cap[c] = a.out.fan_cap[c] = (c < s->d.n_fan_classes) ? s->fan_cap : 0u;
         }
-        a.in_counts = s->counts.p + (size_t)L * ncl;
-        a.out.counts = s->counts.p + (size_t)(L + 1) * ncl;
-        a.out.stats = s->d_stats.p;
+        a.in_counts = sl.counts.p + (size_t)L * ncl;
+        a.out.counts = sl.counts.p + (size_t)(L + 1) * ncl;
+        a.out.stats = sl.d_stats.p;
         a.accum = job.accum;
         a.out_hit = job.out_hit; a.out_t = job.out_t; a.out_o = job.out_o; a.out_d = job.out_d; a.out_n = job.out_n;
         a.shadow_slot = s->slot_shadow.p;
         a.hits = pretrace ? s->d_hits.p : nullptr;
         a.hits_cap = pretrace ? (uint32_t)std::min<size_t>(s->d_hits.n, 0xFFFFFFFFull) : 0u;
-        CUDA_TRY(cudaEventRecord(s->events[L], s->stream));
+        CUDA_TRY(cudaEventRecord(sl.events[L], s->stream));
         a.shq = defer_shadows ? s->d_shq.p : nullptr;
         a.shq_cap = defer_shadows ? (uint32_t)std::min<size_t>(s->d_shq.n / 3, 0xFFFFFFFFull) : 0u;
         a.shq_count = defer_shadows ? s->d_shq_count.p + 2 * (size_t)L : nullptr;
@@ -1408,13 +1441,32 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         CUDA_TRY(sp_launch_level(s->d, a, s->material_set, L == 0 ? s->grid0 : s->grid_q, s->stream));
         if (defer_shadows) CUDA_TRY(sp_launch_shadow(s->d, a, s->device, s->stream));
     }
-    CUDA_TRY(cudaEventRecord(s->events[n_levels], s->stream));
-    std::vector<uint32_t> counts((size_t)(n_levels + 1) * ncl);
-    DeviceStats ds;
-    CUDA_TRY(cudaMemcpyAsync(counts.data(), s->counts.p, counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(&ds, s->d_stats.p, sizeof ds, cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaEventRecord(sl.events[n_levels], s->stream));
+    // the chunk's radiance moves from the scratch frame into the accumulation buffer — on the device, unless one of the
+    // chunk's queues overflowed (then the scratch frame is cleared instead and the host renders the chunk again)
+    sl.folded = fold_into != nullptr;
+    if (fold_into) CUDA_TRY(sp_launch_fold(fold_into, fold_from, fold_n, sl.d_stats.p, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(sl.h_counts, sl.counts.p, (size_t)(n_levels + 1) * ncl * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(sl.h_stats, sl.d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaEventRecord(sl.done, s->stream));
+    sl.busy = true; sl.job = job; sl.n_levels = n_levels; sl.warp = warp; sl.pretrace = pretrace; sl.defer_shadows = defer_shadows;
+    sl.split = split; sl.split_mode = split_mode; sl.split_launches = split_launches;
+    return 0;
+}
 
+// Wait for the chunk in slot k and fold its counters into `st`.  `overflow` comes back true when a queue was too small
+// for the chunk: nothing of it reached the frame and the caller renders it again in smaller pieces.
+static int finish_chunk(sp_scene* s, int k, sp_stats* st, bool& overflow) {
+    ChunkSlot& sl = s->slot[k];
+    overflow = false;
+    if (!sl.busy) return 0;
+    sl.busy = false;
+    CUDA_TRY(cudaEventSynchronize(sl.done));
+    const ChunkJob& job = sl.job;
+    const int n_levels = sl.n_levels, ncl = SP_COUNTS_PER_LEVEL, split_mode = sl.split_mode, split_launches = sl.split_launches;
+    const bool warp = sl.warp, pretrace = sl.pretrace, defer_shadows = sl.defer_shadows, split = sl.split;
+    const uint32_t* counts = sl.h_counts;
+    const DeviceStats& ds = *sl.h_stats;
     uint64_t peak_r = 0, peak_f = 0;
     for (int L = 1; L <= n_levels; ++L) {
         peak_r = std::max<uint64_t>(peak_r, counts[(size_t)L * ncl]);
@@ -1422,13 +1474,17 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
     }
     if (ds.overflow >> 16)
         return fail("internal consistency check failed in the wavefront kernels (SP_CHECKED build): code mask 0x%x", ds.overflow >> 16);
+    // the kernels raise the flag whenever a reservation does not fit; sp_fold_kernel decides by the same flag
+    const bool overflowed = (ds.overflow & 0xFFFFu) != 0u;
+    if (!overflowed && (peak_r > s->ray_cap || peak_f > s->fan_cap))
+        return fail("internal error: a wavefront queue holds more records than its capacity without the overflow flag");
     if (job.n_items > 0) {
         // a queue that overflowed stopped counting at the level that failed: later levels may have needed more
-        const double grow = (ds.overflow || peak_r > s->ray_cap || peak_f > s->fan_cap) ? 1.5 : 1.0;
+        const double grow = overflowed ? 1.5 : 1.0;
         s->use_ray = std::max(s->use_ray, grow * (double)peak_r / job.n_items);
         s->use_fan = std::max(s->use_fan, grow * (double)peak_f / job.n_items);
     }
-    if (ds.overflow || peak_r > s->ray_cap || peak_f > s->fan_cap) {
+    if (overflowed) {
         overflow = true;
         g_error = "wavefront queue overflow";
         char buf[256];
@@ -1439,6 +1495,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
     }
     if (st) {
         st->chunks += 1;
+        if (sl.folded) st->kernel_launches += 1;
         st->kernel_launches += split ? (uint64_t)split_launches + (split_mode == 2 ? 0u : (uint64_t)(n_levels - 1))
                                      : (uint64_t)n_levels * (pretrace ? (defer_shadows ? 3u : 2u) : 1u);
         st->level_kernel_launches += (uint64_t)n_levels;
@@ -1447,7 +1504,7 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
         st->peak_fan_records = std::max<uint64_t>(st->peak_fan_records, peak_f);
         for (int L = 0; L < n_levels; ++L) {
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, s->events[L], s->events[L + 1]);
+            cudaEventElapsedTime(&ms, sl.events[L], sl.events[L + 1]);
             st->level_ms[L] += ms;
             st->level_kernel_ms += ms;
         }
@@ -1470,6 +1527,16 @@ static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overf
                     100.0 * ds.phase_cycles[5] / tot);
     }
     return 0;
+}
+
+
+// One chunk, synchronously (caller rays, single passes): enqueue, wait.
+static int run_chunk(sp_scene* s, const ChunkJob& job, sp_stats* st, bool& overflow) {
+    overflow = false;
+    bool dummy = false;
+    if (int rc = finish_chunk(s, 0, nullptr, dummy)) return rc;          // (nothing is ever left in flight between calls)
+    if (int rc = enqueue_chunk(s, job, 0, nullptr, nullptr, 0u)) return rc;
+    return finish_chunk(s, 0, st, overflow);
 }
 
 static int begin_call(sp_scene* s, uint64_t seed, sp_stats* st, const char* what, uint64_t primaries) {
@@ -1533,46 +1600,71 @@ static int render_chunks(sp_scene* s, uint32_t first_pix, uint32_t n_region, con
     if (!ev0.e || !ev1.e) return fail("%s: cudaEventCreate failed", what);
     cudaEvent_t t0 = ev0.e, t1 = ev1.e;
     // Chunks add their radiance to a scratch frame that is folded into the accumulation buffer once the chunk is
-    // known to be complete, so that a chunk whose queues overflowed can be rendered again in smaller pieces.
-    if (s->scratch.n != s->accum.n) {
-        CUDA_TRY(s->scratch.alloc(s->accum.n));
-        CUDA_TRY(cudaMemsetAsync(s->scratch.p, 0, s->scratch.n * sizeof(float4), s->stream));
-    }
+    // known to be complete (on the device: sp_fold_kernel looks at the chunk's overflow flag), so that a chunk whose
+    // queues overflowed can be rendered again in smaller pieces.  Two chunks are in flight: chunk k + 1 is enqueued
+    // before the host waits for chunk k's counters, each with a scratch frame and counters of its own.
+    for (auto& sl : s->slot)
+        if (sl.scratch.n != s->accum.n) {
+            CUDA_TRY(sl.scratch.alloc(s->accum.n));
+            CUDA_TRY(cudaMemsetAsync(sl.scratch.p, 0, sl.scratch.n * sizeof(float4), s->stream));
+        }
     CUDA_TRY(cudaEventRecord(t0, s->stream));
     if (clear) CUDA_TRY(cudaMemsetAsync(s->accum.p, 0, s->accum.n * sizeof(float4), s->stream));
-    int rc = 0;
-    uint32_t sample = (uint32_t)sample_begin, pix = 0;          // pix: offset inside the region
-    while (n_region > 0 && sample < (uint32_t)sample_end && rc == 0) {
+    // what is left to render: (pixel range inside the region) x (sample range); a chunk is carved off the front
+    struct Todo { uint32_t pix0, npix, s0, s1; };
+    std::deque<Todo> todo;
+    if (n_region > 0 && sample_end > sample_begin) todo.push_back({0u, n_region, (uint32_t)sample_begin, (uint32_t)sample_end});
+    int rc = 0, next_slot = 0;
+    auto finish = [&](int k) -> int {
+        ChunkSlot& sl = s->slot[k];
+        if (!sl.busy) return 0;
+        bool overflow = false;
+        const uint32_t pix0 = sl.region_pix, npix = sl.job.n_pix, s0 = sl.job.sample_begin, ns = sl.region_ns, n_items = sl.job.n_items;
+        if (int r = finish_chunk(s, k, st, overflow)) return r;
+        if (overflow) {                                         // nothing of it was folded: again, in smaller pieces
+            todo.push_front({pix0, npix, s0, s0 + ns});
+            return shrink_after_overflow(s, n_items, st);
+        }
+        return 0;
+    };
+    while (rc == 0 && !todo.empty()) {
         const uint32_t P = pick_chunk(s, n_region);
+        ChunkSlot& sl = s->slot[next_slot];
         ChunkJob job{};
-        job.source = SP_SRC_CAMERA; job.run = SP_RUN_FULL; job.accum = s->scratch.p;
+        job.source = SP_SRC_CAMERA; job.run = SP_RUN_FULL; job.accum = sl.scratch.p;
         job.tiles = tiles; job.tile_shift = tile_shift; job.tiles_x = tiles_x;
-        uint32_t next_sample = sample, next_pix = pix;
-        if (pix == 0 && P >= n_region) {                         // whole region x several samples
-            const uint32_t ns = std::min<uint32_t>(P / n_region, (uint32_t)sample_end - sample);
-            job.pix_begin = first_pix; job.n_pix = n_region; job.sample_begin = sample; job.n_items = ns * n_region;
-            next_sample = sample + ns;
-        } else {                                                 // a slice of the region, one sample
-            const uint32_t n = std::min<uint32_t>(P, n_region - pix);
-            job.pix_begin = first_pix + pix; job.n_pix = n; job.sample_begin = sample; job.n_items = n;
-            next_pix = pix + n;
-            if (next_pix == n_region) { next_pix = 0; next_sample = sample + 1; }
+        Todo r = todo.front();
+        todo.pop_front();
+        uint32_t ns = 1;
+        if (P >= r.npix) {                                       // the whole pixel range x several samples
+            ns = std::max<uint32_t>(std::min<uint32_t>(P / r.npix, r.s1 - r.s0), 1u);
+            job.pix_begin = first_pix + r.pix0; job.n_pix = r.npix; job.sample_begin = r.s0; job.n_items = ns * r.npix;
+            if (r.s0 + ns < r.s1) todo.push_front({r.pix0, r.npix, r.s0 + ns, r.s1});
+        } else {                                                 // a slice of the pixel range, one sample
+            const uint32_t n = std::min<uint32_t>(P, r.npix);
+            job.pix_begin = first_pix + r.pix0; job.n_pix = n; job.sample_begin = r.s0; job.n_items = n;
+            if (r.s0 + 1 < r.s1) todo.push_front({r.pix0, r.npix, r.s0 + 1, r.s1});
+            if (n < r.npix) todo.push_front({r.pix0 + n, r.npix - n, r.s0, r.s0 + 1});
         }
         // the part of the frame the chunk can touch: its pixel range, or (tiles) anything
         float4* const acc_lo = tiles ? s->accum.p : s->accum.p + job.pix_begin;
-        float4* const scr_lo = tiles ? s->scratch.p : s->scratch.p + job.pix_begin;
+        float4* const scr_lo = tiles ? sl.scratch.p : sl.scratch.p + job.pix_begin;
         const uint32_t n_touch = tiles ? (uint32_t)s->accum.n : job.n_pix;
-        bool overflow = false;
-        rc = run_chunk(s, job, st, overflow);
+        // nothing is known about the scene's queue occupancy yet: this chunk is the probe, wait for it
+        const bool probe = s->use_ray == 0.0 && s->use_fan == 0.0;
+        rc = enqueue_chunk(s, job, next_slot, acc_lo, scr_lo, n_touch);
         if (rc) break;
-        if (overflow) {
-            CUDA_TRY(cudaMemsetAsync(scr_lo, 0, (size_t)n_touch * sizeof(float4), s->stream));
-            rc = shrink_after_overflow(s, job.n_items, st);
-            continue;
+        sl.region_pix = r.pix0; sl.region_ns = ns;
+        if (probe) rc = finish(next_slot);
+        else { rc = finish(next_slot ^ 1); next_slot ^= 1; }      // wait for the chunk before this one while this one runs
+        if (rc == 0 && todo.empty()) {                            // the last chunks: nothing left to overlap them with
+            rc = finish(0);
+            if (rc == 0) rc = finish(1);
         }
-        CUDA_TRY(sp_launch_fold(acc_lo, scr_lo, n_touch, s->stream));
-        if (st) st->kernel_launches += 1;
-        sample = next_sample; pix = next_pix;
+    }
+    for (int k = 0; k < 2; ++k) {                                // (an error above may have left a chunk in flight)
+        bool ov = false;
+        if (s->slot[k].busy) { const int r2 = finish_chunk(s, k, nullptr, ov); if (rc == 0) rc = r2; }
     }
     int rc2 = end_call(s, st, t0, t1);
     return rc ? rc : rc2;
@@ -1864,12 +1956,12 @@ int sp_render_group(sp_scene** scenes, int n, int spp, uint64_t seed, int shard_
                 cudaGetLastError();
             }
             if (!can) {                                          // no direct access: stage the peer's frame in the scratch frame
-                CUDA_TRY(cudaMemcpyPeerAsync(s0->scratch.p, s0->device, scenes[r]->accum.p, scenes[r]->device,
+                CUDA_TRY(cudaMemcpyPeerAsync(s0->slot[0].scratch.p, s0->device, scenes[r]->accum.p, scenes[r]->device,
                                              s0->accum.n * sizeof(float4), s0->stream));
-                src = s0->scratch.p;
+                src = s0->slot[0].scratch.p;
             }
             CUDA_TRY(sp_launch_add(s0->accum.p, src, (uint32_t)s0->accum.n, s0->stream));
-            if (!can) CUDA_TRY(cudaMemsetAsync(s0->scratch.p, 0, s0->accum.n * sizeof(float4), s0->stream));
+            if (!can) CUDA_TRY(cudaMemsetAsync(s0->slot[0].scratch.p, 0, s0->accum.n * sizeof(float4), s0->stream));
         }
         CUDA_TRY(cudaStreamSynchronize(s0->stream));
     }

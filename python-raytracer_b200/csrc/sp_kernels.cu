@@ -867,16 +867,21 @@ __global__ void __launch_bounds__(256) sp_resolve_kernel(const ResolveArgs a) {
     }
 }
 
-// A finished chunk's radiance moves from the scratch frame to the accumulation buffer (sp_api.cu: a chunk whose queues
-// overflowed is discarded and rendered again in smaller pieces, so it must not touch the frame before it is complete).
-__global__ void __launch_bounds__(256) sp_fold_kernel(float4* __restrict__ accum, float4* __restrict__ scratch, uint32_t n) {
+// A finished chunk's radiance moves from the scratch frame to the accumulation buffer — unless one of the chunk's queues
+// overflowed (stats->overflow, set by the level kernels): what the chunk added is then incomplete, the scratch frame is
+// cleared instead, and the host renders the chunk again in smaller pieces (sp_api.cu).  Deciding this on the device
+// lets the host enqueue the next chunk without waiting for this one's counters.
+__global__ void __launch_bounds__(256) sp_fold_kernel(float4* __restrict__ accum, float4* __restrict__ scratch, uint32_t n,
+                                                      const DeviceStats* __restrict__ stats) {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= n) return;
     const float4 s = scratch[i];
     if (s.x == 0.f && s.y == 0.f && s.z == 0.f) return;
-    float4 a = accum[i];
-    a.x += s.x; a.y += s.y; a.z += s.z;
-    accum[i] = a;
+    if (!(stats->overflow & 0xFFFFu)) {
+        float4 a = accum[i];
+        a.x += s.x; a.y += s.y; a.z += s.z;
+        accum[i] = a;
+    }
     scratch[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
@@ -1057,9 +1062,9 @@ cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st) {
+cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, const DeviceStats* stats, cudaStream_t st) {
     if (n_pix == 0) return cudaSuccess;
-    sp_fold_kernel<<<(n_pix + 255u) / 256u, 256, 0, st>>>(accum, scratch, n_pix);
+    sp_fold_kernel<<<(n_pix + 255u) / 256u, 256, 0, st>>>(accum, scratch, n_pix, stats);
     return cudaGetLastError();
 }
 

@@ -70,7 +70,8 @@ cudaError_t sp_launch_trace(const DScene& sc, const LevelArgs& a, uint32_t mater
 bool sp_can_split(const DScene& sc, uint32_t material_set);
 cudaError_t sp_launch_split_level(const DScene& sc, const LevelArgs& a, uint32_t kind_mask, int device, cudaStream_t st, int* launched);
 cudaError_t sp_launch_resolve(const ResolveArgs& a, cudaStream_t st);
-cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, cudaStream_t st);   // accum += scratch; scratch = 0
+// accum += scratch unless the chunk's stats say a queue overflowed; scratch = 0 either way
+cudaError_t sp_launch_fold(float4* accum, float4* scratch, uint32_t n_pix, const DeviceStats* stats, cudaStream_t st);
 cudaError_t sp_launch_add(float4* accum, const float4* other, uint32_t n_pix, cudaStream_t st);   // accum.xyz += other.xyz (other may be peer memory)
 cudaError_t sp_upload_decode_tables(const float* plain256, const float* linear256);
 // sky-box blur of a cross-layout cube map of packed texels (sp_imaging.cu); tmp0 / tmp1: two (3 * (H / 3))^2 canvases
