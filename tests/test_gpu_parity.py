@@ -198,6 +198,25 @@ def test_queue_overflow_is_reported():
     nat.close()
 
 
+def test_overflowing_chunks_are_rendered_again_in_smaller_pieces():
+    """A chunk whose queues overflow never reaches the frame (sp_fold_kernel checks the chunk's overflow flag on the
+    device) and is re-queued at half the size while the next chunk is already in flight: the frame and the ray counts
+    equal those of a render with ample queues, and the retries are reported."""
+    import scenes
+    import sightpy
+    from sightpy.backend import NativeScene
+    flat = flatten_scene(scenes.cornell(sightpy, width=128, height=96))
+    nat = NativeScene(flat)
+    _, want, st_w = nat.render(5, seed=13)
+    assert st_w["chunk_retries"] == 0
+    nat.set_option("fan_queue_capacity", 80000)          # one sample of the frame needs ~230 000 fan records per level
+    _, got, st_g = nat.render(5, seed=13)
+    nat.close()
+    assert st_g["chunk_retries"] > 0 and st_g["chunks"] > st_w["chunks"]
+    assert st_g["rays_per_depth"] == st_w["rays_per_depth"]
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6)
+
+
 def test_cornell_frame_equals_oracle_frame_pixel_by_pixel():
     """A whole sp_render frame (camera -> bounces -> accumulate -> average) against the oracle fed
     with the same primary rays and the same (pixel, sample) Philox keys: per-pixel parity of the
