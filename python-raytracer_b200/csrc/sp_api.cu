@@ -282,6 +282,11 @@ struct sp_scene {
 
     ~sp_scene() {
         release_device(); release_textures();
+        for (auto& sl : slot) {
+            if (sl.h_counts) cudaFreeHost(sl.h_counts);
+            if (sl.h_stats) cudaFreeHost(sl.h_stats);
+            sl.h_counts = nullptr; sl.h_stats = nullptr;
+        }
         pool_trim(kPoolIdleLimit);           // what a destroyed scene leaves idle beyond the limit goes back to the driver
     }
     void release_textures() {                    // a scene holds one reference per shared texture for its whole life
@@ -306,9 +311,7 @@ struct sp_scene {
             for (auto e : sl.events) g_ctx[device].event_pool.push_back(e);
             sl.events.clear();
             if (sl.done) { g_ctx[device].event_pool.push_back(sl.done); sl.done = nullptr; }
-            if (sl.h_counts) { cudaFreeHost(sl.h_counts); sl.h_counts = nullptr; }
-            if (sl.h_stats) { cudaFreeHost(sl.h_stats); sl.h_stats = nullptr; }
-            sl.busy = false;
+            sl.busy = false;                 // (the pinned host copies are fixed-size: kept until the scene is destroyed)
         }
         if (own_stream) { cudaStreamSynchronize(own_stream); g_ctx[device].stream_pool.push_back(own_stream); }
         own_stream = nullptr;

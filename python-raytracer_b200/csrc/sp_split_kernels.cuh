@@ -117,7 +117,7 @@ sp_hit_kernel(const __grid_constant__ DScene sc, const __grid_constant__ LevelAr
         int bin = SPS_KINDS;                                 // nothing to shade
         if (active) {
             traced += 1u;
-            if ((FEAT & SP_F_LEVEL0) && a.level == 0) {
+            if ((FEAT & SP_F_LEVEL0) && a.level == 0 && (a.out_hit || a.out_t)) {                    // per-ray outputs (sp_trace)
                 const size_t oi = (a.source == SP_SRC_USER) ? (size_t)a.user_base + (size_t)item : (size_t)item;
                 if (a.out_hit) a.out_hit[oi] = hit.id;
                 if (a.out_t) a.out_t[oi] = hit.t;
